@@ -1,0 +1,1341 @@
+/*
+ * dnagpu.cu -- the C ABI of libdnagpu (include/dnagpu.h) over the sm_100a
+ * kernels in kernels.cuh.  Host-side logic only: argument checks that mirror
+ * the reference's ereport(ERROR) sites, device memory, launch geometry.
+ *
+ * There is no CPU implementation of any operation in this file: when no
+ * sm_100 device is usable dnagpu_create fails and nothing else can run.
+ */
+#include "../../include/dnagpu.h"
+
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <new>
+#include <string>
+#include <vector>
+
+#include "kernels.cuh"
+
+using namespace dnagpu;
+
+/* ---- objects ----------------------------------------------------------------- */
+struct ProfRec {
+    std::string name;
+    cudaEvent_t e0, e1;
+};
+
+struct dnagpu_ctx {
+    int device = 0;
+    int sm_count = 0;
+    cudaStream_t stream = nullptr;
+    bool own_stream = true;
+    unsigned long long *d_ctr = nullptr; /* C_COUNT + kMaxParts*2 u64 device counters */
+    unsigned long long *h_ctr = nullptr; /* pinned mirror */
+    bool profiling = false;
+    std::vector<ProfRec> prof;
+    char err[512] = {0};
+};
+
+struct dnagpu_seq {
+    dnagpu_ctx *ctx = nullptr;
+    int layout = kSingle;
+    uint64_t *d_words = nullptr;
+    bool own_words = true;
+    uint64_t n_words_alloc = 0; /* incl. pad */
+    uint64_t n_words = 0;       /* payload words (download) */
+    uint64_t n_seqs = 1;
+    uint64_t bases = 0;  /* per sequence (single / fixed) */
+    uint64_t stride = 0; /* words per sequence (fixed) */
+    uint64_t start_limit = 0;
+    /* ragged */
+    std::vector<uint64_t> h_n_bases;
+    uint64_t *d_word_off = nullptr, *d_n_bases = nullptr;
+    int cached_k = 0;
+    uint64_t *d_row_off = nullptr, *d_item_off = nullptr;
+    uint64_t cached_rows = 0, cached_items = 0;
+};
+
+struct dnagpu_table {
+    dnagpu_ctx *ctx = nullptr;
+    int k = 0;
+    uint64_t rows = 0;
+    uint64_t *d_kmers = nullptr, *d_counts = nullptr;
+};
+
+static thread_local char g_err[512] = "";
+
+static int fail(dnagpu_ctx *ctx, int code, const char *fmt, ...)
+{
+    char buf[512];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof buf, fmt, ap);
+    va_end(ap);
+    snprintf(g_err, sizeof g_err, "%s", buf);
+    if (ctx) snprintf(ctx->err, sizeof ctx->err, "%s", buf);
+    return code;
+}
+
+#define CU(ctx, call)                                                                        \
+    do {                                                                                     \
+        cudaError_t e_ = (call);                                                             \
+        if (e_ != cudaSuccess)                                                               \
+            return fail(ctx, e_ == cudaErrorMemoryAllocation ? DNAGPU_ENOMEM : DNAGPU_ECUDA, \
+                        "%s: %s (%s:%d)", #call, cudaGetErrorString(e_), __FILE__, __LINE__); \
+    } while (0)
+
+/* every launch goes through here so that profiling sees it */
+template <class F>
+static int launch(dnagpu_ctx *ctx, const char *name, F &&f)
+{
+    if (ctx->profiling) {
+        ProfRec r;
+        r.name = name;
+        CU(ctx, cudaEventCreate(&r.e0));
+        CU(ctx, cudaEventCreate(&r.e1));
+        CU(ctx, cudaEventRecord(r.e0, ctx->stream));
+        f();
+        CU(ctx, cudaEventRecord(r.e1, ctx->stream));
+        ctx->prof.push_back(r);
+    } else {
+        f();
+    }
+    CU(ctx, cudaGetLastError());
+    return DNAGPU_OK;
+}
+#define TRY(x)                         \
+    do {                               \
+        int rc_ = (x);                 \
+        if (rc_ != DNAGPU_OK) return rc_; \
+    } while (0)
+
+static int dalloc(dnagpu_ctx *ctx, void **p, uint64_t bytes)
+{
+    *p = nullptr;
+    if (bytes == 0) bytes = 16;
+    cudaError_t e = cudaMallocAsync(p, bytes, ctx->stream);
+    if (e != cudaSuccess) {
+        cudaGetLastError();
+        return fail(ctx, DNAGPU_ENOMEM, "device allocation of %llu bytes failed: %s",
+                    (unsigned long long)bytes, cudaGetErrorString(e));
+    }
+    return DNAGPU_OK;
+}
+static void dfree(dnagpu_ctx *ctx, void *p)
+{
+    if (p) cudaFreeAsync(p, ctx->stream);
+}
+/* scope guard for scratch buffers */
+struct Scratch {
+    dnagpu_ctx *ctx;
+    std::vector<void *> ptrs;
+    explicit Scratch(dnagpu_ctx *c) : ctx(c) {}
+    ~Scratch()
+    {
+        for (void *p : ptrs) dfree(ctx, p);
+    }
+    int get(void **p, uint64_t bytes)
+    {
+        int rc = dalloc(ctx, p, bytes);
+        if (rc == DNAGPU_OK) ptrs.push_back(*p);
+        return rc;
+    }
+    void release(void *p) { ptrs.erase(std::remove(ptrs.begin(), ptrs.end(), p), ptrs.end()); }
+};
+
+static inline uint64_t rows_of(uint64_t n_bases, int k)
+{
+    return n_bases >= (uint64_t)k ? n_bases - (uint64_t)k + 1 : 0; /* Q2 (dna.c:781) */
+}
+static inline uint64_t words_of(uint64_t n_bases) { return (n_bases + 31) / 32; }
+static inline uint64_t kmer_mask(int k) { return k >= 32 ? ~0ull : ((1ull << (2 * k)) - 1); }
+static inline unsigned grid_for(uint64_t n, uint64_t per_cta)
+{
+    uint64_t g = (n + per_cta - 1) / per_cta;
+    return (unsigned)std::max<uint64_t>(1, std::min<uint64_t>(g, 0x7fffffffull));
+}
+
+/* ---- context ------------------------------------------------------------------ */
+extern "C" int dnagpu_version(void) { return DNAGPU_VERSION; }
+
+extern "C" const char *dnagpu_strerror(int code)
+{
+    switch (code) {
+    case DNAGPU_OK: return "ok";
+    case DNAGPU_EINVAL_K: return "Invalid k value: must be between 1 and 32";        /* dna.c:773 */
+    case DNAGPU_EPREFIX_LEN: return "Prefix length cannot exceed kmer length";       /* dna.c:855 */
+    case DNAGPU_EQKMER_LEN: return "Qkmer pattern and kmer lengths do not match";    /* dna.c:1107 */
+    case DNAGPU_EQKMER_CHAR: return "Invalid character in qkmer pattern";            /* dna.c:894 */
+    case DNAGPU_EQKMER_EMPTY: return "qkmer pattern cannot be empty";                /* dna.c:878 */
+    case DNAGPU_EQKMER_TOOLONG: return "Qkmer pattern length cannot exceed 32 characters"; /* dna.c:884 */
+    case DNAGPU_EPREFIX_BITS: return "prefix kmer has bits set beyond its length";
+    case DNAGPU_EARG: return "invalid argument";
+    case DNAGPU_ECAPACITY: return "output buffer too small";
+    case DNAGPU_ENOMEM: return "out of device or pinned host memory";
+    case DNAGPU_ECUDA: return "CUDA error";
+    case DNAGPU_ENODEVICE: return "no usable sm_100 GPU";
+    case DNAGPU_EINTERNAL: return "internal error";
+    }
+    return "unknown error";
+}
+
+extern "C" int dnagpu_create(dnagpu_ctx **out, int device)
+{
+    if (!out) return fail(nullptr, DNAGPU_EARG, "dnagpu_create: out is NULL");
+    *out = nullptr;
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess || n == 0) {
+        cudaGetLastError();
+        return fail(nullptr, DNAGPU_ENODEVICE, "no CUDA device: %s (libdnagpu has no CPU path)",
+                    e == cudaSuccess ? "device count is 0" : cudaGetErrorString(e));
+    }
+    if (device < 0 || device >= n)
+        return fail(nullptr, DNAGPU_EARG, "device %d out of range (0..%d)", device, n - 1);
+    cudaDeviceProp prop;
+    CU(nullptr, cudaGetDeviceProperties(&prop, device));
+    if (prop.major != 10)
+        return fail(nullptr, DNAGPU_ENODEVICE,
+                    "device %d (%s) is sm_%d%d; libdnagpu is built for sm_100a only", device,
+                    prop.name, prop.major, prop.minor);
+    dnagpu_ctx *ctx = new (std::nothrow) dnagpu_ctx();
+    if (!ctx) return fail(nullptr, DNAGPU_ENOMEM, "out of host memory");
+    ctx->device = device;
+    ctx->sm_count = prop.multiProcessorCount;
+    CU(nullptr, cudaSetDevice(device));
+    CU(nullptr, cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
+    /* keep freed scratch in the stream-ordered pool: repeated queries reuse it */
+    cudaMemPool_t pool;
+    if (cudaDeviceGetDefaultMemPool(&pool, device) == cudaSuccess) {
+        uint64_t thr = UINT64_MAX;
+        cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &thr);
+    }
+    const size_t ctr_bytes = (C_COUNT + 2 * kMaxParts) * sizeof(unsigned long long);
+    CU(nullptr, cudaMalloc((void **)&ctx->d_ctr, ctr_bytes));
+    CU(nullptr, cudaMallocHost((void **)&ctx->h_ctr, ctr_bytes));
+    /* opt in to the 64 KB staging tiles */
+    const int smem = kThreads * 32 * (int)sizeof(uint64_t);
+#define SMEM_ATTR(kern) cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem)
+    SMEM_ATTR(k_filter_write<kSingle>);
+    SMEM_ATTR(k_filter_write<kFixed>);
+    SMEM_ATTR(k_filter_write<kRagged>);
+    SMEM_ATTR((k_partition_write<kSingle, false>));
+    SMEM_ATTR((k_partition_write<kSingle, true>));
+    SMEM_ATTR((k_partition_write<kFixed, false>));
+    SMEM_ATTR((k_partition_write<kFixed, true>));
+    SMEM_ATTR((k_partition_write<kRagged, false>));
+    SMEM_ATTR((k_partition_write<kRagged, true>));
+    SMEM_ATTR((k_count_dense_smem<kSingle, false, uint32_t>));
+    SMEM_ATTR((k_count_dense_smem<kSingle, true, uint32_t>));
+    SMEM_ATTR((k_count_dense_smem<kFixed, false, uint32_t>));
+    SMEM_ATTR((k_count_dense_smem<kFixed, true, uint32_t>));
+    SMEM_ATTR((k_count_dense_smem<kRagged, false, uint32_t>));
+    SMEM_ATTR((k_count_dense_smem<kRagged, true, uint32_t>));
+    SMEM_ATTR((k_count_dense_smem<kSingle, false, unsigned long long>));
+    SMEM_ATTR((k_count_dense_smem<kSingle, true, unsigned long long>));
+    SMEM_ATTR((k_count_dense_smem<kFixed, false, unsigned long long>));
+    SMEM_ATTR((k_count_dense_smem<kFixed, true, unsigned long long>));
+    SMEM_ATTR((k_count_dense_smem<kRagged, false, unsigned long long>));
+    SMEM_ATTR((k_count_dense_smem<kRagged, true, unsigned long long>));
+#undef SMEM_ATTR
+    CU(nullptr, cudaGetLastError());
+    *out = ctx;
+    return DNAGPU_OK;
+}
+
+extern "C" void dnagpu_destroy(dnagpu_ctx *ctx)
+{
+    if (!ctx) return;
+    cudaSetDevice(ctx->device);
+    cudaStreamSynchronize(ctx->stream);
+    for (auto &r : ctx->prof) {
+        cudaEventDestroy(r.e0);
+        cudaEventDestroy(r.e1);
+    }
+    if (ctx->d_ctr) cudaFree(ctx->d_ctr);
+    if (ctx->h_ctr) cudaFreeHost(ctx->h_ctr);
+    if (ctx->own_stream && ctx->stream) cudaStreamDestroy(ctx->stream);
+    delete ctx;
+}
+
+extern "C" const char *dnagpu_last_error(const dnagpu_ctx *ctx) { return ctx ? ctx->err : g_err; }
+
+extern "C" int dnagpu_set_stream(dnagpu_ctx *ctx, void *cuda_stream)
+{
+    if (!ctx) return fail(nullptr, DNAGPU_EARG, "ctx is NULL");
+    CU(ctx, cudaStreamSynchronize(ctx->stream));
+    if (ctx->own_stream && ctx->stream) cudaStreamDestroy(ctx->stream);
+    if (cuda_stream) {
+        ctx->stream = (cudaStream_t)cuda_stream;
+        ctx->own_stream = false;
+    } else {
+        CU(ctx, cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
+        ctx->own_stream = true;
+    }
+    return DNAGPU_OK;
+}
+
+extern "C" int dnagpu_synchronize(dnagpu_ctx *ctx)
+{
+    if (!ctx) return fail(nullptr, DNAGPU_EARG, "ctx is NULL");
+    CU(ctx, cudaStreamSynchronize(ctx->stream));
+    return DNAGPU_OK;
+}
+
+extern "C" int dnagpu_device_info(dnagpu_ctx *ctx, char *name, size_t cap, int *sm_count,
+                                  uint64_t *hbm_free, uint64_t *hbm_total)
+{
+    if (!ctx) return fail(nullptr, DNAGPU_EARG, "ctx is NULL");
+    cudaDeviceProp prop;
+    CU(ctx, cudaGetDeviceProperties(&prop, ctx->device));
+    if (name && cap) snprintf(name, cap, "%s", prop.name);
+    if (sm_count) *sm_count = prop.multiProcessorCount;
+    size_t f = 0, t = 0;
+    CU(ctx, cudaSetDevice(ctx->device));
+    CU(ctx, cudaMemGetInfo(&f, &t));
+    if (hbm_free) *hbm_free = f;
+    if (hbm_total) *hbm_total = t;
+    return DNAGPU_OK;
+}
+
+extern "C" int dnagpu_host_alloc(dnagpu_ctx *ctx, void **out, uint64_t bytes)
+{
+    if (!ctx || !out) return fail(ctx, DNAGPU_EARG, "dnagpu_host_alloc: NULL argument");
+    *out = nullptr;
+    cudaError_t e = cudaMallocHost(out, bytes ? bytes : 16);
+    if (e != cudaSuccess) {
+        cudaGetLastError();
+        return fail(ctx, DNAGPU_ENOMEM, "pinned allocation of %llu bytes failed: %s",
+                    (unsigned long long)bytes, cudaGetErrorString(e));
+    }
+    return DNAGPU_OK;
+}
+extern "C" void dnagpu_host_free(dnagpu_ctx *ctx, void *p)
+{
+    (void)ctx;
+    if (p) cudaFreeHost(p);
+}
+
+/* ---- sequences ------------------------------------------------------------------ */
+static int seq_new(dnagpu_ctx *ctx, dnagpu_seq **out, dnagpu_seq **s)
+{
+    if (!ctx || !out) return fail(ctx, DNAGPU_EARG, "NULL ctx or output pointer");
+    *out = nullptr;
+    *s = new (std::nothrow) dnagpu_seq();
+    if (!*s) return fail(ctx, DNAGPU_ENOMEM, "out of host memory");
+    (*s)->ctx = ctx;
+    CU(ctx, cudaSetDevice(ctx->device));
+    return DNAGPU_OK;
+}
+
+/* allocate payload + zeroed pad (>= 1 word, total even => 16-byte granules) */
+static int seq_alloc_words(dnagpu_seq *s, uint64_t payload_words)
+{
+    dnagpu_ctx *ctx = s->ctx;
+    s->n_words = payload_words;
+    s->n_words_alloc = (payload_words + 2 + 1) & ~1ull;
+    TRY(dalloc(ctx, (void **)&s->d_words, s->n_words_alloc * 8));
+    CU(ctx, cudaMemsetAsync(s->d_words + payload_words, 0, (s->n_words_alloc - payload_words) * 8,
+                            ctx->stream));
+    return DNAGPU_OK;
+}
+
+extern "C" void dnagpu_seq_free(dnagpu_seq *s)
+{
+    if (!s) return;
+    dnagpu_ctx *ctx = s->ctx;
+    cudaSetDevice(ctx->device);
+    if (s->own_words) dfree(ctx, s->d_words);
+    dfree(ctx, s->d_word_off);
+    dfree(ctx, s->d_n_bases);
+    dfree(ctx, s->d_row_off);
+    dfree(ctx, s->d_item_off);
+    delete s;
+}
+
+extern "C" int dnagpu_seq_upload(dnagpu_ctx *ctx, const uint64_t *words, uint64_t n_bases,
+                                 dnagpu_seq **out)
+{
+    dnagpu_seq *s;
+    TRY(seq_new(ctx, out, &s));
+    if (!words && n_bases) {
+        delete s;
+        return fail(ctx, DNAGPU_EARG, "dnagpu_seq_upload: words is NULL");
+    }
+    s->layout = kSingle;
+    s->bases = n_bases;
+    int rc = seq_alloc_words(s, words_of(n_bases));
+    if (rc == DNAGPU_OK && s->n_words) {
+        cudaError_t e = cudaMemcpyAsync(s->d_words, words, s->n_words * 8, cudaMemcpyHostToDevice,
+                                        ctx->stream);
+        if (e != cudaSuccess) rc = fail(ctx, DNAGPU_ECUDA, "H2D copy: %s", cudaGetErrorString(e));
+    }
+    if (rc != DNAGPU_OK) {
+        dnagpu_seq_free(s);
+        return rc;
+    }
+    *out = s;
+    return DNAGPU_OK;
+}
+
+extern "C" int dnagpu_seq_upload_reads(dnagpu_ctx *ctx, const uint64_t *words, uint64_t n_reads,
+                                       uint32_t bases_per_read, uint32_t stride_words,
+                                       dnagpu_seq **out)
+{
+    dnagpu_seq *s;
+    TRY(seq_new(ctx, out, &s));
+    if ((!words && n_reads) || stride_words < words_of(bases_per_read)) {
+        delete s;
+        return fail(ctx, DNAGPU_EARG, "dnagpu_seq_upload_reads: NULL words or stride < words per read");
+    }
+    s->layout = kFixed;
+    s->n_seqs = n_reads;
+    s->bases = bases_per_read;
+    s->stride = stride_words;
+    int rc = seq_alloc_words(s, n_reads * stride_words);
+    if (rc == DNAGPU_OK && s->n_words) {
+        cudaError_t e = cudaMemcpyAsync(s->d_words, words, s->n_words * 8, cudaMemcpyHostToDevice,
+                                        ctx->stream);
+        if (e != cudaSuccess) rc = fail(ctx, DNAGPU_ECUDA, "H2D copy: %s", cudaGetErrorString(e));
+    }
+    if (rc != DNAGPU_OK) {
+        dnagpu_seq_free(s);
+        return rc;
+    }
+    *out = s;
+    return DNAGPU_OK;
+}
+
+extern "C" int dnagpu_seq_upload_ragged(dnagpu_ctx *ctx, const uint64_t *words,
+                                        const uint64_t *word_offsets, const uint64_t *n_bases,
+                                        uint64_t n_seqs, dnagpu_seq **out)
+{
+    dnagpu_seq *s;
+    TRY(seq_new(ctx, out, &s));
+    if (n_seqs && (!words || !word_offsets || !n_bases)) {
+        delete s;
+        return fail(ctx, DNAGPU_EARG, "dnagpu_seq_upload_ragged: NULL argument");
+    }
+    s->layout = kRagged;
+    s->n_seqs = n_seqs;
+    s->h_n_bases.assign(n_bases, n_bases + n_seqs);
+    uint64_t total_words = 0;
+    for (uint64_t i = 0; i < n_seqs; ++i)
+        total_words = std::max(total_words, word_offsets[i] + words_of(n_bases[i]));
+    int rc = seq_alloc_words(s, total_words);
+    if (rc == DNAGPU_OK) rc = dalloc(ctx, (void **)&s->d_word_off, (n_seqs + 1) * 8);
+    if (rc == DNAGPU_OK) rc = dalloc(ctx, (void **)&s->d_n_bases, (n_seqs + 1) * 8);
+    if (rc == DNAGPU_OK && n_seqs) {
+        cudaError_t e = cudaSuccess;
+        if (total_words)
+            e = cudaMemcpyAsync(s->d_words, words, total_words * 8, cudaMemcpyHostToDevice, ctx->stream);
+        if (e == cudaSuccess)
+            e = cudaMemcpyAsync(s->d_word_off, word_offsets, n_seqs * 8, cudaMemcpyHostToDevice, ctx->stream);
+        if (e == cudaSuccess)
+            e = cudaMemcpyAsync(s->d_n_bases, n_bases, n_seqs * 8, cudaMemcpyHostToDevice, ctx->stream);
+        /* the offsets/lengths arrays are the caller's: finish before returning */
+        if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+        if (e != cudaSuccess) rc = fail(ctx, DNAGPU_ECUDA, "H2D copy: %s", cudaGetErrorString(e));
+    }
+    if (rc != DNAGPU_OK) {
+        dnagpu_seq_free(s);
+        return rc;
+    }
+    *out = s;
+    return DNAGPU_OK;
+}
+
+extern "C" int dnagpu_seq_synth_range(dnagpu_ctx *ctx, uint64_t n_bases_total, uint64_t seed,
+                                      uint32_t repeat_every, uint64_t first_base,
+                                      uint64_t n_starts, int overlap_k, dnagpu_seq **out)
+{
+    dnagpu_seq *s;
+    if (overlap_k < 1 || overlap_k > DNAGPU_MAX_K)
+        return fail(ctx, DNAGPU_EINVAL_K, "%s", dnagpu_strerror(DNAGPU_EINVAL_K));
+    if ((first_base & 31) || first_base > n_bases_total)
+        return fail(ctx, DNAGPU_EARG, "first_base must be a multiple of 32 inside the sequence");
+    TRY(seq_new(ctx, out, &s));
+    uint64_t local = std::min(n_bases_total - first_base, n_starts + (uint64_t)overlap_k - 1);
+    s->layout = kSingle;
+    s->bases = local;
+    s->start_limit = n_starts;
+    int rc = seq_alloc_words(s, words_of(local));
+    if (rc == DNAGPU_OK && s->n_words)
+        rc = launch(ctx, "synth_seq", [&] {
+            k_synth_seq<<<grid_for(s->n_words, kThreads), kThreads, 0, ctx->stream>>>(
+                seed, repeat_every, n_bases_total, first_base / 32, s->n_words, s->d_words);
+        });
+    if (rc != DNAGPU_OK) {
+        dnagpu_seq_free(s);
+        return rc;
+    }
+    *out = s;
+    return DNAGPU_OK;
+}
+
+extern "C" int dnagpu_seq_synth(dnagpu_ctx *ctx, uint64_t n_bases, uint64_t seed,
+                                uint32_t repeat_every, dnagpu_seq **out)
+{
+    int rc = dnagpu_seq_synth_range(ctx, n_bases, seed, repeat_every, 0, n_bases, 1, out);
+    if (rc == DNAGPU_OK) (*out)->start_limit = 0;
+    return rc;
+}
+
+extern "C" int dnagpu_seq_synth_reads(dnagpu_ctx *ctx, uint64_t first_read, uint64_t n_reads,
+                                      uint32_t bases_per_read, uint32_t stride_words,
+                                      uint64_t seed, uint32_t repeat_every, dnagpu_seq **out)
+{
+    dnagpu_seq *s;
+    if (stride_words < words_of(bases_per_read))
+        return fail(ctx, DNAGPU_EARG, "stride_words < words per read");
+    TRY(seq_new(ctx, out, &s));
+    s->layout = kFixed;
+    s->n_seqs = n_reads;
+    s->bases = bases_per_read;
+    s->stride = stride_words;
+    int rc = seq_alloc_words(s, n_reads * stride_words);
+    if (rc == DNAGPU_OK && s->n_words)
+        rc = launch(ctx, "synth_reads", [&] {
+            k_synth_reads<<<grid_for(s->n_words, kThreads), kThreads, 0, ctx->stream>>>(
+                seed, repeat_every, first_read, n_reads, bases_per_read, stride_words, s->d_words);
+        });
+    if (rc != DNAGPU_OK) {
+        dnagpu_seq_free(s);
+        return rc;
+    }
+    *out = s;
+    return DNAGPU_OK;
+}
+
+extern "C" int dnagpu_seq_wrap(dnagpu_ctx *ctx, const void *d_words, uint64_t n_bases,
+                               uint64_t n_words_alloc, dnagpu_seq **out)
+{
+    dnagpu_seq *s;
+    if (!d_words || ((uintptr_t)d_words & 15) || n_words_alloc < words_of(n_bases) + 1)
+        return fail(ctx, DNAGPU_EARG,
+                    "dnagpu_seq_wrap: need a 16-byte aligned device pointer with >= 1 pad word");
+    TRY(seq_new(ctx, out, &s));
+    s->layout = kSingle;
+    s->bases = n_bases;
+    s->d_words = (uint64_t *)d_words;
+    s->own_words = false;
+    s->n_words = words_of(n_bases);
+    s->n_words_alloc = n_words_alloc;
+    *out = s;
+    return DNAGPU_OK;
+}
+
+extern "C" int dnagpu_seq_wrap_reads(dnagpu_ctx *ctx, const void *d_words, uint64_t n_reads,
+                                     uint32_t bases_per_read, uint32_t stride_words,
+                                     uint64_t n_words_alloc, dnagpu_seq **out)
+{
+    dnagpu_seq *s;
+    if (!d_words || ((uintptr_t)d_words & 15) || stride_words < words_of(bases_per_read) ||
+        n_words_alloc < n_reads * stride_words + 1)
+        return fail(ctx, DNAGPU_EARG,
+                    "dnagpu_seq_wrap_reads: need a 16-byte aligned device pointer with >= 1 pad word");
+    TRY(seq_new(ctx, out, &s));
+    s->layout = kFixed;
+    s->n_seqs = n_reads;
+    s->bases = bases_per_read;
+    s->stride = stride_words;
+    s->d_words = (uint64_t *)d_words;
+    s->own_words = false;
+    s->n_words = n_reads * stride_words;
+    s->n_words_alloc = n_words_alloc;
+    *out = s;
+    return DNAGPU_OK;
+}
+
+extern "C" int dnagpu_seq_set_start_limit(dnagpu_seq *seq, uint64_t n_starts)
+{
+    if (!seq || seq->layout != kSingle)
+        return fail(seq ? seq->ctx : nullptr, DNAGPU_EARG, "start limit applies to a single sequence");
+    seq->start_limit = n_starts;
+    return DNAGPU_OK;
+}
+
+extern "C" int dnagpu_seq_download(dnagpu_ctx *ctx, const dnagpu_seq *seq, uint64_t *words,
+                                   uint64_t n_words)
+{
+    if (!ctx || !seq || (!words && n_words)) return fail(ctx, DNAGPU_EARG, "NULL argument");
+    if (n_words > seq->n_words) return fail(ctx, DNAGPU_EARG, "n_words exceeds the batch");
+    CU(ctx, cudaSetDevice(ctx->device));
+    if (n_words) CU(ctx, cudaMemcpyAsync(words, seq->d_words, n_words * 8, cudaMemcpyDeviceToHost, ctx->stream));
+    CU(ctx, cudaStreamSynchronize(ctx->stream));
+    return DNAGPU_OK;
+}
+
+extern "C" uint64_t dnagpu_seq_words(const dnagpu_seq *seq) { return seq ? seq->n_words : 0; }
+
+extern "C" const void *dnagpu_seq_device_words(const dnagpu_seq *seq)
+{
+    return seq ? seq->d_words : nullptr;
+}
+
+extern "C" uint64_t dnagpu_seq_kmer_count(const dnagpu_seq *seq, int k)
+{
+    if (!seq || k < 1 || k > DNAGPU_MAX_K) return 0;
+    if (seq->layout == kSingle) {
+        uint64_t r = rows_of(seq->bases, k);
+        return seq->start_limit ? std::min(r, seq->start_limit) : r;
+    }
+    if (seq->layout == kFixed) return seq->n_seqs * rows_of(seq->bases, k);
+    uint64_t t = 0;
+    for (uint64_t n : seq->h_n_bases) t += rows_of(n, k);
+    return t;
+}
+
+/* the device view of a sequence for one k (ragged: builds and caches the prefix sums) */
+static int make_view(dnagpu_ctx *ctx, const dnagpu_seq *cseq, int k, SeqView *v)
+{
+    dnagpu_seq *seq = const_cast<dnagpu_seq *>(cseq);
+    memset(v, 0, sizeof *v);
+    v->words = seq->d_words;
+    v->n_seqs = seq->n_seqs;
+    v->stride = seq->stride;
+    if (seq->layout != kRagged) {
+        uint64_t r = rows_of(seq->bases, k);
+        if (seq->layout == kSingle && seq->start_limit) r = std::min(r, seq->start_limit);
+        v->rows_per_seq = r;
+        v->items_per_seq = (r + 31) / 32;
+        v->n_rows = r * seq->n_seqs;
+        v->n_items = v->items_per_seq * seq->n_seqs;
+        return DNAGPU_OK;
+    }
+    if (seq->cached_k != k) {
+        const uint64_t n = seq->n_seqs;
+        if (!seq->d_row_off) TRY(dalloc(ctx, (void **)&seq->d_row_off, (n + 1) * 8));
+        if (!seq->d_item_off) TRY(dalloc(ctx, (void **)&seq->d_item_off, (n + 1) * 8));
+        Scratch sc(ctx);
+        uint64_t *rows, *items;
+        TRY(sc.get((void **)&rows, (n + 1) * 8));
+        TRY(sc.get((void **)&items, (n + 1) * 8));
+        if (n)
+            TRY(launch(ctx, "ragged_rows", [&] {
+                k_ragged_rows<<<grid_for(n, kThreads), kThreads, 0, ctx->stream>>>(seq->d_n_bases, n, k,
+                                                                                  rows, items);
+            }));
+        TRY(launch(ctx, "scan", [&] { k_scan_u64<<<1, 1024, 0, ctx->stream>>>(rows, n, seq->d_row_off); }));
+        TRY(launch(ctx, "scan", [&] { k_scan_u64<<<1, 1024, 0, ctx->stream>>>(items, n, seq->d_item_off); }));
+        CU(ctx, cudaMemcpyAsync(&ctx->h_ctr[0], seq->d_row_off + n, 8, cudaMemcpyDeviceToHost, ctx->stream));
+        CU(ctx, cudaMemcpyAsync(&ctx->h_ctr[1], seq->d_item_off + n, 8, cudaMemcpyDeviceToHost, ctx->stream));
+        CU(ctx, cudaStreamSynchronize(ctx->stream));
+        seq->cached_rows = ctx->h_ctr[0];
+        seq->cached_items = ctx->h_ctr[1];
+        seq->cached_k = k;
+    }
+    v->word_off = seq->d_word_off;
+    v->row_off = seq->d_row_off;
+    v->item_off = seq->d_item_off;
+    v->n_rows = seq->cached_rows;
+    v->n_items = seq->cached_items;
+    return DNAGPU_OK;
+}
+
+/* ---- predicates ------------------------------------------------------------------- */
+static int iupac_set(char c)
+{ /* A=1 T=2 C=4 G=8, the sets of nucleotide_matches (dna.c:1064-1086); 'U' matches
+     nothing because a kmer never decodes to 'U' (dna.c:1070, Q4) */
+    switch (c) {
+    case 'A': return 1;
+    case 'T': return 2;
+    case 'C': return 4;
+    case 'G': return 8;
+    case 'U': return 0;
+    case 'W': return 1 | 2;
+    case 'S': return 4 | 8;
+    case 'M': return 1 | 4;
+    case 'K': return 8 | 2;
+    case 'R': return 1 | 8;
+    case 'Y': return 4 | 2;
+    case 'B': return 4 | 8 | 2;
+    case 'D': return 1 | 8 | 2;
+    case 'H': return 1 | 4 | 2;
+    case 'V': return 1 | 4 | 8;
+    case 'N': return 15;
+    }
+    return -1;
+}
+
+/* validate the literals (the reference does this when it coerces them:
+ * qkmer_in -> validate_qkmer_pattern, dna.c:876-900) */
+static int check_filter_literals(dnagpu_ctx *ctx, const dnagpu_where *f)
+{
+    if (!f) return DNAGPU_OK;
+    if (f->reserved != 0) return fail(ctx, DNAGPU_EARG, "dnagpu_where.reserved must be 0");
+    if (f->prefix_len < 0 || f->prefix_len > DNAGPU_MAX_K)
+        return fail(ctx, DNAGPU_EARG, "prefix_len out of range");
+    if (f->prefix_len > 0 && f->prefix_len < 32 && (f->prefix_bits >> (2 * f->prefix_len)))
+        return fail(ctx, DNAGPU_EPREFIX_BITS, "%s", dnagpu_strerror(DNAGPU_EPREFIX_BITS));
+    if (f->qkmer) {
+        size_t len = strlen(f->qkmer);
+        if (len == 0) return fail(ctx, DNAGPU_EQKMER_EMPTY, "%s", dnagpu_strerror(DNAGPU_EQKMER_EMPTY));
+        if (len > 32) return fail(ctx, DNAGPU_EQKMER_TOOLONG, "%s", dnagpu_strerror(DNAGPU_EQKMER_TOOLONG));
+        for (size_t i = 0; i < len; ++i)
+            if (iupac_set(f->qkmer[i]) < 0)
+                return fail(ctx, DNAGPU_EQKMER_CHAR, "Invalid character in qkmer pattern: %c", f->qkmer[i]);
+    }
+    return DNAGPU_OK;
+}
+
+/* the per-row ERRORs (dna.c:854-856, 1106-1108) fire only when a row is evaluated */
+static int build_pred(dnagpu_ctx *ctx, const dnagpu_where *f, int k, uint64_t n_rows, Pred *p,
+                      bool *active)
+{
+    *active = false;
+    p->ma = p->mt = p->mc = p->mg = ~0ull;
+    if (!f || (f->prefix_len == 0 && !f->qkmer)) return DNAGPU_OK;
+    if (n_rows == 0) return DNAGPU_OK;
+    if (f->prefix_len > k) return fail(ctx, DNAGPU_EPREFIX_LEN, "%s", dnagpu_strerror(DNAGPU_EPREFIX_LEN));
+    if (f->qkmer && (int)strlen(f->qkmer) != k)
+        return fail(ctx, DNAGPU_EQKMER_LEN, "%s", dnagpu_strerror(DNAGPU_EQKMER_LEN));
+    uint64_t plane[4] = {~0ull, ~0ull, ~0ull, ~0ull};
+    for (int j = 0; j < k; ++j) {
+        int set = f->qkmer ? iupac_set(f->qkmer[j]) : 15;
+        if (j < f->prefix_len) set &= 1 << ((f->prefix_bits >> (2 * j)) & 3); /* Q1: len 32 = all 64 bits */
+        for (int b = 0; b < 4; ++b)
+            if (!(set & (1 << b))) plane[b] &= ~(1ull << (2 * j));
+    }
+    p->ma = plane[0];
+    p->mt = plane[1];
+    p->mc = plane[2];
+    p->mg = plane[3];
+    *active = true;
+    return DNAGPU_OK;
+}
+
+static int check_k(dnagpu_ctx *ctx, int k)
+{
+    if (k <= 0 || k > DNAGPU_MAX_K) /* dna.c:772-773 */
+        return fail(ctx, DNAGPU_EINVAL_K, "%s", dnagpu_strerror(DNAGPU_EINVAL_K));
+    return DNAGPU_OK;
+}
+
+#define DISPATCH_LAYOUT(layout, CALL) \
+    switch (layout) {                 \
+    case kSingle: { constexpr int LY = kSingle; CALL; } break; \
+    case kFixed: { constexpr int LY = kFixed; CALL; } break;   \
+    default: { constexpr int LY = kRagged; CALL; } break;      \
+    }
+
+/* ---- generate_kmers ----------------------------------------------------------------- */
+extern "C" int dnagpu_extract(dnagpu_ctx *ctx, const dnagpu_seq *seq, int k, uint64_t *d_out,
+                              uint64_t cap, uint64_t *n_out)
+{
+    if (!ctx || !seq || !n_out) return fail(ctx, DNAGPU_EARG, "dnagpu_extract: NULL argument");
+    TRY(check_k(ctx, k));
+    CU(ctx, cudaSetDevice(ctx->device));
+    SeqView v;
+    TRY(make_view(ctx, seq, k, &v));
+    *n_out = v.n_rows;
+    if (v.n_rows == 0) return DNAGPU_OK;
+    if (!d_out || cap < v.n_rows)
+        return fail(ctx, DNAGPU_ECAPACITY, "generate_kmers needs room for %llu rows",
+                    (unsigned long long)v.n_rows);
+    if ((uintptr_t)d_out & 15) return fail(ctx, DNAGPU_EARG, "d_out must be 16-byte aligned");
+    const unsigned grid = grid_for((v.n_rows + 1) / 2, (uint64_t)kThreads * kPairsPerThread);
+    DISPATCH_LAYOUT(seq->layout, TRY(launch(ctx, "extract", [&] {
+        k_extract<LY><<<grid, kThreads, 0, ctx->stream>>>(v, kmer_mask(k), d_out);
+    })));
+    return DNAGPU_OK;
+}
+
+extern "C" int dnagpu_generate_kmers(dnagpu_ctx *ctx, const uint64_t *words, uint64_t n_bases,
+                                     int k, uint64_t *out, uint64_t cap, uint64_t *n_out)
+{
+    if (!ctx || !n_out) return fail(ctx, DNAGPU_EARG, "dnagpu_generate_kmers: NULL argument");
+    TRY(check_k(ctx, k));
+    const uint64_t rows = rows_of(n_bases, k);
+    *n_out = rows;
+    if (rows == 0) return DNAGPU_OK;
+    if (!out || cap < rows)
+        return fail(ctx, DNAGPU_ECAPACITY, "generate_kmers needs room for %llu rows",
+                    (unsigned long long)rows);
+    dnagpu_seq *seq = nullptr;
+    TRY(dnagpu_seq_upload(ctx, words, n_bases, &seq));
+    uint64_t *d_out = nullptr;
+    int rc = dalloc(ctx, (void **)&d_out, rows * 8);
+    if (rc == DNAGPU_OK) rc = dnagpu_extract(ctx, seq, k, d_out, rows, n_out);
+    if (rc == DNAGPU_OK) {
+        cudaError_t e = cudaMemcpyAsync(out, d_out, rows * 8, cudaMemcpyDeviceToHost, ctx->stream);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+        if (e != cudaSuccess) rc = fail(ctx, DNAGPU_ECUDA, "D2H copy: %s", cudaGetErrorString(e));
+    }
+    dfree(ctx, d_out);
+    dnagpu_seq_free(seq);
+    return rc;
+}
+
+/* ---- WHERE ^@ / @> -------------------------------------------------------------------- */
+static int read_u64(dnagpu_ctx *ctx, const uint64_t *d, uint64_t *h)
+{
+    CU(ctx, cudaMemcpyAsync(&ctx->h_ctr[0], d, 8, cudaMemcpyDeviceToHost, ctx->stream));
+    CU(ctx, cudaStreamSynchronize(ctx->stream));
+    *h = ctx->h_ctr[0];
+    return DNAGPU_OK;
+}
+
+/* matches per CTA tile + their exclusive scan; *n_match = total */
+static int filter_scan(dnagpu_ctx *ctx, const dnagpu_seq *seq, const SeqView &v, const Pred &p,
+                       Scratch &sc, uint64_t **tile_off, uint64_t *n_match)
+{
+    const unsigned tiles = grid_for(v.n_items, kThreads);
+    uint64_t *tile_cnt;
+    TRY(sc.get((void **)&tile_cnt, ((uint64_t)tiles + 1) * 8));
+    TRY(sc.get((void **)tile_off, ((uint64_t)tiles + 1) * 8));
+    DISPATCH_LAYOUT(seq->layout, TRY(launch(ctx, "filter_count", [&] {
+        k_filter_count<LY><<<tiles, kThreads, 0, ctx->stream>>>(v, p, tile_cnt);
+    })));
+    TRY(launch(ctx, "scan", [&] { k_scan_u64<<<1, 1024, 0, ctx->stream>>>(tile_cnt, tiles, *tile_off); }));
+    return read_u64(ctx, *tile_off + tiles, n_match);
+}
+
+extern "C" int dnagpu_filter(dnagpu_ctx *ctx, const dnagpu_seq *seq, int k,
+                             const dnagpu_where *filter, uint64_t *d_out, uint64_t cap,
+                             uint64_t *n_out)
+{
+    if (!ctx || !seq || !n_out) return fail(ctx, DNAGPU_EARG, "dnagpu_filter: NULL argument");
+    TRY(check_k(ctx, k));
+    TRY(check_filter_literals(ctx, filter));
+    CU(ctx, cudaSetDevice(ctx->device));
+    SeqView v;
+    TRY(make_view(ctx, seq, k, &v));
+    Pred p;
+    bool active;
+    TRY(build_pred(ctx, filter, k, v.n_rows, &p, &active));
+    if (!active) {
+        if (!d_out) {
+            *n_out = v.n_rows;
+            return DNAGPU_OK;
+        }
+        return dnagpu_extract(ctx, seq, k, d_out, cap, n_out);
+    }
+    *n_out = 0;
+    if (v.n_rows == 0) return DNAGPU_OK;
+    Scratch sc(ctx);
+    uint64_t *tile_off, n_match;
+    TRY(filter_scan(ctx, seq, v, p, sc, &tile_off, &n_match));
+    *n_out = n_match;
+    if (!d_out || n_match == 0) return DNAGPU_OK;
+    if (cap < n_match)
+        return fail(ctx, DNAGPU_ECAPACITY, "filter needs room for %llu rows", (unsigned long long)n_match);
+    const unsigned tiles = grid_for(v.n_items, kThreads);
+    const int smem = kThreads * 32 * (int)sizeof(uint64_t);
+    DISPATCH_LAYOUT(seq->layout, TRY(launch(ctx, "filter_write", [&] {
+        k_filter_write<LY><<<tiles, kThreads, smem, ctx->stream>>>(v, p, kmer_mask(k), tile_off, d_out);
+    })));
+    return DNAGPU_OK;
+}
+
+extern "C" int dnagpu_filter_kmers(dnagpu_ctx *ctx, const uint64_t *words, uint64_t n_bases,
+                                   int k, const dnagpu_where *filter, uint64_t *out,
+                                   uint64_t cap, uint64_t *n_out)
+{
+    if (!ctx || !n_out) return fail(ctx, DNAGPU_EARG, "dnagpu_filter_kmers: NULL argument");
+    TRY(check_k(ctx, k));
+    TRY(check_filter_literals(ctx, filter));
+    dnagpu_seq *seq = nullptr;
+    TRY(dnagpu_seq_upload(ctx, words, n_bases, &seq));
+    uint64_t need = 0, *d_out = nullptr;
+    int rc = dnagpu_filter(ctx, seq, k, filter, nullptr, 0, &need);
+    *n_out = need;
+    if (rc == DNAGPU_OK && need > 0) {
+        if (!out || cap < need)
+            rc = fail(ctx, DNAGPU_ECAPACITY, "filter needs room for %llu rows", (unsigned long long)need);
+        if (rc == DNAGPU_OK) rc = dalloc(ctx, (void **)&d_out, need * 8);
+        if (rc == DNAGPU_OK) rc = dnagpu_filter(ctx, seq, k, filter, d_out, need, n_out);
+        if (rc == DNAGPU_OK) {
+            cudaError_t e = cudaMemcpyAsync(out, d_out, need * 8, cudaMemcpyDeviceToHost, ctx->stream);
+            if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+            if (e != cudaSuccess) rc = fail(ctx, DNAGPU_ECUDA, "D2H copy: %s", cudaGetErrorString(e));
+        }
+    }
+    dfree(ctx, d_out);
+    dnagpu_seq_free(seq);
+    return rc;
+}
+
+extern "C" int dnagpu_filter_keys(dnagpu_ctx *ctx, const uint64_t *d_keys, uint64_t n, int k,
+                                  const dnagpu_where *filter, uint64_t *d_out, uint64_t cap,
+                                  uint64_t *n_out)
+{
+    if (!ctx || !n_out || (!d_keys && n)) return fail(ctx, DNAGPU_EARG, "dnagpu_filter_keys: NULL argument");
+    TRY(check_k(ctx, k));
+    TRY(check_filter_literals(ctx, filter));
+    CU(ctx, cudaSetDevice(ctx->device));
+    Pred p;
+    bool active;
+    TRY(build_pred(ctx, filter, k, n, &p, &active));
+    *n_out = 0;
+    if (n == 0) return DNAGPU_OK;
+    if (!active) {
+        *n_out = n;
+        if (!d_out) return DNAGPU_OK;
+        if (cap < n) return fail(ctx, DNAGPU_ECAPACITY, "filter needs room for %llu rows", (unsigned long long)n);
+        CU(ctx, cudaMemcpyAsync(d_out, d_keys, n * 8, cudaMemcpyDeviceToDevice, ctx->stream));
+        return DNAGPU_OK;
+    }
+    Scratch sc(ctx);
+    const unsigned tiles = grid_for(n, (uint64_t)kThreads * kKeysPerThread);
+    uint64_t *tile_cnt, *tile_off, n_match;
+    TRY(sc.get((void **)&tile_cnt, ((uint64_t)tiles + 1) * 8));
+    TRY(sc.get((void **)&tile_off, ((uint64_t)tiles + 1) * 8));
+    TRY(launch(ctx, "filter_keys_count", [&] {
+        k_filter_keys_count<<<tiles, kThreads, 0, ctx->stream>>>(d_keys, n, p, tile_cnt);
+    }));
+    TRY(launch(ctx, "scan", [&] { k_scan_u64<<<1, 1024, 0, ctx->stream>>>(tile_cnt, tiles, tile_off); }));
+    TRY(read_u64(ctx, tile_off + tiles, &n_match));
+    *n_out = n_match;
+    if (!d_out || n_match == 0) return DNAGPU_OK;
+    if (cap < n_match)
+        return fail(ctx, DNAGPU_ECAPACITY, "filter needs room for %llu rows", (unsigned long long)n_match);
+    TRY(launch(ctx, "filter_keys_write", [&] {
+        k_filter_keys_write<<<tiles, kThreads, 0, ctx->stream>>>(d_keys, n, p, tile_off, d_out);
+    }));
+    return DNAGPU_OK;
+}
+
+/* ---- GROUP BY kmer ---------------------------------------------------------------------- */
+static int zero_counters(dnagpu_ctx *ctx)
+{
+    CU(ctx, cudaMemsetAsync(ctx->d_ctr, 0, (C_COUNT + 2 * kMaxParts) * 8, ctx->stream));
+    return DNAGPU_OK;
+}
+static int fetch_counters(dnagpu_ctx *ctx)
+{
+    CU(ctx, cudaMemcpyAsync(ctx->h_ctr, ctx->d_ctr, (C_COUNT + 2 * kMaxParts) * 8,
+                            cudaMemcpyDeviceToHost, ctx->stream));
+    CU(ctx, cudaStreamSynchronize(ctx->stream));
+    return DNAGPU_OK;
+}
+
+static int table_new(dnagpu_ctx *ctx, int k, uint64_t rows, dnagpu_table **out)
+{
+    dnagpu_table *t = new (std::nothrow) dnagpu_table();
+    if (!t) return fail(ctx, DNAGPU_ENOMEM, "out of host memory");
+    t->ctx = ctx;
+    t->k = k;
+    t->rows = rows;
+    int rc = dalloc(ctx, (void **)&t->d_kmers, rows * 8);
+    if (rc == DNAGPU_OK) rc = dalloc(ctx, (void **)&t->d_counts, rows * 8);
+    if (rc != DNAGPU_OK) {
+        dnagpu_table_free(t);
+        return rc;
+    }
+    *out = t;
+    return DNAGPU_OK;
+}
+
+/* What the counting kernels consume: packed sequences or a materialised key list. */
+struct CountInput {
+    const dnagpu_seq *seq = nullptr;
+    SeqView v;
+    const uint64_t *d_keys = nullptr;
+    uint64_t n = 0; /* rows (before WHERE) */
+    bool filtered = false;
+    Pred p;
+};
+
+static uint64_t pow4_capped(int k) { return k >= 32 ? UINT64_MAX : (1ull << (2 * k)); }
+
+static int pick_method(const dnagpu_count_opts *opts, int k, uint64_t n)
+{
+    int m = opts ? opts->method : DNAGPU_COUNT_AUTO;
+    if (m == DNAGPU_COUNT_PARTITION) m = DNAGPU_COUNT_HASH; /* not split out yet: see DESIGN.md */
+    if (m == DNAGPU_COUNT_DENSE && k > 16) m = DNAGPU_COUNT_HASH;
+    if (m != DNAGPU_COUNT_AUTO) return m;
+    /* dense when the 4^k counters are no bigger than a hash table of the input */
+    if (k <= 16 && pow4_capped(k) <= std::max<uint64_t>(1ull << 16, 8 * n)) return DNAGPU_COUNT_DENSE;
+    return DNAGPU_COUNT_HASH;
+}
+
+template <typename CT>
+static int count_dense_t(dnagpu_ctx *ctx, const CountInput &in, int k, dnagpu_stats *stats,
+                         dnagpu_table **table)
+{
+    const uint64_t bins = 1ull << (2 * k);
+    const uint64_t mask = kmer_mask(k);
+    Scratch sc(ctx);
+    CT *tab;
+    TRY(sc.get((void **)&tab, bins * sizeof(CT)));
+    TRY(launch(ctx, "dense_init", [&] { cudaMemsetAsync(tab, 0, bins * sizeof(CT), ctx->stream); }));
+    TRY(zero_counters(ctx));
+    if (in.d_keys) {
+        TRY(launch(ctx, "count_dense_keys", [&] {
+            k_count_dense_keys<CT><<<grid_for(in.n, kThreads * 8), kThreads, 0, ctx->stream>>>(
+                in.d_keys, in.n, bins, tab, ctx->d_ctr);
+        }));
+    } else if (k <= 7) {
+        const uint32_t rep_shift = (uint32_t)std::min(5, 14 - 2 * k);
+        const int smem = (int)((bins << rep_shift) * sizeof(uint32_t));
+        /* persistent grid; enough CTAs that none sees 2^32 k-mers */
+        uint64_t want = std::max<uint64_t>((uint64_t)ctx->sm_count * 4, in.v.n_items / (1ull << 26) + 1);
+        const unsigned grid = (unsigned)std::min<uint64_t>(want, grid_for(in.v.n_items, kThreads));
+        DISPATCH_LAYOUT(in.seq->layout, TRY(launch(ctx, "count_dense_smem", [&] {
+            if (in.filtered)
+                k_count_dense_smem<LY, true, CT><<<grid, kThreads, smem, ctx->stream>>>(
+                    in.v, in.p, mask, (uint32_t)bins, rep_shift, tab, ctx->d_ctr);
+            else
+                k_count_dense_smem<LY, false, CT><<<grid, kThreads, smem, ctx->stream>>>(
+                    in.v, in.p, mask, (uint32_t)bins, rep_shift, tab, ctx->d_ctr);
+        })));
+    } else {
+        const unsigned grid = grid_for(in.v.n_items, kThreads);
+        DISPATCH_LAYOUT(in.seq->layout, TRY(launch(ctx, "count_dense", [&] {
+            if (in.filtered)
+                k_count_dense<LY, true, CT><<<grid, kThreads, 0, ctx->stream>>>(in.v, in.p, mask, tab, ctx->d_ctr);
+            else
+                k_count_dense<LY, false, CT><<<grid, kThreads, 0, ctx->stream>>>(in.v, in.p, mask, tab, ctx->d_ctr);
+        })));
+    }
+    const unsigned sgrid = (unsigned)std::min<uint64_t>(grid_for(bins, kThreads), (uint64_t)ctx->sm_count * 16);
+    TRY(launch(ctx, "dense_stats", [&] {
+        k_dense_stats<CT><<<sgrid, kThreads, 0, ctx->stream>>>(tab, bins, ctx->d_ctr);
+    }));
+    TRY(fetch_counters(ctx));
+    if (ctx->h_ctr[C_OVERFLOW]) return fail(ctx, DNAGPU_EARG, "a key is not a %d-mer (>= 4^k)", k);
+    stats->total = ctx->h_ctr[C_TOTAL];
+    stats->distinct = ctx->h_ctr[C_DISTINCT];
+    stats->unique = ctx->h_ctr[C_UNIQUE];
+    if (table) {
+        TRY(table_new(ctx, k, stats->distinct, table));
+        if (stats->distinct)
+            TRY(launch(ctx, "dense_compact", [&] {
+                k_dense_compact<CT><<<sgrid, kThreads, 0, ctx->stream>>>(tab, bins, (*table)->d_kmers,
+                                                                        (*table)->d_counts, ctx->d_ctr);
+            }));
+    }
+    return DNAGPU_OK;
+}
+
+static int count_hash(dnagpu_ctx *ctx, const CountInput &in, int k, const dnagpu_count_opts *opts,
+                      uint64_t n_keys_bound, dnagpu_stats *stats, dnagpu_table **table)
+{
+    double load = (opts && opts->load_factor > 0.0) ? opts->load_factor : 0.5;
+    load = std::min(0.95, std::max(0.05, load));
+    uint64_t expected = (opts && opts->expected_keys) ? opts->expected_keys
+                                                      : std::min(n_keys_bound, pow4_capped(k));
+    uint64_t cap = std::max<uint64_t>(1024, (uint64_t)((double)expected / load) + 1);
+    size_t free_b = 0, total_b = 0;
+    CU(ctx, cudaMemGetInfo(&free_b, &total_b));
+    (void)total_b;
+    Scratch sc(ctx);
+    Slot *slots = nullptr;
+    int rc = sc.get((void **)&slots, cap * sizeof(Slot));
+    if (rc == DNAGPU_ENOMEM && !(opts && opts->load_factor > 0.0)) {
+        /* default load does not fit: pack the table tighter before giving up */
+        cap = std::max<uint64_t>(1024, (uint64_t)((double)expected / 0.85) + 1);
+        rc = sc.get((void **)&slots, cap * sizeof(Slot));
+    }
+    TRY(rc);
+    const unsigned igrid = (unsigned)std::min<uint64_t>(grid_for(cap, kThreads), (uint64_t)ctx->sm_count * 32);
+    TRY(launch(ctx, "table_init", [&] { k_table_init<<<igrid, kThreads, 0, ctx->stream>>>(slots, cap); }));
+    TRY(zero_counters(ctx));
+    if (in.d_keys) {
+        TRY(launch(ctx, "count_hash_keys", [&] {
+            k_count_hash_keys<<<grid_for(in.n, (uint64_t)kThreads * kKeysPerThread), kThreads, 0, ctx->stream>>>(
+                in.d_keys, in.n, slots, cap, ctx->d_ctr);
+        }));
+    } else {
+        const unsigned grid = grid_for(in.v.n_items, kThreads);
+        const uint64_t mask = kmer_mask(k);
+        DISPATCH_LAYOUT(in.seq->layout, TRY(launch(ctx, "count_hash", [&] {
+            if (in.filtered)
+                k_count_hash<LY, true><<<grid, kThreads, 0, ctx->stream>>>(in.v, in.p, mask, slots, cap, ctx->d_ctr);
+            else
+                k_count_hash<LY, false><<<grid, kThreads, 0, ctx->stream>>>(in.v, in.p, mask, slots, cap, ctx->d_ctr);
+        })));
+    }
+    TRY(fetch_counters(ctx));
+    if (ctx->h_ctr[C_OVERFLOW])
+        return fail(ctx, DNAGPU_EINTERNAL, "hash table of %llu slots overflowed (expected_keys too small)",
+                    (unsigned long long)cap);
+    const uint64_t side = ctx->h_ctr[C_SIDE]; /* 'G' x 32, the one key equal to the sentinel */
+    const uint64_t in_table = ctx->h_ctr[C_DISTINCT];
+    stats->total = ctx->h_ctr[C_TOTAL];
+    stats->distinct = in_table + (side > 0);
+    stats->unique = ctx->h_ctr[C_UNIQUE] + (side == 1);
+    if (table) {
+        TRY(table_new(ctx, k, stats->distinct, table));
+        if (in_table) {
+            const unsigned cgrid = (unsigned)std::min<uint64_t>(grid_for(cap, kThreads), (uint64_t)ctx->sm_count * 32);
+            TRY(launch(ctx, "table_compact", [&] {
+                k_table_compact<<<cgrid, kThreads, 0, ctx->stream>>>(slots, cap, (*table)->d_kmers,
+                                                                    (*table)->d_counts, ctx->d_ctr);
+            }));
+        }
+        if (side) {
+            ctx->h_ctr[0] = kEmpty;
+            ctx->h_ctr[1] = side;
+            CU(ctx, cudaMemcpyAsync((*table)->d_kmers + in_table, &ctx->h_ctr[0], 8, cudaMemcpyHostToDevice, ctx->stream));
+            CU(ctx, cudaMemcpyAsync((*table)->d_counts + in_table, &ctx->h_ctr[1], 8, cudaMemcpyHostToDevice, ctx->stream));
+            CU(ctx, cudaStreamSynchronize(ctx->stream));
+        }
+    }
+    return DNAGPU_OK;
+}
+
+static int count_any(dnagpu_ctx *ctx, CountInput &in, int k, const dnagpu_count_opts *opts,
+                     dnagpu_stats *stats, dnagpu_table **table)
+{
+    dnagpu_stats local;
+    if (!stats) stats = &local;
+    stats->total = stats->distinct = stats->unique = 0;
+    if (table) *table = nullptr;
+    if (in.n == 0) {
+        if (table) TRY(table_new(ctx, k, 0, table));
+        return DNAGPU_OK;
+    }
+    const int method = pick_method(opts, k, in.n);
+    int rc;
+    if (method == DNAGPU_COUNT_DENSE) {
+        rc = in.n < 0xffffffffull ? count_dense_t<uint32_t>(ctx, in, k, stats, table)
+                                  : count_dense_t<unsigned long long>(ctx, in, k, stats, table);
+    } else {
+        uint64_t bound = in.n;
+        if (in.filtered && !(opts && opts->expected_keys)) {
+            /* size the table from the exact number of rows the WHERE clause keeps */
+            Scratch sc(ctx);
+            uint64_t *tile_off;
+            TRY(filter_scan(ctx, in.seq, in.v, in.p, sc, &tile_off, &bound));
+            if (bound == 0) {
+                if (table) TRY(table_new(ctx, k, 0, table));
+                return DNAGPU_OK;
+            }
+        }
+        rc = count_hash(ctx, in, k, opts, bound, stats, table);
+    }
+    if (rc != DNAGPU_OK && table && *table) {
+        dnagpu_table_free(*table);
+        *table = nullptr;
+    }
+    return rc;
+}
+
+extern "C" int dnagpu_count(dnagpu_ctx *ctx, const dnagpu_seq *seq, int k,
+                            const dnagpu_where *filter, const dnagpu_count_opts *opts,
+                            dnagpu_stats *stats, dnagpu_table **table)
+{
+    if (!ctx || !seq) return fail(ctx, DNAGPU_EARG, "dnagpu_count: NULL argument");
+    TRY(check_k(ctx, k));
+    TRY(check_filter_literals(ctx, filter));
+    CU(ctx, cudaSetDevice(ctx->device));
+    CountInput in;
+    in.seq = seq;
+    TRY(make_view(ctx, seq, k, &in.v));
+    in.n = in.v.n_rows;
+    TRY(build_pred(ctx, filter, k, in.n, &in.p, &in.filtered));
+    return count_any(ctx, in, k, opts, stats, table);
+}
+
+extern "C" int dnagpu_count_keys(dnagpu_ctx *ctx, const uint64_t *d_keys, uint64_t n, int k,
+                                 const dnagpu_count_opts *opts, dnagpu_stats *stats,
+                                 dnagpu_table **table)
+{
+    if (!ctx || (!d_keys && n)) return fail(ctx, DNAGPU_EARG, "dnagpu_count_keys: NULL argument");
+    TRY(check_k(ctx, k));
+    CU(ctx, cudaSetDevice(ctx->device));
+    CountInput in;
+    in.d_keys = d_keys;
+    in.n = n;
+    return count_any(ctx, in, k, opts, stats, table);
+}
+
+extern "C" int dnagpu_count_kmers(dnagpu_ctx *ctx, const uint64_t *words, uint64_t n_bases, int k,
+                                  const dnagpu_where *filter, dnagpu_stats *stats,
+                                  dnagpu_table **table)
+{
+    if (!ctx) return fail(ctx, DNAGPU_EARG, "dnagpu_count_kmers: NULL ctx");
+    TRY(check_k(ctx, k));
+    TRY(check_filter_literals(ctx, filter));
+    dnagpu_seq *seq = nullptr;
+    TRY(dnagpu_seq_upload(ctx, words, n_bases, &seq));
+    int rc = dnagpu_count(ctx, seq, k, filter, nullptr, stats, table);
+    dnagpu_seq_free(seq);
+    return rc;
+}
+
+extern "C" int dnagpu_count_reads(dnagpu_ctx *ctx, const uint64_t *words, uint64_t n_reads,
+                                  uint32_t bases_per_read, uint32_t stride_words, int k,
+                                  const dnagpu_where *filter, dnagpu_stats *stats,
+                                  dnagpu_table **table)
+{
+    if (!ctx) return fail(ctx, DNAGPU_EARG, "dnagpu_count_reads: NULL ctx");
+    TRY(check_k(ctx, k));
+    TRY(check_filter_literals(ctx, filter));
+    dnagpu_seq *seq = nullptr;
+    TRY(dnagpu_seq_upload_reads(ctx, words, n_reads, bases_per_read, stride_words, &seq));
+    int rc = dnagpu_count(ctx, seq, k, filter, nullptr, stats, table);
+    dnagpu_seq_free(seq);
+    return rc;
+}
+
+/* ---- the grouped result -------------------------------------------------------------------- */
+extern "C" uint64_t dnagpu_table_rows(const dnagpu_table *t) { return t ? t->rows : 0; }
+extern "C" int dnagpu_table_k(const dnagpu_table *t) { return t ? t->k : 0; }
+
+extern "C" int dnagpu_table_fetch(dnagpu_ctx *ctx, const dnagpu_table *t, uint64_t offset,
+                                  uint64_t n, uint64_t *kmers, uint64_t *counts)
+{
+    if (!ctx || !t) return fail(ctx, DNAGPU_EARG, "dnagpu_table_fetch: NULL argument");
+    if (offset > t->rows || n > t->rows - offset) return fail(ctx, DNAGPU_EARG, "row range outside the table");
+    CU(ctx, cudaSetDevice(ctx->device));
+    if (n && kmers) CU(ctx, cudaMemcpyAsync(kmers, t->d_kmers + offset, n * 8, cudaMemcpyDeviceToHost, ctx->stream));
+    if (n && counts) CU(ctx, cudaMemcpyAsync(counts, t->d_counts + offset, n * 8, cudaMemcpyDeviceToHost, ctx->stream));
+    CU(ctx, cudaStreamSynchronize(ctx->stream));
+    return DNAGPU_OK;
+}
+
+extern "C" int dnagpu_table_device(const dnagpu_table *t, const uint64_t **d_kmers,
+                                   const uint64_t **d_counts)
+{
+    if (!t) return fail(nullptr, DNAGPU_EARG, "table is NULL");
+    if (d_kmers) *d_kmers = t->d_kmers;
+    if (d_counts) *d_counts = t->d_counts;
+    return DNAGPU_OK;
+}
+
+extern "C" void dnagpu_table_free(dnagpu_table *t)
+{
+    if (!t) return;
+    cudaSetDevice(t->ctx->device);
+    dfree(t->ctx, t->d_kmers);
+    dfree(t->ctx, t->d_counts);
+    delete t;
+}
+
+/* ---- owner routing --------------------------------------------------------------------------- */
+extern "C" uint32_t dnagpu_owner_of(uint64_t kmer, uint32_t n_parts)
+{
+    return owner_of(mix64(kmer), n_parts);
+}
+
+extern "C" int dnagpu_partition(dnagpu_ctx *ctx, const dnagpu_seq *seq, int k,
+                                const dnagpu_where *filter, uint32_t n_parts, uint64_t *d_out,
+                                uint64_t cap, uint64_t *part_counts)
+{
+    if (!ctx || !seq || !part_counts) return fail(ctx, DNAGPU_EARG, "dnagpu_partition: NULL argument");
+    if (n_parts < 1 || n_parts > (uint32_t)kMaxParts)
+        return fail(ctx, DNAGPU_EARG, "n_parts must be between 1 and %d", kMaxParts);
+    TRY(check_k(ctx, k));
+    TRY(check_filter_literals(ctx, filter));
+    CU(ctx, cudaSetDevice(ctx->device));
+    SeqView v;
+    TRY(make_view(ctx, seq, k, &v));
+    Pred p;
+    bool active;
+    TRY(build_pred(ctx, filter, k, v.n_rows, &p, &active));
+    for (uint32_t i = 0; i < n_parts; ++i) part_counts[i] = 0;
+    if (v.n_rows == 0) return DNAGPU_OK;
+    const uint64_t mask = kmer_mask(k);
+    unsigned long long *d_cnt = ctx->d_ctr + C_COUNT, *d_cur = ctx->d_ctr + C_COUNT + kMaxParts;
+    TRY(zero_counters(ctx));
+    const unsigned pgrid = (unsigned)std::min<uint64_t>(grid_for(v.n_items, kThreads), (uint64_t)ctx->sm_count * 16);
+    DISPATCH_LAYOUT(seq->layout, TRY(launch(ctx, "partition_count", [&] {
+        if (active)
+            k_partition_count<LY, true><<<pgrid, kThreads, 0, ctx->stream>>>(v, p, mask, n_parts, d_cnt);
+        else
+            k_partition_count<LY, false><<<pgrid, kThreads, 0, ctx->stream>>>(v, p, mask, n_parts, d_cnt);
+    })));
+    TRY(fetch_counters(ctx));
+    uint64_t total = 0;
+    uint64_t offs[kMaxParts];
+    for (uint32_t i = 0; i < n_parts; ++i) {
+        part_counts[i] = ctx->h_ctr[C_COUNT + i];
+        offs[i] = total;
+        total += part_counts[i];
+    }
+    if (!d_out) return DNAGPU_OK;
+    if (cap < total)
+        return fail(ctx, DNAGPU_ECAPACITY, "partition needs room for %llu rows", (unsigned long long)total);
+    if (total == 0) return DNAGPU_OK;
+    Scratch sc(ctx);
+    uint64_t *d_off;
+    TRY(sc.get((void **)&d_off, kMaxParts * 8));
+    memcpy(ctx->h_ctr, offs, n_parts * 8); /* pinned staging */
+    CU(ctx, cudaMemcpyAsync(d_off, ctx->h_ctr, n_parts * 8, cudaMemcpyHostToDevice, ctx->stream));
+    const unsigned grid = grid_for(v.n_items, kThreads);
+    const int smem = kThreads * 32 * (int)sizeof(uint64_t);
+    DISPATCH_LAYOUT(seq->layout, TRY(launch(ctx, "partition_write", [&] {
+        if (active)
+            k_partition_write<LY, true><<<grid, kThreads, smem, ctx->stream>>>(v, p, mask, n_parts, d_off, d_cur, d_out);
+        else
+            k_partition_write<LY, false><<<grid, kThreads, smem, ctx->stream>>>(v, p, mask, n_parts, d_off, d_cur, d_out);
+    })));
+    CU(ctx, cudaStreamSynchronize(ctx->stream)); /* h_ctr staging is reused by the next call */
+    return DNAGPU_OK;
+}
+
+/* ---- profiling --------------------------------------------------------------------------------- */
+extern "C" int dnagpu_profile_enable(dnagpu_ctx *ctx, int on)
+{
+    if (!ctx) return fail(nullptr, DNAGPU_EARG, "ctx is NULL");
+    ctx->profiling = on != 0;
+    return DNAGPU_OK;
+}
+
+extern "C" int dnagpu_profile_reset(dnagpu_ctx *ctx)
+{
+    if (!ctx) return fail(nullptr, DNAGPU_EARG, "ctx is NULL");
+    CU(ctx, cudaStreamSynchronize(ctx->stream));
+    for (auto &r : ctx->prof) {
+        cudaEventDestroy(r.e0);
+        cudaEventDestroy(r.e1);
+    }
+    ctx->prof.clear();
+    return DNAGPU_OK;
+}
+
+extern "C" int dnagpu_profile_query(dnagpu_ctx *ctx, const char *prefix, double *total_ms,
+                                    uint64_t *launches)
+{
+    if (!ctx) return fail(nullptr, DNAGPU_EARG, "ctx is NULL");
+    CU(ctx, cudaStreamSynchronize(ctx->stream));
+    double ms = 0;
+    uint64_t n = 0;
+    const size_t plen = prefix ? strlen(prefix) : 0;
+    for (auto &r : ctx->prof) {
+        if (plen && r.name.compare(0, plen, prefix) != 0) continue;
+        float t = 0;
+        CU(ctx, cudaEventElapsedTime(&t, r.e0, r.e1));
+        ms += t;
+        n++;
+    }
+    if (total_ms) *total_ms = ms;
+    if (launches) *launches = n;
+    return DNAGPU_OK;
+}
+
+extern "C" int dnagpu_profile_dump(dnagpu_ctx *ctx, char *buf, size_t cap)
+{
+    if (!ctx || !buf || !cap) return fail(ctx, DNAGPU_EARG, "NULL argument");
+    CU(ctx, cudaStreamSynchronize(ctx->stream));
+    std::vector<std::string> names;
+    for (auto &r : ctx->prof)
+        if (std::find(names.begin(), names.end(), r.name) == names.end()) names.push_back(r.name);
+    std::string js = "{";
+    for (size_t i = 0; i < names.size(); ++i) {
+        double ms = 0;
+        uint64_t n = 0;
+        for (auto &r : ctx->prof)
+            if (r.name == names[i]) {
+                float t = 0;
+                cudaEventElapsedTime(&t, r.e0, r.e1);
+                ms += t;
+                n++;
+            }
+        char item[256];
+        snprintf(item, sizeof item, "%s\"%s\": {\"ms\": %.6f, \"launches\": %llu}", i ? ", " : "",
+                 names[i].c_str(), ms, (unsigned long long)n);
+        js += item;
+    }
+    js += "}";
+    if (js.size() + 1 > cap) return fail(ctx, DNAGPU_ECAPACITY, "profile buffer too small");
+    memcpy(buf, js.c_str(), js.size() + 1);
+    return DNAGPU_OK;
+}

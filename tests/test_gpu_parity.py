@@ -1,0 +1,335 @@
+"""Parity of the CUDA path (through the C ABI) with the CPU oracle.  Bit-exact: every
+value on this path is an integer.  Mirrors the statements of the reference's test.sql."""
+import numpy as np
+import pytest
+
+import dnagpu
+from dnagpu import Dna, DnaError, Kmer
+from oracle import ref_cpu as R
+
+pytestmark = pytest.mark.gpu
+
+IUPAC = "ATCGUWSMKRYBDHVN"
+
+
+def rand_dna_words(rng, n):
+    words = rng.integers(0, 2**64, size=(n + 31) // 32, dtype=np.uint64)
+    if n % 32:
+        words[-1] &= np.uint64((1 << (2 * (n % 32))) - 1)
+    return words
+
+
+# ---- the reference's own statements (test.sql:46-119, README.md:66-135) -----------------
+def test_kat_generate_kmers(gpu, kats):
+    for v in kats["generate_kmers"]:
+        assert gpu.generate_kmers(v["dna"], v["k"]).strings() == v["rows"], v["source"]
+
+
+def test_kat_starts_with(gpu, kats):
+    for v in kats["starts_with"]:
+        assert gpu.filter_kmers(v["dna"], v["k"], prefix=v["prefix"]).strings() == v["rows"], v["source"]
+
+
+def test_kat_contains(gpu, kats):
+    for v in kats["contains"]:
+        assert gpu.filter_kmers(v["dna"], v["k"], pattern=v["pattern"]).strings() == v["rows"], v["source"]
+
+
+def test_kat_equality_filter(gpu, kats):
+    for v in kats["equality_filter"]:  # kmer = 'ACGTAC'  <=>  prefix of full length
+        assert gpu.filter_kmers(v["dna"], v["k"], prefix=v["equals"]).strings() == v["rows"], v["source"]
+
+
+def test_kat_group_by(gpu, kats):
+    for v in kats["group_by"]:
+        assert dnagpu.count_kmers(v["dna"], v["k"], ctx=gpu) == v["counts"], v["source"]
+
+
+def test_kat_stats(gpu, kats):
+    for v in kats["stats"]:
+        assert dnagpu.kmer_stats(v["dna"], v["k"], ctx=gpu) == (v["total"], v["distinct"], v["unique"]), v["source"]
+
+
+# ---- generate_kmers ----------------------------------------------------------------------------
+@pytest.mark.parametrize("k", [1, 2, 3, 5, 8, 13, 16, 17, 21, 31, 32])
+def test_extract_matches_oracle(gpu, k):
+    rng = np.random.default_rng(100 + k)
+    for n in (k, k + 1, 32, 33, 64, 65, 1000, 2049, 70_001):
+        if n < k:
+            continue
+        words = rand_dna_words(rng, n)
+        want = R.generate_kmers(words, n, k)            # faithful decode/re-encode form
+        got = gpu.generate_kmers(Dna.from_words(words, n), k).bits
+        assert np.array_equal(got, want), (k, n)
+
+
+def test_extract_edge_cases(gpu):
+    d = Dna("ACGT")
+    assert len(gpu.generate_kmers(d, 5)) == 0                       # Q2: length < k -> 0 rows
+    assert gpu.generate_kmers(d, 4).strings() == ["ACGT"]
+    for k in (0, -1, 33):
+        with pytest.raises(DnaError, match="Invalid k value: must be between 1 and 32") as e:
+            gpu.generate_kmers(d, k)
+        assert e.value.code == 1
+    g = Dna("G" * 40)
+    assert set(gpu.generate_kmers(g, 32).bits.tolist()) == {2**64 - 1}
+    a = Dna("A" * 40)
+    assert set(gpu.generate_kmers(a, 32).bits.tolist()) == {0}
+
+
+def test_extract_device_path_and_synth(gpu):
+    import torch
+    n = 1_000_003
+    seq = gpu.synth(n, seed=9)
+    words = R.synth_seq(9, n)
+    assert np.array_equal(seq.download(), words)                 # device generator == host generator
+    for k in (21, 32):
+        out = gpu.extract(seq, k)
+        gpu.synchronize()
+        got = out.cpu().numpy().view(np.uint64)
+        assert np.array_equal(got, R.generate_kmers(words, n, k, window=True))
+    seq.free()
+
+
+def test_extract_reads_and_ragged(gpu):
+    rng = np.random.default_rng(5)
+    reads = R.synth_reads(3, 1000, 150, 5)
+    for k in (31, 30, 7):
+        seq = gpu.upload_reads(reads, 1000, 150, 5)
+        got = gpu.extract(seq, k).cpu().numpy().view(np.uint64)
+        want = np.concatenate([R.generate_kmers(reads[r * 5:(r + 1) * 5], 150, k) for r in range(1000)])
+        assert np.array_equal(got, want), k
+        seq.free()
+    lens = [1, 5, 31, 32, 33, 100, 7, 64, 2000, 3]
+    dnas = [Dna.from_words(rand_dna_words(rng, n), n) for n in lens]
+    seq = gpu.upload_ragged(dnas)
+    for k in (1, 5, 32):
+        got = gpu.extract(seq, k).cpu().numpy().view(np.uint64)
+        parts = [R.generate_kmers(d.words, d.length, k) for d in dnas]
+        assert np.array_equal(got, np.concatenate(parts)), k
+        assert seq.kmer_count(k) == sum(p.size for p in parts)
+    seq.free()
+
+
+# ---- WHERE ^@ / @> -------------------------------------------------------------------------------
+@pytest.mark.parametrize("k", [1, 3, 6, 16, 21, 31, 32])
+def test_filter_matches_oracle(gpu, k):
+    rng = np.random.default_rng(200 + k)
+    n = 20_011
+    words = rand_dna_words(rng, n)
+    d = Dna.from_words(words, n)
+    rows = R.generate_kmers(words, n, k)
+    for trial in range(6):
+        plen = int(rng.integers(0, min(k, 4) + 1))
+        prefix = None
+        if plen:
+            src = int(rows[int(rng.integers(0, rows.size))])
+            prefix = Kmer(bits=src & ((1 << (2 * plen)) - 1), length=plen)
+        pattern = None
+        if trial % 2 == 0:
+            # mostly N with a few degenerate / exact positions so that some rows survive
+            pat = ["N"] * k
+            for pos in rng.choice(k, size=min(k, 3), replace=False):
+                pat[pos] = str(rng.choice(list(IUPAC)))
+            pattern = "".join(pat)
+        want = R.filter_kmers(words, n, k, prefix=(prefix.bits, prefix.length) if prefix else None,
+                              pattern=pattern)
+        got = gpu.filter_kmers(d, k, prefix=prefix, pattern=pattern).bits
+        assert np.array_equal(got, want), (k, prefix, pattern)
+
+
+def test_filter_every_iupac_code_and_u(gpu):
+    n = 5000
+    words = rand_dna_words(np.random.default_rng(1), n)
+    d = Dna.from_words(words, n)
+    for code in IUPAC:
+        for pos in (0, 2, 4):
+            pat = "".join(code if i == pos else "N" for i in range(5))
+            want = R.filter_kmers(words, n, 5, pattern=pat)
+            got = gpu.filter_kmers(d, 5, pattern=pat).bits
+            assert np.array_equal(got, want), pat
+            if code == "U":
+                assert got.size == 0        # Q4: U matches nothing (dna.c:1070)
+
+
+def test_filter_errors_are_the_references(gpu):
+    d = Dna("ACGTACGTAC")
+    with pytest.raises(DnaError, match="Prefix length cannot exceed kmer length") as e:
+        gpu.filter_kmers(d, 3, prefix="ACGT")
+    assert e.value.code == 2
+    with pytest.raises(DnaError, match="Qkmer pattern and kmer lengths do not match") as e:
+        gpu.filter_kmers(d, 3, pattern="NN")
+    assert e.value.code == 3
+    with pytest.raises(DnaError, match="Invalid character in qkmer pattern: X") as e:
+        gpu.filter_kmers(d, 3, pattern="NXN")
+    assert e.value.code == 4
+    with pytest.raises(DnaError, match="qkmer pattern cannot be empty"):
+        gpu.filter_kmers(d, 3, pattern="")
+    with pytest.raises(DnaError, match="cannot exceed 32 characters"):
+        gpu.filter_kmers(d, 3, pattern="N" * 33)
+    # no rows evaluated -> the per-row ERRORs never fire (dna.c:854, 1106 run per row)
+    assert len(gpu.filter_kmers(Dna("AC"), 3, prefix="ACGT")) == 0
+
+
+def test_prefix_of_32_bases_uses_the_full_mask(gpu):
+    s = "ACGT" * 8 + "GGGG" + "ACGT" * 8
+    d = Dna(s)
+    got = gpu.filter_kmers(d, 32, prefix="ACGT" * 8).strings()       # Q1
+    assert got == ["ACGT" * 8] * 2
+
+
+def test_filter_keys_over_a_kmer_column(gpu):
+    import torch
+    rng = np.random.default_rng(3)
+    k = 5
+    col = rng.integers(0, 4**k, size=100_003, dtype=np.uint64)    # the 1 M-row kmer table of test.sql:168-179
+    dev = torch.from_numpy(col.view(np.int64)).cuda()
+    for prefix, pattern in (("ACTG", None), (None, "MRKYN"), ("AT", "NNSNN")):   # test.sql:223, 253
+        got = gpu.filter_keys(dev, k, prefix=prefix, pattern=pattern).cpu().numpy().view(np.uint64)
+        keep = np.ones(col.size, dtype=bool)
+        if prefix:
+            pb, pl = R.kmer_make(prefix)
+            keep &= (col & np.uint64((1 << (2 * pl)) - 1)) == np.uint64(pb)
+        want = np.array([x for x in col[keep] if pattern is None or R.contains(pattern, int(x), k)], dtype=np.uint64)
+        assert np.array_equal(got, want), (prefix, pattern)
+
+
+# ---- GROUP BY kmer --------------------------------------------------------------------------------
+def _check_count(gpu, seq, oracle, k, **kw):
+    st, table = gpu.count(seq, k, table=True, **kw)
+    assert (st.total, st.distinct, st.unique) == oracle.stats, (k, kw)
+    kmers, counts = table.sorted()
+    assert table.rows == oracle.distinct
+    assert np.array_equal(kmers, oracle.kmers) and np.array_equal(counts, oracle.counts), (k, kw)
+    table.free()
+
+
+@pytest.mark.parametrize("k", [1, 2, 3, 4, 5, 6, 7, 8, 9, 12, 13, 16, 17, 21, 31, 32])
+def test_count_matches_oracle_all_methods(gpu, k):
+    n = 150_001
+    words = R.synth_seq(40 + k, n)                  # planted repeats + G x 64 / A x 64 windows
+    seq = gpu.upload(Dna.from_words(words, n))
+    oracle = R.count_query(words, 1, n, words.size, k, faithful=(k in (3, 21, 32)))
+    _check_count(gpu, seq, oracle, k)                                  # AUTO
+    _check_count(gpu, seq, oracle, k, method=dnagpu.COUNT_HASH)
+    if k <= 12:
+        _check_count(gpu, seq, oracle, k, method=dnagpu.COUNT_DENSE)
+    seq.free()
+
+
+def test_count_k32_all_g_sentinel(gpu):
+    """'G' x 32 has the bit pattern of the hash table's EMPTY marker: it must still be counted."""
+    for s, want_g in (("G" * 32, 1), ("G" * 40 + "ACGT" * 20 + "G" * 33, 11), ("ACGT" * 20, 0)):
+        d = Dna(s)
+        words, n = R.encode_dna(s)
+        oracle = R.count_query(words, 1, n, words.size, 32)
+        st, table = gpu.count_kmers(d, 32)
+        assert (st.total, st.distinct, st.unique) == oracle.stats
+        kmers, counts = table.sorted()
+        assert np.array_equal(kmers, oracle.kmers) and np.array_equal(counts, oracle.counts)
+        got_g = int(counts[kmers == np.uint64(2**64 - 1)].sum())
+        assert got_g == want_g
+
+
+def test_count_with_where_clause_fused(gpu):
+    n = 300_000
+    words = R.synth_seq(77, n)
+    seq = gpu.upload(Dna.from_words(words, n))
+    cases = [(5, "AC", None), (5, None, "MRKYN"), (21, "AC", None), (21, "A", "NNNNNNNNWSNNNNNNNNNRY"),
+             (31, "AC", "NNNNNNNNNNNNWSNNNNNNNNNNNNNNNRY"), (12, None, "SNNNNNNNNNNW"), (31, "T", "U" + "N" * 30)]
+    for k, prefix, pattern in cases:
+        pk = R.kmer_make(prefix) if prefix else None
+        oracle = R.count_query(words, 1, n, words.size, k, prefix=pk, pattern=pattern, faithful=False)
+        _check_count(gpu, seq, oracle, k, prefix=prefix, pattern=pattern)
+    seq.free()
+
+
+def test_count_reads_never_span_rows(gpu):
+    n_reads, bpr, stride = 20_000, 150, 5
+    reads = R.synth_reads(3, n_reads, bpr, stride)
+    seq = gpu.upload_reads(reads, n_reads, bpr, stride)
+    for k, prefix, pattern in ((31, None, None), (31, "AC", None), (12, None, None), (4, None, None),
+                               (31, "AC", "NNNNNNNNNNNNWSNNNNNNNNNNNNNNNRY")):
+        pk = R.kmer_make(prefix) if prefix else None
+        oracle = R.count_query(reads, n_reads, bpr, stride, k, prefix=pk, pattern=pattern, faithful=False)
+        if prefix is None and pattern is None:
+            assert oracle.total == n_reads * (bpr - k + 1)
+        _check_count(gpu, seq, oracle, k, prefix=prefix, pattern=pattern)
+    seq.free()
+    st, table = gpu.count_reads(reads, n_reads, bpr, stride, 31)     # the host-buffer C-ABI call
+    oracle = R.count_query(reads, n_reads, bpr, stride, 31, faithful=False)
+    assert (st.total, st.distinct, st.unique) == oracle.stats
+
+
+def test_count_ragged_table_of_sequences(gpu):
+    """SELECT ... FROM dna_sequences d, generate_kmers(d.sequence, k) GROUP BY kmer (test.sql:140-150)."""
+    rng = np.random.default_rng(8)
+    lens = [int(x) for x in rng.integers(1, 400, size=300)] + [3, 9, 10, 11, 5000]
+    dnas = [Dna.from_words(rand_dna_words(rng, n), n) for n in lens]
+    seq = gpu.upload_ragged(dnas)
+    for k in (10, 3, 32):
+        oracle = R.count_ragged([(d.words, d.length) for d in dnas], k, faithful=False)
+        _check_count(gpu, seq, oracle, k)
+        _check_count(gpu, seq, oracle, k, method=dnagpu.COUNT_HASH)
+    seq.free()
+
+
+def test_count_empty_and_tiny_inputs(gpu):
+    st, table = gpu.count_kmers(Dna("ACG"), 5)
+    assert (st.total, st.distinct, st.unique) == (0, 0, 0) and table.rows == 0
+    st, table = gpu.count_kmers(Dna("A"), 1)
+    assert (st.total, st.distinct, st.unique) == (1, 1, 1)
+    assert table.fetch()[0].tolist() == [0] and table.fetch()[1].tolist() == [1]
+    st, _ = gpu.count_kmers(Dna("ACGTACGT"), 4, prefix="GG", table=False)     # WHERE keeps nothing
+    assert (st.total, st.distinct, st.unique) == (0, 0, 0)
+
+
+def test_count_keys_and_partition_compose_to_the_single_gpu_answer(gpu):
+    """Owner routing (the multi-GPU GROUP BY) on one device: bucket, count each bucket,
+    add the aggregates -- must equal the direct count."""
+    import torch
+    n, k = 400_000, 31
+    words = R.synth_seq(4, n)
+    seq = gpu.upload(Dna.from_words(words, n))
+    oracle = R.count_query(words, 1, n, words.size, k, faithful=False)
+    for parts in (1, 2, 3, 8):
+        buf, counts = gpu.partition(seq, k, parts)
+        assert int(counts.sum()) == oracle.total
+        assert np.array_equal(counts, gpu.partition_counts(seq, k, parts))
+        host = buf.cpu().numpy().view(np.uint64)
+        assert np.array_equal(np.sort(host), np.sort(R.generate_kmers(words, n, k, window=True)))
+        tot = [0, 0, 0]
+        off = 0
+        all_k, all_c = [], []
+        for p in range(parts):
+            c = int(counts[p])
+            part = host[off:off + c]
+            assert all(dnagpu.owner_of(int(x), parts) == p for x in part[:200])
+            st, table = gpu.count_keys(buf[off:off + c], k, table=True)
+            kk, cc = table.fetch()
+            all_k.append(kk); all_c.append(cc)
+            tot[0] += st.total; tot[1] += st.distinct; tot[2] += st.unique
+            off += c
+        assert tuple(tot) == oracle.stats, parts
+        kk = np.concatenate(all_k); cc = np.concatenate(all_c)
+        order = np.argsort(kk)
+        assert np.array_equal(kk[order], oracle.kmers) and np.array_equal(cc[order], oracle.counts)
+    seq.free()
+
+
+def test_shards_with_overlap_cover_the_sequence_once(gpu):
+    """Base-range shards with a (k-1)-base overlap (synth_range + start limit) reproduce the
+    k-mers of the whole sequence exactly once."""
+    n, k, G = 1_000_000, 31, 4
+    words = R.synth_seq(6, n)
+    whole = R.generate_kmers(words, n, k, window=True)
+    per = ((n + G - 1) // G + 31) // 32 * 32
+    pieces = []
+    for g in range(G):
+        first = g * per
+        starts = min(per, max(0, (n - k + 1) - first))
+        seq = gpu.synth_range(n, 6, 8, first, starts, k)
+        assert seq.kmer_count(k) == starts
+        pieces.append(gpu.extract(seq, k).cpu().numpy().view(np.uint64))
+        seq.free()
+    assert np.array_equal(np.concatenate(pieces), whole)
