@@ -1,0 +1,384 @@
+#!/usr/bin/env python
+"""bench.py -- the k-mer hot path on B200, one JSON line per run.
+
+Workload (BASELINE.json configs[3], the one the metric is quoted on): one synthetic
+3.1 Gbp sequence (seeded generator of include/dnagpu_synth.h, every 8th 1024-base block a
+planted repeat), k = 31, `GROUP BY kmer` with total / distinct / unique.  At N > 1 the
+sequence is sharded by base range with a (k-1)-base overlap, k-mers are routed to their
+owner rank by hash (NCCL all-to-all) and each rank counts its partition: total work is
+fixed, so scaling is "strong".
+
+  value   Gkmer/s with the packed words already resident in HBM (table init + extract +
+          count + aggregates; at N > 1 also partition + exchange), CUDA-event timed.
+  e2e     the same query through the host-buffer C-ABI call dnagpu_count_kmers():
+          pinned host words -> H2D -> count -> D2H of the three aggregates, every step.
+  roofline  the dominant kernel (count_hash / count_hash_keys): algorithmic bytes
+          (0.25 B/base read + 16 B slot per k-mer) / its CUDA-event duration.
+  cpu_baseline  the oracle's faithful restatement of dna.c on the host cores, bounded sample.
+
+`--impl reference` times the reference's CPU implementation of the same query
+(oracle/_ref = the reference's own dna.c when it could be compiled, else the oracle port).
+"""
+import argparse
+import ctypes as C
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+PKG = os.path.join(ROOT, "dna-sequences-pg-extension_b200")
+for _p in (ROOT, PKG):
+    if _p not in sys.path:
+        sys.path.insert(0, _p)
+
+WORKLOADS = {
+    # name: (n_bases, k, seed, description)
+    "c4": (3_100_000_000, 31, 4, "3.1 Gbp synthetic sequence, k=31 GROUP BY kmer count + total/distinct/unique"),
+    "c2": (100_000_000, 21, 2, "100 Mbp synthetic sequence, k=21 full count + total/distinct/unique"),
+    "c5": (1_000_000_000, 31, 5, "1 Gbp synthetic sequence, k=31 count"),
+}
+REPEAT_EVERY = 8
+METRIC = "Gkmer/s counted (k=31) at 1/2/4/8 B200; extraction HBM GB/s vs peak"
+
+
+def measured_peaks():
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured"
+    except Exception:
+        return 6650.0, "fallback"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons DURING the timed region."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.proc, self.lines = index, None, []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100",
+                 "-i", str(self.index)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons, pw = [], [], set(), []
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 7:
+                continue
+            try:
+                sm.append(float(f[0])); mx.append(float(f[1])); pw.append(float(f[2]))
+            except ValueError:
+                continue
+            for name, v in zip(names, f[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "power_w_max": max(pw) if pw else None, "samples": len(sm), "reasons": sorted(reasons)}
+
+
+def dist_env():
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    return rank, world, local
+
+
+def shard_of(n_bases, k, world, rank):
+    """Base-range shard: starts [first, first+starts) with first a multiple of 32."""
+    rows = n_bases - k + 1
+    per = ((rows + world - 1) // world + 31) // 32 * 32
+    first = min(rank * per, (rows + 31) // 32 * 32)
+    starts = max(0, min(per, rows - first))
+    return first, starts
+
+
+# ============================== the reference arm ==============================
+def cpu_reference_rate(n_bases, k, seed, threads, sample_bases, faithful=True):
+    """Time the CPU restatement of the reference's query on a prefix of the workload."""
+    from oracle import ref_cpu as R
+    words = R.synth_seq(seed, n_bases, REPEAT_EVERY, first_word=0, n_words=(sample_bases + 31) // 32)
+    t0 = time.perf_counter()
+    r = R.count_query(words, 1, sample_bases, words.size, k, faithful=faithful, threads=threads,
+                      want_rows=False, expected_keys=sample_bases // max(1, threads))
+    dt = time.perf_counter() - t0
+    return r.total / dt / 1e9, dt, r
+
+
+def run_reference(args):
+    rank, world, local = dist_env()
+    if rank != 0:
+        return 0
+    n_bases, k, seed, desc = WORKLOADS[args.workload]
+    threads = max(1, min(os.cpu_count() or 1, 64))
+    # calibrate the per-step sample so that the whole run ends within a few minutes
+    rate, dt, _ = cpu_reference_rate(n_bases, k, seed, threads, 4_000_000)
+    budget_s = max(1.0, min(6.0, 150.0 / max(1, args.steps + args.warmup)))
+    sample = int(max(4_000_000, min(64_000_000, rate * 1e9 * budget_s)))
+    for _ in range(args.warmup):
+        cpu_reference_rate(n_bases, k, seed, threads, sample)
+    times, total = [], 0
+    for _ in range(args.steps):
+        _, dt, r = cpu_reference_rate(n_bases, k, seed, threads, sample)
+        times.append(dt)
+        total += r.total
+    wall = sum(times)
+    value = total / wall / 1e9
+    kind = "port"
+    sample_desc = (f"first {sample} bases of the workload per step, faithful per-k-mer decode/validate/encode "
+                   f"(dna.c:803-825) + kmer_hash/kmer_eq hash aggregate, {threads} threads "
+                   "(Postgres itself would run this serially: generate_kmers is PARALLEL UNSAFE)")
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": "Gkmer/s", "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * wall / max(1, args.steps),
+        "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "u64", "data": "synthetic",
+        "config": {"workload": desc, "n_bases": n_bases, "k": k, "seed": seed, "repeat_every": REPEAT_EVERY,
+                   "sample_bases_per_step": sample},
+        "cpu_baseline": {"value": value, "unit": "Gkmer/s", "cores": threads, "kind": kind, "sample": sample_desc},
+        "e2e": {"value": value, "unit": "Gkmer/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+    return 0
+
+
+# ================================= our arm =====================================
+def run_b200(args):
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+    import dnagpu
+
+    rank, world, local = dist_env()
+    n_bases, k, seed, desc = WORKLOADS[args.workload]
+    if args.n_bases:
+        n_bases = args.n_bases
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    stream = torch.cuda.Stream(device=dev)
+    peak, peak_src = measured_peaks()
+
+    with torch.cuda.stream(stream):
+        ctx = dnagpu.Context(local, torch_stream=True)
+        first, starts = shard_of(n_bases, k, world, rank)
+        seq = ctx.synth_range(n_bases, seed, REPEAT_EVERY, first, starts, k)
+        n_rows_local = seq.kmer_count(k)
+        n_rows_total = n_bases - k + 1
+        n_words_local = seq.n_words
+        # host copy of this rank's packed words, pinned (the dna value a backend would hold)
+        host = torch.empty(n_words_local + 2, dtype=torch.int64, pin_memory=True)
+        host.zero_()
+        ctx.synchronize()
+        rc = ctx.lib.dnagpu_seq_download(ctx.handle, seq.handle, C.c_void_p(host.data_ptr()), n_words_local)
+        assert rc == 0
+        local_bases = min(n_bases - first, starts + k - 1)
+
+        def barrier():
+            if world > 1:
+                dist.barrier(device_ids=[local])
+            torch.cuda.synchronize(dev)
+
+        send_buf = recv_buf = None
+        if world > 1:
+            send_buf = torch.empty(n_rows_local + 2, dtype=torch.int64, device=dev)
+
+        def count_resident(s):
+            """One pass of the hot path with the packed words resident in HBM -> (total, distinct, unique)."""
+            nonlocal recv_buf
+            if world == 1:
+                st, _ = ctx.count(s, k, table=False, load_factor=args.load_factor)
+                return st.total, st.distinct, st.unique
+            out, counts = ctx.partition(s, k, world, out=send_buf)
+            send_counts = torch.from_numpy(counts.astype(np.int64)).to(dev)
+            recv_counts = torch.empty_like(send_counts)
+            dist.all_to_all_single(recv_counts, send_counts)
+            rc_host = recv_counts.cpu().tolist()
+            n_recv = int(sum(rc_host))
+            if recv_buf is None or recv_buf.numel() < n_recv + 2:
+                recv_buf = torch.empty(int(n_recv * 1.05) + 2, dtype=torch.int64, device=dev)
+            dist.all_to_all_single(recv_buf[:n_recv], out, rc_host, [int(c) for c in counts])
+            st, _ = ctx.count_keys(recv_buf[:n_recv], k, table=False, load_factor=args.load_factor)
+            agg = torch.tensor([st.total, st.distinct, st.unique], dtype=torch.int64, device=dev)
+            dist.all_reduce(agg)
+            t = agg.cpu().tolist()
+            return t[0], t[1], t[2]
+
+        def count_e2e():
+            """The reference-facing call: host words in, aggregates out (H2D and D2H inside)."""
+            if world == 1:
+                st = ctx.count_kmers_ptr(C.c_void_p(host.data_ptr()), local_bases, k)
+                return st.total, st.distinct, st.unique
+            s = ctx.upload_words(C.c_void_p(host.data_ptr()), local_bases)
+            s.set_start_limit(starts)
+            r = count_resident(s)
+            s.free()
+            return r
+
+        # ---- value leg: resident inputs, CUDA events ----
+        for _ in range(args.warmup):
+            stats = count_resident(seq)
+        ctx.profile(True)
+        ctx.profile_reset()
+        sampler = ClockSampler(local)
+        barrier()
+        if rank == 0:
+            sampler.start()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(stream)
+        for _ in range(args.steps):
+            stats = count_resident(seq)
+        e1.record(stream)
+        barrier()
+        clocks = sampler.stop() if rank == 0 else None
+        ms = e0.elapsed_time(e1)
+        kernels = ctx.profile_dump()
+        ctx.profile(False)
+        ctx.profile_reset()
+
+        # ---- e2e leg: host buffers through the C ABI, wall clock around synchronous calls ----
+        for _ in range(min(args.warmup, 2)):
+            count_e2e()
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(args.e2e_steps):
+            stats_e2e = count_e2e()
+        barrier()
+        e2e_s = time.perf_counter() - t0
+
+        # ---- extraction GB/s (the second half of the metric), timed on its own ----
+        extract = None
+        if not args.no_extract:
+            xs_bases = min(local_bases, 1_000_000_000)
+            xs = ctx.synth_range(n_bases, seed, REPEAT_EVERY, first, max(0, xs_bases - k + 1), k)
+            xr = xs.kmer_count(k)
+            xout = torch.empty(xr + 2, dtype=torch.int64, device=dev)
+            for _ in range(3):
+                ctx.extract(xs, k, out=xout)
+            x0, x1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            torch.cuda.synchronize(dev)
+            x0.record(stream)
+            xn = 10
+            for _ in range(xn):
+                ctx.extract(xs, k, out=xout)
+            x1.record(stream)
+            torch.cuda.synchronize(dev)
+            xms = x0.elapsed_time(x1) / xn
+            xbytes = 0.25 * xs_bases + 8.0 * xr
+            extract = {"rows": xr, "ms": xms, "gkmer_s": xr / xms / 1e6, "gbs": xbytes / xms / 1e6,
+                       "frac": xbytes / xms / 1e6 / peak, "bytes_per_row": 8.25,
+                       "note": "output (8 B/row) larger than L2; 10 back-to-back launches"}
+            del xout
+            xs.free()
+
+    # ---- reduce over ranks ----
+    if world > 1:
+        t = torch.tensor([ms, e2e_s], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms, e2e_s = t.tolist()
+    assert stats[0] == n_rows_total, (stats, n_rows_total)
+    assert tuple(stats) == tuple(stats_e2e), (stats, stats_e2e)
+
+    if rank == 0:
+        value = n_rows_total * args.steps / (ms * 1e-3) / 1e9
+        e2e_value = n_rows_total * args.e2e_steps / e2e_s / 1e9
+        dom = "count_hash" if world == 1 else "count_hash_keys"
+        d = kernels.get(dom, {"ms": 0.0, "launches": 0})
+        launches = sum(v["launches"] for v in kernels.values())
+        roofline = None
+        if d["launches"]:
+            per_launch_ms = d["ms"] / d["launches"]
+            rows_per_launch = n_rows_total / world  # owner partitions are uniform to < 0.1 %
+            alg_bytes = (0.25 * local_bases if world == 1 else 8.0 * rows_per_launch) + 16.0 * rows_per_launch
+            achieved = alg_bytes / per_launch_ms / 1e6
+            traffic = None
+            try:
+                with open(os.path.join(ROOT, "profiles", "traffic.json")) as f:
+                    traffic = json.load(f).get(f"{args.workload}:{dom}")
+            except Exception:
+                pass
+            roofline = {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak, "unit": "GB/s",
+                        "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
+                        "algorithmic_bytes_per_launch": alg_bytes, "ms_per_launch": per_launch_ms,
+                        "share_of_step": d["ms"] / ms}
+        cpu = None
+        if world == 1 or True:
+            threads = max(1, min(os.cpu_count() or 1, 64))
+            sample = args.cpu_sample
+            cv, cdt, cr = cpu_reference_rate(n_bases, k, seed, threads, sample)
+            cpu = {"value": cv, "unit": "Gkmer/s", "cores": threads, "kind": "port",
+                   "sample": f"first {sample} bases of the workload ({cdt:.1f} s): faithful per-k-mer "
+                             "decode/validate/encode of dna.c:803-825 + kmer_hash/kmer_eq hash aggregate"}
+        line = {
+            "metric": METRIC, "value": value, "unit": "Gkmer/s", "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True,
+            "scaling": "strong", "vs_baseline": None, "dtype": "u64", "data": "synthetic",
+            "config": {"workload": desc, "n_bases": n_bases, "k": k, "seed": seed,
+                       "repeat_every": REPEAT_EVERY, "block_bases": 1024,
+                       "l2": "inputs (packed words + hash table) larger than L2; no flush needed",
+                       "parallelism": "single GPU" if world == 1 else
+                       f"{world} base-range shards + owner-hash all-to-all (NCCL)",
+                       "load_factor": args.load_factor or 0.5},
+            "result": {"total": stats[0], "distinct": stats[1], "unique": stats[2]},
+            "e2e": {"value": e2e_value, "unit": "Gkmer/s", "steps": args.e2e_steps,
+                    "ms_per_step": 1e3 * e2e_s / args.e2e_steps,
+                    "h2d_bytes_per_step": int(8 * ((n_bases + 31) // 32)), "d2h_bytes_per_step": 24 * world,
+                    "api": "dnagpu_count_kmers(ctx, host_words, n_bases, k, NULL, &stats, NULL)"},
+            "gpu_launches": launches, "kernels": kernels, "roofline": roofline, "cpu_baseline": cpu,
+            "extract": extract, "clocks": clocks,
+        }
+        print(json.dumps(line), flush=True)
+    seq.free()
+    ctx.close()
+    if world > 1:
+        dist.destroy_process_group()
+    return 0
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--workload", default="c4", choices=sorted(WORKLOADS))
+    ap.add_argument("--n-bases", type=int, default=0, help="override the workload size (debugging)")
+    ap.add_argument("--e2e-steps", type=int, default=3)
+    ap.add_argument("--load-factor", type=float, default=0.0)
+    ap.add_argument("--cpu-sample", type=int, default=64_000_000)
+    ap.add_argument("--no-extract", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
+    if args.impl == "reference":
+        return run_reference(args)
+    return run_b200(args)
+
+
+if __name__ == "__main__":
+    sys.exit(main())
