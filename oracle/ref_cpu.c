@@ -353,6 +353,10 @@ struct ref_agg {
     uint64_t cap; /* power of two */
     uint64_t groups;
     int k;
+    /* after a multi-threaded query the groups live in n_shards disjoint sub-aggregates
+     * (shard = hash >> 8 mod n_shards); every reader below walks them */
+    int n_shards;
+    struct ref_agg **shards;
 };
 
 static uint64_t ref_pow2_at_least(uint64_t x)
@@ -378,7 +382,10 @@ ref_agg *ref_agg_new(uint64_t expected_keys)
 
 void ref_agg_free(ref_agg *agg)
 {
+    int t;
     if (!agg) return;
+    for (t = 0; t < agg->n_shards; t++) ref_agg_free(agg->shards[t]);
+    free(agg->shards);
     free(agg->slots);
     free(agg);
 }
@@ -389,6 +396,9 @@ int ref_agg_add(ref_agg *agg, uint64_t kmer_bits, uint64_t times)
 {
     uint64_t mask, i;
     if (times == 0) return 0;
+    if (agg->n_shards)
+        return ref_agg_add(agg->shards[(ref_kmer_hash(kmer_bits) >> 8) % (uint32_t)agg->n_shards],
+                           kmer_bits, times);
     if ((agg->groups + 1) * 4 > agg->cap * 3) {
         if (ref_agg_grow(agg) != 0) return -1;
     }
@@ -428,19 +438,33 @@ static int ref_agg_grow(ref_agg *agg)
     return 0;
 }
 
-uint64_t ref_agg_groups(const ref_agg *agg) { return agg->groups; }
+uint64_t ref_agg_groups(const ref_agg *agg)
+{
+    uint64_t g = agg->groups;
+    int t;
+    for (t = 0; t < agg->n_shards; t++) g += agg->shards[t]->groups;
+    return g;
+}
 
 /* README.md:122-130 / test.sql:107-115: sum(count), count(*),
  * count(*) FILTER (WHERE count = 1) over the grouped rows. */
 void ref_agg_stats(const ref_agg *agg, uint64_t *total, uint64_t *distinct, uint64_t *unique)
 {
     uint64_t t = 0, d = 0, u = 0, i;
+    int sh;
     for (i = 0; i < agg->cap; i++) {
         uint64_t c = agg->slots[i].count;
         if (!c) continue;
         t += c;
         d += 1;
         u += (c == 1);
+    }
+    for (sh = 0; sh < agg->n_shards; sh++) {
+        uint64_t t2, d2, u2;
+        ref_agg_stats(agg->shards[sh], &t2, &d2, &u2);
+        t += t2;
+        d += d2;
+        u += u2;
     }
     *total = t;
     *distinct = d;
@@ -459,14 +483,19 @@ static int ref_pair_cmp(const void *a, const void *b)
 
 void ref_agg_sorted(const ref_agg *agg, uint64_t *kmers, uint64_t *counts)
 {
-    ref_pair *p = (ref_pair *)malloc((agg->groups ? agg->groups : 1) * sizeof(ref_pair));
+    uint64_t groups = ref_agg_groups(agg);
+    ref_pair *p = (ref_pair *)malloc((groups ? groups : 1) * sizeof(ref_pair));
     uint64_t i, m = 0;
-    for (i = 0; i < agg->cap; i++)
-        if (agg->slots[i].count) {
-            p[m].key = agg->slots[i].key;
-            p[m].count = agg->slots[i].count;
-            m++;
-        }
+    int sh;
+    for (sh = -1; sh < agg->n_shards; sh++) {
+        const ref_agg *a = sh < 0 ? agg : agg->shards[sh];
+        for (i = 0; i < a->cap; i++)
+            if (a->slots[i].count) {
+                p[m].key = a->slots[i].key;
+                p[m].count = a->slots[i].count;
+                m++;
+            }
+    }
     qsort(p, m, sizeof(ref_pair), ref_pair_cmp);
     for (i = 0; i < m; i++) {
         kmers[i] = p[i].key;
@@ -488,9 +517,13 @@ static inline void ref_digest_step(uint64_t digest[4], uint64_t kmer, uint64_t c
 void ref_agg_digest(const ref_agg *agg, uint64_t digest[4])
 {
     uint64_t i;
+    int sh;
     digest[0] = digest[1] = digest[2] = digest[3] = 0;
-    for (i = 0; i < agg->cap; i++)
-        if (agg->slots[i].count) ref_digest_step(digest, agg->slots[i].key, agg->slots[i].count);
+    for (sh = -1; sh < agg->n_shards; sh++) {
+        const ref_agg *a = sh < 0 ? agg : agg->shards[sh];
+        for (i = 0; i < a->cap; i++)
+            if (a->slots[i].count) ref_digest_step(digest, a->slots[i].key, a->slots[i].count);
+    }
 }
 
 void ref_pairs_digest(const uint64_t *kmers, const uint64_t *counts, uint64_t n,
@@ -566,6 +599,10 @@ int ref_count_query(const uint64_t *words, uint64_t n_seqs, uint64_t bases_per_s
 }
 
 typedef struct ref_mt_job {
+    /* phase 2: shard `shard` of `n_jobs` collects its keys from every private aggregate */
+    struct ref_mt_job *all;
+    int n_jobs, shard;
+    ref_agg *final;
     const uint64_t *words;
     uint64_t seq_first, seq_last, bases_per_seq, stride_words, row_first, row_last;
     int k, prefix_len, faithful, rc;
@@ -580,6 +617,21 @@ static void *ref_mt_main(void *arg)
     j->rc = ref_count_range(j->words, j->seq_first, j->seq_last, j->bases_per_seq,
                             j->stride_words, j->row_first, j->row_last, j->k, j->prefix_bits,
                             j->prefix_len, j->pattern, j->faithful, j->agg);
+    return NULL;
+}
+
+static void *ref_mt_merge(void *arg)
+{
+    ref_mt_job *j = (ref_mt_job *)arg;
+    int t;
+    for (t = 0; t < j->n_jobs; t++) {
+        const ref_agg *a = j->all[t].agg;
+        uint64_t i;
+        for (i = 0; i < a->cap; i++)
+            if (a->slots[i].count &&
+                (int)((ref_kmer_hash(a->slots[i].key) >> 8) % (uint32_t)j->n_jobs) == j->shard)
+                ref_agg_add(j->final, a->slots[i].key, a->slots[i].count);
+    }
     return NULL;
 }
 
@@ -619,19 +671,41 @@ int ref_count_query_mt(const uint64_t *words, uint64_t n_seqs, uint64_t bases_pe
             j->row_first = 0;
             j->row_last = UINT64_MAX;
         }
-        j->agg = ref_agg_new((n_seqs * rows) / (uint64_t)threads / 2 + 1024);
+        j->agg = ref_agg_new((n_seqs * rows) / (uint64_t)threads + 1024);
         pthread_create(&tids[t], NULL, ref_mt_main, j);
     }
     agg->k = k;
     for (t = 0; t < threads; t++) {
-        uint64_t i;
         pthread_join(tids[t], NULL);
         if (jobs[t].rc != REF_OK) rc = jobs[t].rc;
-        for (i = 0; i < jobs[t].agg->cap; i++)
-            if (jobs[t].agg->slots[i].count)
-                ref_agg_add(agg, jobs[t].agg->slots[i].key, jobs[t].agg->slots[i].count);
-        ref_agg_free(jobs[t].agg);
     }
+    /* phase 2: merge in parallel into `threads` disjoint shards of the caller's aggregate */
+    if (agg->n_shards == 0) {
+        agg->shards = (ref_agg **)calloc((size_t)threads, sizeof(ref_agg *));
+        agg->n_shards = threads;
+        for (t = 0; t < threads; t++) {
+            agg->shards[t] = ref_agg_new((n_seqs * rows) / (uint64_t)threads + 1024);
+            agg->shards[t]->k = k;
+        }
+    }
+    if (agg->n_shards == threads) {
+        for (t = 0; t < threads; t++) {
+            jobs[t].all = jobs;
+            jobs[t].n_jobs = threads;
+            jobs[t].shard = t;
+            jobs[t].final = agg->shards[t];
+            pthread_create(&tids[t], NULL, ref_mt_merge, &jobs[t]);
+        }
+        for (t = 0; t < threads; t++) pthread_join(tids[t], NULL);
+    } else { /* shard count differs from an earlier call: plain serial merge */
+        for (t = 0; t < threads; t++) {
+            uint64_t i;
+            for (i = 0; i < jobs[t].agg->cap; i++)
+                if (jobs[t].agg->slots[i].count)
+                    ref_agg_add(agg, jobs[t].agg->slots[i].key, jobs[t].agg->slots[i].count);
+        }
+    }
+    for (t = 0; t < threads; t++) ref_agg_free(jobs[t].agg);
     free(jobs);
     free(tids);
     return rc;
