@@ -19,6 +19,7 @@
 #include <vector>
 
 #include "kernels.cuh"
+#include "partition.cuh"
 
 using namespace dnagpu;
 
@@ -242,6 +243,22 @@ extern "C" int dnagpu_create(dnagpu_ctx **out, int device)
     SMEM_ATTR((k_count_dense_smem<kRagged, false, unsigned long long>));
     SMEM_ATTR((k_count_dense_smem<kRagged, true, unsigned long long>));
 #undef SMEM_ATTR
+    {
+        const int psmem = kTileKeys * (int)sizeof(uint64_t) + (int)sizeof(ScatterSmem);
+#define PSMEM_ATTR(kern) cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, psmem)
+        PSMEM_ATTR((k_part_scatter_seq<kSingle, false>));
+        PSMEM_ATTR((k_part_scatter_seq<kSingle, true>));
+        PSMEM_ATTR((k_part_scatter_seq<kFixed, false>));
+        PSMEM_ATTR((k_part_scatter_seq<kFixed, true>));
+        PSMEM_ATTR((k_part_scatter_seq<kRagged, false>));
+        PSMEM_ATTR((k_part_scatter_seq<kRagged, true>));
+        PSMEM_ATTR(k_part_scatter_keys<false>);
+        PSMEM_ATTR(k_part_scatter_keys<true>);
+#undef PSMEM_ATTR
+        const int bsmem = kBucketSlots * 12;
+        cudaFuncSetAttribute(k_count_buckets<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, bsmem);
+        cudaFuncSetAttribute(k_count_buckets<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, bsmem);
+    }
     CU(nullptr, cudaGetLastError());
     *out = ctx;
     return DNAGPU_OK;
@@ -946,10 +963,13 @@ static uint64_t pow4_capped(int k) { return k >= 32 ? UINT64_MAX : (1ull << (2 *
 static int pick_method(const dnagpu_count_opts *opts, int k, uint64_t n)
 {
     int m = opts ? opts->method : DNAGPU_COUNT_AUTO;
-    if (m == DNAGPU_COUNT_PARTITION) m = DNAGPU_COUNT_HASH; /* not split out yet: see DESIGN.md */
     if (m == DNAGPU_COUNT_DENSE && k > 16) m = DNAGPU_COUNT_HASH;
     if (m != DNAGPU_COUNT_AUTO) return m;
-    /* dense when the 4^k counters are no bigger than a hash table of the input */
+    /* measured on 1 Gbp (profiles/r01a_ksweep): shared-memory / L2-resident dense counters
+     * (k <= 12) run at 200-1400 Gkmer/s; dense or hash tables that live in HBM (k >= 13)
+     * drop to 15-30 Gkmer/s, where partition + shared-memory count wins by > 5x. */
+    if (k <= 12 && pow4_capped(k) <= std::max<uint64_t>(1ull << 16, 8 * n)) return DNAGPU_COUNT_DENSE;
+    if (n >= (1ull << 21)) return DNAGPU_COUNT_PARTITION;
     if (k <= 16 && pow4_capped(k) <= std::max<uint64_t>(1ull << 16, 8 * n)) return DNAGPU_COUNT_DENSE;
     return DNAGPU_COUNT_HASH;
 }
@@ -1080,6 +1100,191 @@ static int count_hash(dnagpu_ctx *ctx, const CountInput &in, int k, const dnagpu
     return DNAGPU_OK;
 }
 
+/* exclusive scan of n u64 (out has n + 1 entries); multi-CTA above 16 K entries */
+static int scan_any(dnagpu_ctx *ctx, Scratch &sc, const uint64_t *in, uint64_t n, uint64_t *out)
+{
+    if (n <= 16384)
+        return launch(ctx, "scan", [&] { k_scan_u64<<<1, 1024, 0, ctx->stream>>>(in, n, out); });
+    const unsigned blocks = grid_for(n, 1024 * kScanPer);
+    uint64_t *sums, *offs;
+    TRY(sc.get((void **)&sums, ((uint64_t)blocks + 1) * 8));
+    TRY(sc.get((void **)&offs, ((uint64_t)blocks + 1) * 8));
+    TRY(launch(ctx, "scan", [&] { k_scan_block<<<blocks, 1024, 0, ctx->stream>>>(in, n, out, sums); }));
+    TRY(launch(ctx, "scan", [&] { k_scan_u64<<<1, 1024, 0, ctx->stream>>>(sums, blocks, offs); }));
+    TRY(launch(ctx, "scan", [&] { k_scan_add<<<blocks, 1024, 0, ctx->stream>>>(out, n, offs); }));
+    return DNAGPU_OK;
+}
+
+static int ceil_log2(uint64_t x)
+{
+    int b = 0;
+    while (b < 63 && (1ull << b) < x) ++b;
+    return b;
+}
+/* number of hash bits so that a bucket averages (1024, 2048] keys (4096-slot table) */
+static int bucket_bits(uint64_t n) { return std::max(1, std::min(22, ceil_log2((n + 2047) / 2048))); }
+
+/* tile prefix sums of a partitioned key array: out_tile_off[n_parents + 1] */
+static int part_tiles(dnagpu_ctx *ctx, Scratch &sc, const uint64_t *parent_off, uint64_t n_parents,
+                      uint64_t tile_keys, uint64_t **out_tile_off)
+{
+    uint64_t *tiles;
+    TRY(sc.get((void **)&tiles, (n_parents + 1) * 8));
+    TRY(sc.get((void **)out_tile_off, (n_parents + 1) * 8));
+    TRY(launch(ctx, "part_tiles", [&] {
+        k_part_tiles<<<grid_for(n_parents, kThreads), kThreads, 0, ctx->stream>>>(parent_off, n_parents,
+                                                                                tile_keys, tiles);
+    }));
+    return scan_any(ctx, sc, tiles, n_parents, *out_tile_off);
+}
+
+/* GROUP BY kmer by radix partition + shared-memory count (partition.cuh) */
+static int count_partition(dnagpu_ctx *ctx, const CountInput &in, int k, dnagpu_stats *stats,
+                           dnagpu_table **table)
+{
+    const uint64_t mask = kmer_mask(k);
+    const int psmem = kTileKeys * (int)sizeof(uint64_t) + (int)sizeof(ScatterSmem);
+    Scratch sc(ctx);
+    uint64_t n = in.n; /* upper bound; exact after the level-1 histogram when a WHERE clause is fused */
+    const int b_bound = bucket_bits(n);
+    const int b1 = b_bound <= 11 ? b_bound : b_bound / 2;
+    const uint32_t P1 = 1u << b1;
+    const int shift1 = 64 - b1;
+    TRY(zero_counters(ctx));
+
+    /* ---- level 1: histogram, offsets, scatter ---- */
+    unsigned long long *hist1, *cur1;
+    uint64_t *off1, *root_off;
+    TRY(sc.get((void **)&hist1, (uint64_t)P1 * 8));
+    TRY(sc.get((void **)&cur1, (uint64_t)P1 * 8));
+    TRY(sc.get((void **)&off1, ((uint64_t)P1 + 1) * 8));
+    TRY(sc.get((void **)&root_off, 2 * 8));
+    CU(ctx, cudaMemsetAsync(hist1, 0, (uint64_t)P1 * 8, ctx->stream));
+    CU(ctx, cudaMemsetAsync(cur1, 0, (uint64_t)P1 * 8, ctx->stream));
+    uint64_t *root_tiles_hist = nullptr, *root_tiles_scat = nullptr;
+    if (in.d_keys) {
+        ctx->h_ctr[0] = 0;
+        ctx->h_ctr[1] = n;
+        CU(ctx, cudaMemcpyAsync(root_off, ctx->h_ctr, 16, cudaMemcpyHostToDevice, ctx->stream));
+        CU(ctx, cudaStreamSynchronize(ctx->stream)); /* h_ctr is reused below */
+        TRY(part_tiles(ctx, sc, root_off, 1, kSuperTile, &root_tiles_hist));
+        TRY(part_tiles(ctx, sc, root_off, 1, kTileKeys, &root_tiles_scat));
+        TRY(launch(ctx, "part_hist", [&] {
+            k_part_hist_keys<<<grid_for(n, kSuperTile), kThreads, 0, ctx->stream>>>(
+                in.d_keys, root_off, root_tiles_hist, 1, shift1, P1, hist1);
+        }));
+    } else {
+        const unsigned hgrid = (unsigned)std::min<uint64_t>(grid_for(in.v.n_items, kThreads), (uint64_t)ctx->sm_count * 8);
+        DISPATCH_LAYOUT(in.seq->layout, TRY(launch(ctx, "part_hist", [&] {
+            if (in.filtered)
+                k_part_hist_seq<LY, true><<<hgrid, kThreads, 0, ctx->stream>>>(in.v, in.p, mask, shift1, P1, hist1);
+            else
+                k_part_hist_seq<LY, false><<<hgrid, kThreads, 0, ctx->stream>>>(in.v, in.p, mask, shift1, P1, hist1);
+        })));
+    }
+    TRY(scan_any(ctx, sc, (const uint64_t *)hist1, P1, off1));
+    if (in.filtered) { /* the WHERE clause decides how many keys there are */
+        TRY(read_u64(ctx, off1 + P1, &n));
+    }
+    uint64_t *bufA;
+    TRY(sc.get((void **)&bufA, (n + 2) * 8));
+    if (in.d_keys) {
+        TRY(launch(ctx, "part_scatter", [&] {
+            k_part_scatter_keys<true><<<grid_for(n, kTileKeys), kThreads, psmem, ctx->stream>>>(
+                in.d_keys, root_off, root_tiles_scat, 1, shift1, P1, off1, cur1, bufA, ctx->d_ctr);
+        }));
+    } else {
+        const unsigned grid = grid_for(in.v.n_items, kThreads);
+        DISPATCH_LAYOUT(in.seq->layout, TRY(launch(ctx, "part_scatter", [&] {
+            if (in.filtered)
+                k_part_scatter_seq<LY, true><<<grid, kThreads, psmem, ctx->stream>>>(
+                    in.v, in.p, mask, shift1, P1, off1, cur1, bufA, ctx->d_ctr);
+            else
+                k_part_scatter_seq<LY, false><<<grid, kThreads, psmem, ctx->stream>>>(
+                    in.v, in.p, mask, shift1, P1, off1, cur1, bufA, ctx->d_ctr);
+        })));
+    }
+
+    /* ---- level 2 inside every partition, when buckets are still too big ---- */
+    const int b_exact = bucket_bits(n);
+    const int b2 = std::max(0, std::min(11, b_exact - b1));
+    const uint64_t *bucket_keys = bufA, *bucket_off = off1;
+    uint64_t n_buckets = P1;
+    if (b2 > 0) {
+        const uint32_t P2 = 1u << b2;
+        const int shift2 = 64 - b1 - b2;
+        n_buckets = (uint64_t)P1 * P2;
+        unsigned long long *hist2, *cur2;
+        uint64_t *off2, *tiles_hist, *tiles_scat, *bufB;
+        TRY(sc.get((void **)&hist2, n_buckets * 8));
+        TRY(sc.get((void **)&cur2, n_buckets * 8));
+        TRY(sc.get((void **)&off2, (n_buckets + 1) * 8));
+        TRY(sc.get((void **)&bufB, (n + 2) * 8));
+        CU(ctx, cudaMemsetAsync(hist2, 0, n_buckets * 8, ctx->stream));
+        CU(ctx, cudaMemsetAsync(cur2, 0, n_buckets * 8, ctx->stream));
+        TRY(part_tiles(ctx, sc, off1, P1, kSuperTile, &tiles_hist));
+        TRY(part_tiles(ctx, sc, off1, P1, kTileKeys, &tiles_scat));
+        TRY(launch(ctx, "part_hist2", [&] {
+            k_part_hist_keys<<<grid_for(n, kSuperTile) + P1, kThreads, 0, ctx->stream>>>(
+                bufA, off1, tiles_hist, P1, shift2, P2, hist2);
+        }));
+        TRY(scan_any(ctx, sc, (const uint64_t *)hist2, n_buckets, off2));
+        TRY(launch(ctx, "part_scatter2", [&] {
+            k_part_scatter_keys<false><<<grid_for(n, kTileKeys) + P1, kThreads, psmem, ctx->stream>>>(
+                bufA, off1, tiles_scat, P1, shift2, P2, off2, cur2, bufB, ctx->d_ctr);
+        }));
+        bucket_keys = bufB;
+        bucket_off = off2;
+    }
+
+    /* ---- count every bucket in shared memory ---- */
+    const uint64_t spill_cap = std::max<uint64_t>(1ull << 16, n / 64);
+    Slot *spill;
+    TRY(sc.get((void **)&spill, spill_cap * sizeof(Slot)));
+    TRY(launch(ctx, "table_init", [&] {
+        k_table_init<<<(unsigned)std::min<uint64_t>(grid_for(spill_cap, kThreads), (uint64_t)ctx->sm_count * 8),
+                       kThreads, 0, ctx->stream>>>(spill, spill_cap);
+    }));
+    const int bsmem = kBucketSlots * 12;
+    const unsigned cgrid = (unsigned)std::min<uint64_t>(n_buckets, (uint64_t)ctx->sm_count * 4);
+    TRY(launch(ctx, "count_buckets", [&] {
+        k_count_buckets<false><<<cgrid, kThreads, bsmem, ctx->stream>>>(bucket_keys, bucket_off, n_buckets,
+                                                                       spill, spill_cap, ctx->d_ctr, nullptr, nullptr);
+    }));
+    TRY(fetch_counters(ctx));
+    if (ctx->h_ctr[C_OVERFLOW])
+        return fail(ctx, DNAGPU_EINTERNAL, "spill table of %llu slots overflowed", (unsigned long long)spill_cap);
+    const uint64_t side = ctx->h_ctr[C_SIDE];
+    const uint64_t keyed = ctx->h_ctr[C_DISTINCT];
+    stats->total = ctx->h_ctr[C_TOTAL];
+    stats->distinct = keyed + (side > 0);
+    stats->unique = ctx->h_ctr[C_UNIQUE] + (side == 1);
+    if (table) {
+        TRY(table_new(ctx, k, stats->distinct, table));
+        if (keyed) {
+            CU(ctx, cudaMemsetAsync(ctx->d_ctr + C_CURSOR, 0, 8, ctx->stream));
+            TRY(launch(ctx, "count_buckets_emit", [&] {
+                k_count_buckets<true><<<cgrid, kThreads, bsmem, ctx->stream>>>(
+                    bucket_keys, bucket_off, n_buckets, spill, spill_cap, ctx->d_ctr, (*table)->d_kmers,
+                    (*table)->d_counts);
+            }));
+            TRY(launch(ctx, "table_compact", [&] { /* rows that spilled, appended after the bucket rows */
+                k_table_compact<<<(unsigned)std::min<uint64_t>(grid_for(spill_cap, kThreads), (uint64_t)ctx->sm_count * 8),
+                                  kThreads, 0, ctx->stream>>>(spill, spill_cap, (*table)->d_kmers,
+                                                              (*table)->d_counts, ctx->d_ctr);
+            }));
+        }
+        if (side) {
+            ctx->h_ctr[0] = kEmpty;
+            ctx->h_ctr[1] = side;
+            CU(ctx, cudaMemcpyAsync((*table)->d_kmers + keyed, &ctx->h_ctr[0], 8, cudaMemcpyHostToDevice, ctx->stream));
+            CU(ctx, cudaMemcpyAsync((*table)->d_counts + keyed, &ctx->h_ctr[1], 8, cudaMemcpyHostToDevice, ctx->stream));
+        }
+        CU(ctx, cudaStreamSynchronize(ctx->stream));
+    }
+    return DNAGPU_OK;
+}
+
 static int count_any(dnagpu_ctx *ctx, CountInput &in, int k, const dnagpu_count_opts *opts,
                      dnagpu_stats *stats, dnagpu_table **table)
 {
@@ -1096,6 +1301,8 @@ static int count_any(dnagpu_ctx *ctx, CountInput &in, int k, const dnagpu_count_
     if (method == DNAGPU_COUNT_DENSE) {
         rc = in.n < 0xffffffffull ? count_dense_t<uint32_t>(ctx, in, k, stats, table)
                                   : count_dense_t<unsigned long long>(ctx, in, k, stats, table);
+    } else if (method == DNAGPU_COUNT_PARTITION) {
+        rc = count_partition(ctx, in, k, stats, table);
     } else {
         uint64_t bound = in.n;
         if (in.filtered && !(opts && opts->expected_keys)) {

@@ -212,8 +212,46 @@ def test_count_matches_oracle_all_methods(gpu, k):
     oracle = R.count_query(words, 1, n, words.size, k, faithful=(k in (3, 21, 32)))
     _check_count(gpu, seq, oracle, k)                                  # AUTO
     _check_count(gpu, seq, oracle, k, method=dnagpu.COUNT_HASH)
+    _check_count(gpu, seq, oracle, k, method=dnagpu.COUNT_PARTITION)
     if k <= 12:
         _check_count(gpu, seq, oracle, k, method=dnagpu.COUNT_DENSE)
+    seq.free()
+
+
+@pytest.mark.parametrize("k,n", [(31, 9_000_011), (32, 5_000_000), (21, 9_000_011), (14, 9_000_011)])
+def test_count_partition_two_levels(gpu, k, n):
+    """Inputs large enough that the radix partition needs both levels (> 4 M keys), rows included."""
+    words = R.synth_seq(90 + k, n)
+    seq = gpu.upload(Dna.from_words(words, n))
+    oracle = R.count_query(words, 1, n, words.size, k, faithful=False, threads=8)
+    _check_count(gpu, seq, oracle, k)                                   # AUTO -> partition
+    _check_count(gpu, seq, oracle, k, method=dnagpu.COUNT_PARTITION)
+    filtered = R.count_query(words, 1, n, words.size, k, prefix=R.kmer_make("AC"), faithful=False, threads=8)
+    _check_count(gpu, seq, filtered, k, method=dnagpu.COUNT_PARTITION, prefix="AC")
+    seq.free()
+
+
+def test_count_partition_skewed_input_spills_correctly(gpu):
+    """Low-complexity data: a few k-mers with huge counts plus a bucket with more distinct keys
+    than the shared-memory table holds must still give exact rows."""
+    import torch
+    rng = np.random.default_rng(12)
+    k = 31
+    hot = rng.integers(0, 2**62, size=5, dtype=np.uint64)
+    keys = np.concatenate([np.repeat(hot, 400_000), rng.integers(0, 2**62, size=3_000_000, dtype=np.uint64)])
+    rng.shuffle(keys)
+    dev = torch.from_numpy(keys.view(np.int64)).cuda()
+    uk, uc = np.unique(keys, return_counts=True)
+    for method in (dnagpu.COUNT_PARTITION, dnagpu.COUNT_HASH):
+        st, table = gpu.count_keys(dev, k, table=True, method=method)
+        kk, cc = table.sorted()
+        assert (st.total, st.distinct, st.unique) == (keys.size, uk.size, int((uc == 1).sum()))
+        assert np.array_equal(kk, uk) and np.array_equal(cc, uc.astype(np.uint64))
+    # poly-A: one k-mer, millions of copies
+    seq = gpu.upload(Dna("A" * 3_000_000))
+    st, table = gpu.count(seq, k, table=True, method=dnagpu.COUNT_PARTITION)
+    assert (st.total, st.distinct, st.unique) == (3_000_000 - 30, 1, 0)
+    assert table.fetch()[1].tolist() == [3_000_000 - 30]
     seq.free()
 
 
@@ -305,7 +343,8 @@ def test_count_keys_and_partition_compose_to_the_single_gpu_answer(gpu):
             c = int(counts[p])
             part = host[off:off + c]
             assert all(dnagpu.owner_of(int(x), parts) == p for x in part[:200])
-            st, table = gpu.count_keys(buf[off:off + c], k, table=True)
+            st, table = gpu.count_keys(buf[off:off + c], k, table=True,
+                                       method=dnagpu.COUNT_PARTITION if parts == 2 else dnagpu.COUNT_AUTO)
             kk, cc = table.fetch()
             all_k.append(kk); all_c.append(cc)
             tot[0] += st.total; tot[1] += st.distinct; tot[2] += st.unique
