@@ -13,6 +13,7 @@
 #include <algorithm>
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <new>
 #include <string>
@@ -1122,7 +1123,12 @@ static int ceil_log2(uint64_t x)
     return b;
 }
 /* number of hash bits so that a bucket averages (1024, 2048] keys (4096-slot table) */
-static int bucket_bits(uint64_t n) { return std::max(1, std::min(22, ceil_log2((n + 2047) / 2048))); }
+static int bucket_bits(uint64_t n)
+{
+    if (const char *e = getenv("DNAGPU_BUCKET_BITS")) /* profiling aid: force the fan-out */
+        if (atoi(e) >= 1 && atoi(e) <= 22) return atoi(e);
+    return std::max(1, std::min(22, ceil_log2((n + 2047) / 2048)));
+}
 
 /* tile prefix sums of a partitioned key array: out_tile_off[n_parents + 1] */
 static int part_tiles(dnagpu_ctx *ctx, Scratch &sc, const uint64_t *parent_off, uint64_t n_parents,
@@ -1190,17 +1196,17 @@ static int count_partition(dnagpu_ctx *ctx, const CountInput &in, int k, dnagpu_
     TRY(sc.get((void **)&bufA, (n + 2) * 8));
     if (in.d_keys) {
         TRY(launch(ctx, "part_scatter", [&] {
-            k_part_scatter_keys<true><<<grid_for(n, kTileKeys), kThreads, psmem, ctx->stream>>>(
+            k_part_scatter_keys<true><<<grid_for(n, kTileKeys), kScatThreads, psmem, ctx->stream>>>(
                 in.d_keys, root_off, root_tiles_scat, 1, shift1, P1, off1, cur1, bufA, ctx->d_ctr);
         }));
     } else {
-        const unsigned grid = grid_for(in.v.n_items, kThreads);
+        const unsigned grid = grid_for(in.v.n_items, kScatThreads / 2);
         DISPATCH_LAYOUT(in.seq->layout, TRY(launch(ctx, "part_scatter", [&] {
             if (in.filtered)
-                k_part_scatter_seq<LY, true><<<grid, kThreads, psmem, ctx->stream>>>(
+                k_part_scatter_seq<LY, true><<<grid, kScatThreads, psmem, ctx->stream>>>(
                     in.v, in.p, mask, shift1, P1, off1, cur1, bufA, ctx->d_ctr);
             else
-                k_part_scatter_seq<LY, false><<<grid, kThreads, psmem, ctx->stream>>>(
+                k_part_scatter_seq<LY, false><<<grid, kScatThreads, psmem, ctx->stream>>>(
                     in.v, in.p, mask, shift1, P1, off1, cur1, bufA, ctx->d_ctr);
         })));
     }
@@ -1230,7 +1236,7 @@ static int count_partition(dnagpu_ctx *ctx, const CountInput &in, int k, dnagpu_
         }));
         TRY(scan_any(ctx, sc, (const uint64_t *)hist2, n_buckets, off2));
         TRY(launch(ctx, "part_scatter2", [&] {
-            k_part_scatter_keys<false><<<grid_for(n, kTileKeys) + P1, kThreads, psmem, ctx->stream>>>(
+            k_part_scatter_keys<false><<<grid_for(n, kTileKeys) + P1, kScatThreads, psmem, ctx->stream>>>(
                 bufA, off1, tiles_scat, P1, shift2, P2, off2, cur2, bufB, ctx->d_ctr);
         }));
         bucket_keys = bufB;
@@ -1252,6 +1258,12 @@ static int count_partition(dnagpu_ctx *ctx, const CountInput &in, int k, dnagpu_
                                                                        spill, spill_cap, ctx->d_ctr, nullptr, nullptr);
     }));
     TRY(fetch_counters(ctx));
+#ifdef DNAGPU_PHASE_TIMING
+    fprintf(stderr, "scatter_seq phases (cycles/tile, thread 0): load+rank %.0f | barrier %.0f | plan %.0f | place %.0f+sync | flush %.0f | tiles %llu\n",
+            (double)ctx->h_ctr[100] / ctx->h_ctr[105], (double)ctx->h_ctr[101] / ctx->h_ctr[105],
+            (double)ctx->h_ctr[102] / ctx->h_ctr[105], (double)ctx->h_ctr[103] / ctx->h_ctr[105],
+            (double)ctx->h_ctr[104] / ctx->h_ctr[105], (unsigned long long)ctx->h_ctr[105]);
+#endif
     if (ctx->h_ctr[C_OVERFLOW])
         return fail(ctx, DNAGPU_EINTERNAL, "spill table of %llu slots overflowed", (unsigned long long)spill_cap);
     const uint64_t side = ctx->h_ctr[C_SIDE];

@@ -30,12 +30,18 @@
 
 namespace dnagpu {
 
-constexpr int kTileKeys = kThreads * 32;   /* 8192 keys staged per scatter tile (64 KB)   */
+constexpr int kScatThreads = 512;          /* scatter CTA: 512 threads x 16 keys             */
+constexpr int kScatPer = 16;
+constexpr int kTileKeys = kScatThreads * kScatPer; /* 8192 keys staged per scatter tile (64 KB) */
 constexpr int kSuperTile = kTileKeys * 8;  /* keys per CTA in a histogram pass              */
 constexpr int kMaxFan = 2048;              /* partitions per level                          */
 constexpr int kBucketSlots = 4096;         /* shared-memory table of the count kernel       */
 constexpr uint64_t kSlotMul = 0x9E3779B97F4A7C15ull;
+constexpr uint64_t kPartMul = 0xD6E8FEB86659FD93ull;
 
+/* Partition hash: multiply-shift (universal for the TOP bits, which is all the digits use).
+ * One 64-bit multiply instead of mix64's two: the scatter kernels are issue-bound. */
+__device__ __forceinline__ uint64_t part_hash(uint64_t x) { return x * kPartMul; }
 __device__ __forceinline__ uint32_t digit_of(uint64_t h, int shift, uint32_t fan_mask)
 {
     return (uint32_t)(h >> shift) & fan_mask;
@@ -82,7 +88,7 @@ __global__ void __launch_bounds__(kThreads) k_part_hist_seq(SeqView sv, Pred p, 
             if (FILTER && !pred_ok(p, x)) return;
             x &= mask;
             if (x == kEmpty) return; /* 'G' x 32: side counter, added by the scatter pass */
-            atomicAdd(&h[digit_of(mix64(x), shift, fm)], 1u);
+            atomicAdd(&h[digit_of(part_hash(x), shift, fm)], 1u);
         });
     }
     __syncthreads();
@@ -113,7 +119,7 @@ __global__ void __launch_bounds__(kThreads) k_part_hist_keys(const uint64_t *__r
         }
 #pragma unroll
         for (int u = 0; u < 8; ++u)
-            if (x[u] != kEmpty) atomicAdd(&h[digit_of(mix64(x[u]), shift, fm)], 1u);
+            if (x[u] != kEmpty) atomicAdd(&h[digit_of(part_hash(x[u]), shift, fm)], 1u);
     }
     __syncthreads();
     unsigned long long *dst = hist + parent * fan;
@@ -122,27 +128,31 @@ __global__ void __launch_bounds__(kThreads) k_part_hist_keys(const uint64_t *__r
 }
 
 /* ---- scatter passes ------------------------------------------------------------------------ */
-/* Shared state of one scatter tile.  `cur[d]` first counts, then (after the scan) is the
- * running write position of digit d inside the stage; gdelta[d] turns a stage position into
- * the global output index. */
+/* Shared state of one scatter tile: cur[d] counts the keys of digit d (the value atomicAdd
+ * returns is the key's rank inside its digit), then holds the digit's start in the stage;
+ * gdelta[d] turns a stage position into the global output index. */
 struct ScatterSmem {
-    uint32_t cur[kMaxFan];
+    uint32_t cur[kMaxFan + 1]; /* cur[fan] = dummy bin of the keys that are not scattered */
+    uint32_t warp_tot[kScatThreads / 32 + 1];
     long long gdelta[kMaxFan];
     uint16_t dig[kTileKeys];
-    uint32_t warp_tot[kThreads / 32];
 };
 
-/* after counting: scan cur[], claim the global runs, leave cur[] = stage start per digit */
+/* After counting: exclusive scan of cur[] (it becomes the stage start of every digit) and
+ * one global atomicAdd per non-empty digit to claim its output run.  The atomics' results
+ * stay in registers (gd[]) so that their latency hides behind the placing phase; the
+ * caller hands them to scatter_publish() before the flush. */
+constexpr int kPlanPer = kMaxFan / kScatThreads; /* 4 digits per thread */
+
 __device__ __forceinline__ uint32_t scatter_plan(ScatterSmem &s, uint32_t fan,
                                                  const uint64_t *__restrict__ child_off,
-                                                 unsigned long long *__restrict__ child_cur)
+                                                 unsigned long long *__restrict__ child_cur,
+                                                 long long (&gd)[kPlanPer])
 {
-    /* exclusive scan of cur[0..fan) with kThreads threads, fan <= 8 * kThreads */
-    const int per = kMaxFan / kThreads; /* 8 */
-    uint32_t v[per], sum = 0;
-    const uint32_t base = threadIdx.x * per;
+    uint32_t v[kPlanPer], sum = 0;
+    const uint32_t base = threadIdx.x * kPlanPer;
 #pragma unroll
-    for (int i = 0; i < per; ++i) {
+    for (int i = 0; i < kPlanPer; ++i) {
         v[i] = base + i < fan ? s.cur[base + i] : 0;
         sum += v[i];
     }
@@ -157,81 +167,139 @@ __device__ __forceinline__ uint32_t scatter_plan(ScatterSmem &s, uint32_t fan,
     __syncthreads();
     uint32_t woff = 0, total = 0;
 #pragma unroll
-    for (int i = 0; i < kThreads / 32; ++i) {
+    for (int i = 0; i < kScatThreads / 32; ++i) {
         uint32_t t = s.warp_tot[i];
         if (i < wid) woff += t;
         total += t;
     }
     uint32_t ex = woff + inc - sum;
 #pragma unroll
-    for (int i = 0; i < per; ++i) {
+    for (int i = 0; i < kPlanPer; ++i) {
+        gd[i] = 0;
         if (base + i < fan) {
             s.cur[base + i] = ex;
             if (v[i])
-                s.gdelta[base + i] = (long long)(child_off[base + i] +
-                                                 atomicAdd(&child_cur[base + i], (unsigned long long)v[i])) -
-                                     (long long)ex;
+                gd[i] = (long long)(child_off[base + i] +
+                                    atomicAdd(&child_cur[base + i], (unsigned long long)v[i])) -
+                        (long long)ex;
         }
         ex += v[i];
     }
+    if (threadIdx.x == 0) s.cur[fan] = 0;
     __syncthreads();
     return total;
 }
 
+__device__ __forceinline__ void scatter_publish(ScatterSmem &s, uint32_t fan, const long long (&gd)[kPlanPer])
+{
+    const uint32_t base = threadIdx.x * kPlanPer;
+#pragma unroll
+    for (int i = 0; i < kPlanPer; ++i)
+        if (base + i < fan) s.gdelta[base + i] = gd[i];
+}
+
+/* stage -> global: consecutive threads copy consecutive stage entries, i.e. whole runs */
 __device__ __forceinline__ void scatter_flush(const ScatterSmem &s, const uint64_t *stage, uint32_t total,
                                               uint64_t *__restrict__ out)
 {
-    for (uint32_t i = threadIdx.x; i < total; i += kThreads)
-        out[(uint64_t)(s.gdelta[s.dig[i]] + (long long)i)] = stage[i];
+#pragma unroll
+    for (int u = 0; u < kScatPer; ++u) {
+        const uint32_t i = (uint32_t)u * kScatThreads + threadIdx.x;
+        if (i < total) out[(uint64_t)(s.gdelta[s.dig[i]] + (long long)i)] = stage[i];
+    }
 }
 
+/* one thread = HALF an item: 16 consecutive start positions of one packed word.
+ * Straight-line code: a key that is not scattered (past the end, rejected by the WHERE
+ * clause, or the k = 32 sentinel) is ranked into the dummy bin cur[fan] and its stores
+ * are predicated off, so the 16-step loops carry no branches. */
 template <int L, bool FILTER>
-__global__ void __launch_bounds__(kThreads) k_part_scatter_seq(SeqView sv, Pred p, uint64_t mask, int shift,
-                                                               uint32_t fan,
-                                                               const uint64_t *__restrict__ child_off,
-                                                               unsigned long long *__restrict__ child_cur,
-                                                               uint64_t *__restrict__ out,
-                                                               unsigned long long *__restrict__ ctr)
+__global__ void __launch_bounds__(kScatThreads, 2) k_part_scatter_seq(SeqView sv, Pred p, uint64_t mask, int shift,
+                                                                      uint32_t fan,
+                                                                      const uint64_t *__restrict__ child_off,
+                                                                      unsigned long long *__restrict__ child_cur,
+                                                                      uint64_t *__restrict__ out,
+                                                                      unsigned long long *__restrict__ ctr)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     uint64_t *stage = reinterpret_cast<uint64_t *>(smem_raw);
     ScatterSmem &s = *reinterpret_cast<ScatterSmem *>(smem_raw + sizeof(uint64_t) * kTileKeys);
-    for (uint32_t i = threadIdx.x; i < fan; i += kThreads) s.cur[i] = 0;
+#ifdef DNAGPU_PHASE_TIMING
+    long long tq[6];
+    tq[0] = clock64();
+#define PHASE_MARK(i) tq[i] = clock64()
+#else
+#define PHASE_MARK(i)
+#endif
+    for (uint32_t i = threadIdx.x; i <= fan; i += kScatThreads) s.cur[i] = 0;
     __syncthreads();
     const uint32_t fm = fan - 1;
-    uint64_t t = (uint64_t)blockIdx.x * kThreads + threadIdx.x;
-    uint64_t w0 = 0, w1 = 0;
+    const uint64_t t = (uint64_t)blockIdx.x * (kScatThreads / 2) + (threadIdx.x >> 1);
+    const int half = threadIdx.x & 1;
+    uint64_t a0 = 0, a1 = 0; /* the 16 windows of this half start at bit 0 of a0 */
     int c = 0;
     uint32_t side = 0, kept = 0;
+    uint32_t rk[kScatPer / 2]; /* two 16-bit ranks per register; the digit is recomputed */
     if (t < sv.n_items) {
         uint64_t row0;
-        const uint64_t *w = locate_item<L>(sv, t, c, row0);
-        w0 = ld_nc(w);
-        w1 = ld_nc(w + 1);
-        roll_item<8>(w0, w1, c, [&](uint64_t x, int) {
-            if (FILTER && !pred_ok(p, x)) return;
-            kept++;
-            x &= mask;
-            if (x == kEmpty) {
-                side++;
-                return;
-            }
-            atomicAdd(&s.cur[digit_of(mix64(x), shift, fm)], 1u);
-        });
+        int cc;
+        const uint64_t *w = locate_item<L>(sv, t, cc, row0);
+        uint64_t w0 = ld_nc(w), w1 = ld_nc(w + 1);
+        a0 = half ? (w0 >> 32) | (w1 << 32) : w0;
+        a1 = half ? (w1 >> 32) : w1;
+        c = min(16, max(0, cc - 16 * half));
     }
+    uint32_t real_mask = 0; /* bit j: start j is scattered */
+    {
+        uint64_t cur = a0, nxt = a1;
+#pragma unroll
+        for (int j = 0; j < kScatPer; ++j) {
+            const uint64_t x = cur & mask;
+            const bool keep = (j < c) & (!FILTER || pred_ok(p, cur));
+            const bool real = keep & (x != kEmpty);
+            kept += keep;
+            side += keep & !real;
+            real_mask |= (uint32_t)real << j;
+            const uint32_t d = real ? digit_of(part_hash(x), shift, fm) : fan;
+            const uint32_t r = atomicAdd(&s.cur[d], 1u);
+            rk[j >> 1] = (j & 1) ? __byte_perm(rk[j >> 1], r, 0x5410) : r;
+            cur = (cur >> 2) | (nxt << 62);
+            nxt >>= 2;
+        }
+    }
+    PHASE_MARK(1);
     __syncthreads();
-    const uint32_t total = scatter_plan(s, fan, child_off, child_cur);
-    roll_item<8>(w0, w1, c, [&](uint64_t x, int) {
-        if (FILTER && !pred_ok(p, x)) return;
-        x &= mask;
-        if (x == kEmpty) return;
-        uint32_t d = digit_of(mix64(x), shift, fm);
-        uint32_t pos = atomicAdd(&s.cur[d], 1u);
-        stage[pos] = x;
-        s.dig[pos] = (uint16_t)d;
-    });
+    PHASE_MARK(2);
+    long long gd[kPlanPer];
+    const uint32_t total = scatter_plan(s, fan, child_off, child_cur, gd);
+    PHASE_MARK(3);
+    {
+        uint64_t cur = a0, nxt = a1;
+#pragma unroll
+        for (int j = 0; j < kScatPer; ++j) {
+            const uint64_t x = cur & mask;
+            const uint32_t r = (j & 1) ? (rk[j >> 1] >> 16) : (rk[j >> 1] & 0xffffu);
+            const uint32_t d = digit_of(part_hash(x), shift, fm);
+            const uint32_t pos = (s.cur[d] + r) & (kTileKeys - 1);
+            if (real_mask & (1u << j)) {
+                stage[pos] = x;
+                s.dig[pos] = (uint16_t)d;
+            }
+            cur = (cur >> 2) | (nxt << 62);
+            nxt >>= 2;
+        }
+    }
+    scatter_publish(s, fan, gd);
     __syncthreads();
+    PHASE_MARK(4);
     scatter_flush(s, stage, total, out);
+    PHASE_MARK(5);
+#ifdef DNAGPU_PHASE_TIMING
+    if (threadIdx.x == 0) {
+        for (int i = 0; i < 5; ++i) atomicAdd(&ctr[100 + i], (unsigned long long)(tq[i + 1] - tq[i]));
+        atomicAdd(&ctr[105], 1ull);
+    }
+#endif
     kept = warp_sum32(kept);
     side = warp_sum32(side);
     if ((threadIdx.x & 31) == 0) {
@@ -243,48 +311,56 @@ __global__ void __launch_bounds__(kThreads) k_part_scatter_seq(SeqView sv, Pred 
 /* scatter the keys of every parent partition into its children: out[child_off[parent*fan+d] ...].
  * COUNT_SIDE: first level over a raw key list (the caller's keys may hold 'G' x 32). */
 template <bool COUNT_SIDE>
-__global__ void __launch_bounds__(kThreads) k_part_scatter_keys(const uint64_t *__restrict__ keys,
-                                                                const uint64_t *__restrict__ parent_off,
-                                                                const uint64_t *__restrict__ tile_off,
-                                                                uint64_t n_parents, int shift, uint32_t fan,
-                                                                const uint64_t *__restrict__ child_off,
-                                                                unsigned long long *__restrict__ child_cur,
-                                                                uint64_t *__restrict__ out,
-                                                                unsigned long long *__restrict__ ctr)
+__global__ void __launch_bounds__(kScatThreads, 2) k_part_scatter_keys(const uint64_t *__restrict__ keys,
+                                                                       const uint64_t *__restrict__ parent_off,
+                                                                       const uint64_t *__restrict__ tile_off,
+                                                                       uint64_t n_parents, int shift, uint32_t fan,
+                                                                       const uint64_t *__restrict__ child_off,
+                                                                       unsigned long long *__restrict__ child_cur,
+                                                                       uint64_t *__restrict__ out,
+                                                                       unsigned long long *__restrict__ ctr)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     uint64_t *stage = reinterpret_cast<uint64_t *>(smem_raw);
     ScatterSmem &s = *reinterpret_cast<ScatterSmem *>(smem_raw + sizeof(uint64_t) * kTileKeys);
     if (blockIdx.x >= tile_off[n_parents]) return; /* the grid is an upper bound on the tiles */
-    for (uint32_t i = threadIdx.x; i < fan; i += kThreads) s.cur[i] = 0;
+    for (uint32_t i = threadIdx.x; i <= fan; i += kScatThreads) s.cur[i] = 0;
     __syncthreads();
     uint64_t parent, beg, end;
     tile_range(parent_off, tile_off, n_parents, kTileKeys, parent, beg, end);
     const uint32_t fm = fan - 1;
-    uint64_t x[32];
+    uint64_t x[kScatPer];
+    uint32_t rk[kScatPer / 2]; /* two 16-bit ranks per register; the digit is recomputed */
     uint32_t side = 0, kept = 0;
 #pragma unroll
-    for (int u = 0; u < 32; ++u) {
-        uint64_t i = beg + (uint64_t)u * kThreads + threadIdx.x;
+    for (int u = 0; u < kScatPer; ++u) {
+        uint64_t i = beg + (uint64_t)u * kScatThreads + threadIdx.x;
         x[u] = i < end ? ld_nc(keys + i) : kEmpty;
-        if (COUNT_SIDE && i < end) {
-            kept++;
-            side += (x[u] == kEmpty);
+        if (COUNT_SIDE) {
+            kept += (i < end);
+            side += (i < end) & (x[u] == kEmpty);
         }
     }
 #pragma unroll
-    for (int u = 0; u < 32; ++u)
-        if (x[u] != kEmpty) atomicAdd(&s.cur[digit_of(mix64(x[u]), shift, fm)], 1u);
+    for (int u = 0; u < kScatPer; ++u) {
+        const uint32_t d = x[u] != kEmpty ? digit_of(part_hash(x[u]), shift, fm) : fan;
+        const uint32_t r = atomicAdd(&s.cur[d], 1u);
+        rk[u >> 1] = (u & 1) ? __byte_perm(rk[u >> 1], r, 0x5410) : r;
+    }
     __syncthreads();
-    const uint32_t total = scatter_plan(s, fan, child_off + parent * fan, child_cur + parent * fan);
+    long long gd[kPlanPer];
+    const uint32_t total = scatter_plan(s, fan, child_off + parent * fan, child_cur + parent * fan, gd);
 #pragma unroll
-    for (int u = 0; u < 32; ++u)
-        if (x[u] != kEmpty) {
-            uint32_t d = digit_of(mix64(x[u]), shift, fm);
-            uint32_t pos = atomicAdd(&s.cur[d], 1u);
+    for (int u = 0; u < kScatPer; ++u) {
+        const uint32_t r = (u & 1) ? (rk[u >> 1] >> 16) : (rk[u >> 1] & 0xffffu);
+        const uint32_t d = x[u] != kEmpty ? digit_of(part_hash(x[u]), shift, fm) : fan;
+        const uint32_t pos = (s.cur[d] + r) & (kTileKeys - 1);
+        if (d != fan) {
             stage[pos] = x[u];
             s.dig[pos] = (uint16_t)d;
         }
+    }
+    scatter_publish(s, fan, gd);
     __syncthreads();
     scatter_flush(s, stage, total, out);
     if (COUNT_SIDE) {
@@ -298,6 +374,47 @@ __global__ void __launch_bounds__(kThreads) k_part_scatter_keys(const uint64_t *
 }
 
 /* ---- count: one bucket at a time in a shared-memory table ------------------------------------- */
+constexpr int kPre = 8; /* keys per thread fetched one bucket ahead (covers buckets up to 2048 keys) */
+
+/* slot inside a bucket: fold the key and multiply once (32-bit); the digits came from
+ * a different multiplier over the unfolded key, so the two are independent in practice */
+__device__ __forceinline__ uint32_t bucket_slot(uint64_t x)
+{
+    return (((uint32_t)x ^ (uint32_t)(x >> 32)) * 0x9E3779B1u) >> 20; /* 12 bits */
+}
+
+struct BucketTally {
+    uint32_t distinct;
+    int32_t unique;
+};
+
+/* distinct / unique are accounted at insert time: a claim is a new distinct AND unique key; the
+ * first extra occurrence (the add returns 0) takes the key out of the unique set.  No scan. */
+__device__ __forceinline__ void bucket_insert(unsigned long long *tk, uint32_t *tc, uint64_t x, bool spill_ok,
+                                              Slot *__restrict__ spill, uint64_t spill_cap, BucketTally &bt,
+                                              Tally &ty, unsigned long long *ctr)
+{
+    uint32_t sl = bucket_slot(x);
+    int probes = 0;
+    for (;;) {
+        unsigned long long old = atomicCAS(&tk[sl], (unsigned long long)kEmpty, (unsigned long long)x);
+        if (old == kEmpty) {
+            bt.distinct++;
+            bt.unique++;
+            return;
+        }
+        if (old == x) {
+            bt.unique -= (atomicAdd(&tc[sl], 1u) == 0);
+            return;
+        }
+        sl = (sl + 1) & (kBucketSlots - 1);
+        if (++probes == kBucketSlots) { /* table full of other keys: count it in HBM */
+            if (spill_ok) hash_insert(spill, spill_cap, x, ty, ctr);
+            return;
+        }
+    }
+}
+
 template <bool EMIT>
 __global__ void __launch_bounds__(kThreads) k_count_buckets(const uint64_t *__restrict__ keys,
                                                             const uint64_t *__restrict__ bucket_off,
@@ -312,42 +429,75 @@ __global__ void __launch_bounds__(kThreads) k_count_buckets(const uint64_t *__re
     uint32_t *tc = reinterpret_cast<uint32_t *>(smem_raw + sizeof(uint64_t) * kBucketSlots); /* extras */
     __shared__ unsigned long long row_base;
     Tally ty = {0, 0, 0, 0}; /* spilled keys account themselves through hash_insert */
-    uint32_t distinct = 0, unique = 0;
-    for (uint64_t b = blockIdx.x; b < n_buckets; b += gridDim.x) {
-        const uint64_t beg = bucket_off[b], end = bucket_off[b + 1];
-        if (beg == end) continue; /* uniform for the CTA */
-        for (int i = threadIdx.x; i < kBucketSlots; i += kThreads) {
-            tk[i] = kEmpty;
-            tc[i] = 0;
+    BucketTally bt = {0, 0};
+    uint64_t b = blockIdx.x;
+    uint64_t beg = 0, end = 0;
+    uint64_t pre[kPre];
+    if (b < n_buckets) {
+        beg = bucket_off[b];
+        end = bucket_off[b + 1];
+#pragma unroll
+        for (int u = 0; u < kPre; ++u) {
+            uint64_t i = beg + (uint64_t)u * kThreads + threadIdx.x;
+            pre[u] = i < end ? ld_nc(keys + i) : kEmpty;
+        }
+    }
+    while (b < n_buckets) {
+        const uint64_t nb = b + gridDim.x;
+        uint64_t nbeg = 0, nend = 0;
+        if (nb < n_buckets) {
+            nbeg = bucket_off[nb];
+            nend = bucket_off[nb + 1];
+        }
+        { /* 48 KB of 16-byte stores */
+            ulonglong2 *k2 = reinterpret_cast<ulonglong2 *>(tk);
+            uint4 *c4 = reinterpret_cast<uint4 *>(tc);
+#pragma unroll
+            for (int i = 0; i < kBucketSlots / 2 / kThreads; ++i)
+                k2[i * kThreads + threadIdx.x] = make_ulonglong2(kEmpty, kEmpty);
+#pragma unroll
+            for (int i = 0; i < kBucketSlots / 4 / kThreads; ++i)
+                c4[i * kThreads + threadIdx.x] = make_uint4(0, 0, 0, 0);
         }
         __syncthreads();
-        for (uint64_t i = beg + threadIdx.x; i < end; i += kThreads) {
-            const uint64_t x = ld_nc(keys + i);
-            uint32_t sl = (uint32_t)((mix64(x) * kSlotMul) >> 52); /* 12 bits, independent of the digits */
-            int probes = 0;
-            for (;;) {
-                unsigned long long old = atomicCAS(&tk[sl], (unsigned long long)kEmpty, (unsigned long long)x);
-                if (old == kEmpty) break;
-                if (old == x) {
-                    atomicAdd(&tc[sl], 1u);
-                    break;
-                }
-                sl = (sl + 1) & (kBucketSlots - 1);
-                if (++probes == kBucketSlots) { /* table full of other keys: count it in HBM */
-                    if (!EMIT) hash_insert(spill, spill_cap, x, ty, ctr); /* EMIT re-runs: spill rows come from the table */
-                    break;
+        /* EMIT re-runs the count: rows of spilled keys come from the spill table itself.
+         * First probes of all prefetched keys are issued back to back (independent shared-memory
+         * atomics in flight); only a key that met a different key walks on, in bucket_insert. */
+        {
+            uint32_t sl[kPre];
+            unsigned long long old[kPre];
+#pragma unroll
+            for (int u = 0; u < kPre; ++u) {
+                sl[u] = bucket_slot(pre[u]);
+                old[u] = pre[u];
+                if (pre[u] != kEmpty)
+                    old[u] = atomicCAS(&tk[sl[u]], (unsigned long long)kEmpty, (unsigned long long)pre[u]);
+            }
+#pragma unroll
+            for (int u = 0; u < kPre; ++u) {
+                if (pre[u] == kEmpty) continue;
+                if (old[u] == kEmpty) {
+                    bt.distinct++;
+                    bt.unique++;
+                } else if (old[u] == pre[u]) {
+                    bt.unique -= (atomicAdd(&tc[sl[u]], 1u) == 0);
+                } else {
+                    bucket_insert(tk, tc, pre[u], !EMIT, spill, spill_cap, bt, ty, ctr);
                 }
             }
         }
+        for (uint64_t i = beg + (uint64_t)kPre * kThreads + threadIdx.x; i < end; i += kThreads)
+            bucket_insert(tk, tc, ld_nc(keys + i), !EMIT, spill, spill_cap, bt, ty, ctr);
+        /* next bucket's keys fly while this one drains and the table is re-initialised */
+#pragma unroll
+        for (int u = 0; u < kPre; ++u) {
+            uint64_t i = nbeg + (uint64_t)u * kThreads + threadIdx.x;
+            pre[u] = i < nend ? ld_nc(keys + i) : kEmpty;
+        }
         __syncthreads();
-        uint32_t mine = 0;
-        for (int i = threadIdx.x; i < kBucketSlots; i += kThreads)
-            if (tk[i] != kEmpty) {
-                mine++;
-                unique += (tc[i] == 0);
-            }
-        distinct += mine;
         if (EMIT) {
+            uint32_t mine = 0;
+            for (int i = threadIdx.x; i < kBucketSlots; i += kThreads) mine += (tk[i] != kEmpty);
             uint32_t total;
             uint32_t rank = block_exscan(mine, &total);
             if (threadIdx.x == 0) row_base = atomicAdd(&ctr[C_CURSOR], (unsigned long long)total);
@@ -359,14 +509,17 @@ __global__ void __launch_bounds__(kThreads) k_count_buckets(const uint64_t *__re
                     out_counts[pos] = (uint64_t)tc[i] + 1;
                     pos++;
                 }
+            __syncthreads();
         }
-        __syncthreads();
+        b = nb;
+        beg = nbeg;
+        end = nend;
     }
-    distinct = warp_sum32(distinct);
-    unique = warp_sum32(unique);
+    uint32_t d = warp_sum32(bt.distinct);
+    int32_t u = (int32_t)__reduce_add_sync(0xffffffffu, bt.unique);
     if ((threadIdx.x & 31) == 0) {
-        if (distinct) atomicAdd(&ctr[C_DISTINCT], (unsigned long long)distinct);
-        if (unique) atomicAdd(&ctr[C_UNIQUE], (unsigned long long)unique);
+        if (d) atomicAdd(&ctr[C_DISTINCT], (unsigned long long)d);
+        if (u) atomicAdd(&ctr[C_UNIQUE], (unsigned long long)(long long)u);
     }
     ty.total = 0; /* totals were taken by the scatter pass */
     tally_flush(ty, ctr);
