@@ -12,8 +12,9 @@ fixed, so scaling is "strong".
           count + aggregates; at N > 1 also partition + exchange), CUDA-event timed.
   e2e     the same query through the host-buffer C-ABI call dnagpu_count_kmers():
           pinned host words -> H2D -> count -> D2H of the three aggregates, every step.
-  roofline  the dominant kernel (count_hash / count_hash_keys): algorithmic bytes
-          (0.25 B/base read + 16 B slot per k-mer) / its CUDA-event duration.
+  roofline  the kernel with the largest share of the step (CUDA events around every launch, taken
+          inside the timed region): its algorithmic bytes / its average duration, plus the same
+          figure for every kernel of the pipeline and for the whole step.
   cpu_baseline  the reference's own dna.c (oracle/_ref: compiled unmodified against a PostgreSQL
           API shim and driven like the executor) on the host cores, bounded sample; falls back
           to the oracle's faithful restatement when that library is not built.
@@ -111,15 +112,6 @@ def dist_env():
     return rank, world, local
 
 
-def shard_of(n_bases, k, world, rank):
-    """Base-range shard: starts [first, first+starts) with first a multiple of 32."""
-    rows = n_bases - k + 1
-    per = ((rows + world - 1) // world + 31) // 32 * 32
-    first = min(rank * per, (rows + 31) // 32 * 32)
-    starts = max(0, min(per, rows - first))
-    return first, starts
-
-
 # ============================== the reference arm ==============================
 CHUNK_BASES = 1 << 16  # the CPU arms cut the sample into overlapping chunks, one dna value each
 
@@ -194,6 +186,7 @@ def run_b200(args):
     import torch
     import torch.distributed as dist
     import dnagpu
+    from dnagpu.distributed import GpuEngine, count_sharded, shard_of
 
     rank, world, local = dist_env()
     n_bases, k, seed, desc = WORKLOADS[args.workload]
@@ -226,30 +219,14 @@ def run_b200(args):
                 dist.barrier(device_ids=[local])
             torch.cuda.synchronize(dev)
 
-        send_buf = recv_buf = None
-        if world > 1:
-            send_buf = torch.empty(n_rows_local + 2, dtype=torch.int64, device=dev)
+        engine = GpuEngine(ctx) if world > 1 else None
 
         def count_resident(s):
             """One pass of the hot path with the packed words resident in HBM -> (total, distinct, unique)."""
-            nonlocal recv_buf
             if world == 1:
                 st, _ = ctx.count(s, k, table=False, load_factor=args.load_factor)
                 return st.total, st.distinct, st.unique
-            out, counts = ctx.partition(s, k, world, out=send_buf)
-            send_counts = torch.from_numpy(counts.astype(np.int64)).to(dev)
-            recv_counts = torch.empty_like(send_counts)
-            dist.all_to_all_single(recv_counts, send_counts)
-            rc_host = recv_counts.cpu().tolist()
-            n_recv = int(sum(rc_host))
-            if recv_buf is None or recv_buf.numel() < n_recv + 2:
-                recv_buf = torch.empty(int(n_recv * 1.05) + 2, dtype=torch.int64, device=dev)
-            dist.all_to_all_single(recv_buf[:n_recv], out, rc_host, [int(c) for c in counts])
-            st, _ = ctx.count_keys(recv_buf[:n_recv], k, table=False, load_factor=args.load_factor)
-            agg = torch.tensor([st.total, st.distinct, st.unique], dtype=torch.int64, device=dev)
-            dist.all_reduce(agg)
-            t = agg.cpu().tolist()
-            return t[0], t[1], t[2]
+            return count_sharded(engine, s, k, world, load_factor=args.load_factor)
 
         def count_e2e():
             """The reference-facing call: host words in, aggregates out (H2D and D2H inside)."""
@@ -329,25 +306,46 @@ def run_b200(args):
     if rank == 0:
         value = n_rows_total * args.steps / (ms * 1e-3) / 1e9
         e2e_value = n_rows_total * args.e2e_steps / e2e_s / 1e9
-        dom = "count_hash" if world == 1 else "count_hash_keys"
-        d = kernels.get(dom, {"ms": 0.0, "launches": 0})
         launches = sum(v["launches"] for v in kernels.values())
+        # algorithmic bytes per launch of every kernel of the count pipeline:
+        # rows = k-mers one launch handles on this rank; base reads are 0.25 B/base
+        rows_r = n_rows_total / world
+        base_b = 0.25 * local_bases
+        ALG = {
+            "count_hash": base_b + 16.0 * rows_r, "count_hash_keys": 8.0 * rows_r + 16.0 * rows_r,
+            "count_dense": base_b + 4.0 * rows_r, "count_dense_smem": base_b,
+            "part_hist": base_b if world == 1 else 8.0 * rows_r,
+            "part_scatter": (base_b if world == 1 else 8.0 * rows_r) + 8.0 * rows_r,
+            "part_hist2": 8.0 * rows_r, "part_scatter2": 16.0 * rows_r, "count_buckets": 8.0 * rows_r,
+            "partition_count": base_b, "partition_write": base_b + 8.0 * rows_r,
+        }
+        timed = {n: v for n, v in kernels.items() if n in ALG and v["launches"]}
         roofline = None
-        if d["launches"]:
+        if timed:
+            dom = max(timed, key=lambda n: timed[n]["ms"])
+            d = timed[dom]
             per_launch_ms = d["ms"] / d["launches"]
-            rows_per_launch = n_rows_total / world  # owner partitions are uniform to < 0.1 %
-            alg_bytes = (0.25 * local_bases if world == 1 else 8.0 * rows_per_launch) + 16.0 * rows_per_launch
-            achieved = alg_bytes / per_launch_ms / 1e6
+            achieved = ALG[dom] / per_launch_ms / 1e6
             traffic = None
             try:
                 with open(os.path.join(ROOT, "profiles", "traffic.json")) as f:
-                    traffic = json.load(f).get(f"{args.workload}:{dom}")
+                    traffic = json.load(f).get(f"{args.workload}:n{world}:{dom}")
             except Exception:
                 pass
+            pipe_bytes = sum(ALG[n] * v["launches"] / args.steps for n, v in timed.items())
             roofline = {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak, "unit": "GB/s",
                         "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
-                        "algorithmic_bytes_per_launch": alg_bytes, "ms_per_launch": per_launch_ms,
-                        "share_of_step": d["ms"] / ms}
+                        "algorithmic_bytes_per_launch": ALG[dom], "ms_per_launch": per_launch_ms,
+                        "share_of_step": d["ms"] / ms,
+                        "pipeline": {"algorithmic_bytes_per_step": pipe_bytes,
+                                     "bytes_per_kmer": pipe_bytes / rows_r,
+                                     "achieved": pipe_bytes / (ms / args.steps) / 1e6,
+                                     "frac": pipe_bytes / (ms / args.steps) / 1e6 / peak,
+                                     "note": "all kernels of one step on this rank / whole step time"},
+                        "per_kernel": {n: {"ms_per_launch": v["ms"] / v["launches"],
+                                           "achieved": ALG[n] / (v["ms"] / v["launches"]) / 1e6,
+                                           "frac": ALG[n] / (v["ms"] / v["launches"]) / 1e6 / peak}
+                                       for n, v in timed.items()}}
         threads = max(1, min(os.cpu_count() or 1, 64))
         cv, cdt, cstats, ckind, csample = cpu_reference_rate(n_bases, k, seed, threads, args.cpu_sample)
         cpu = {"value": cv, "unit": "Gkmer/s", "cores": threads, "kind": ckind,

@@ -1,0 +1,96 @@
+"""The N > 1 orchestration (dnagpu/distributed.py) on CPU: two gloo ranks, the same shard /
+owner-routing / all-to-all / all-reduce code the GPU run uses, with a stand-in engine (oracle
+extraction, libdnagpu's host-callable dnagpu_owner_of for routing) in place of the CUDA kernels."""
+import os
+import sys
+
+import numpy as np
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+from conftest import PKG, ROOT
+
+
+class OracleEngine:
+    """Test double for GpuEngine: steps 2 and 4 done by the CPU oracle."""
+
+    def __init__(self, n_bases, seed):
+        self.n_bases, self.seed = n_bases, seed
+
+    def device(self):
+        return torch.device("cpu")
+
+    def partition(self, seq, k, world, prefix=None, pattern=None):
+        from oracle import ref_cpu as R
+        import dnagpu
+        first, starts = seq
+        n_local = min(self.n_bases - first, starts + k - 1)
+        words = R.synth_seq(self.seed, self.n_bases, first_word=first // 32, n_words=(n_local + 31) // 32 + 1)
+        rows = R.generate_kmers(words, n_local, k, window=True)[:starts]
+        owners = np.array([dnagpu.owner_of(int(x), world) for x in rows], dtype=np.int64)
+        order = np.argsort(owners, kind="stable")
+        counts = np.bincount(owners, minlength=world).astype(np.uint64)
+        return torch.from_numpy(rows[order].view(np.int64).copy()), counts
+
+    def recv_buffer(self, n):
+        return torch.empty(n, dtype=torch.int64)
+
+    def count_keys(self, keys, k, load_factor=0.0):
+        u, c = np.unique(keys.numpy().view(np.uint64), return_counts=True)
+        return int(c.sum()), int(u.size), int((c == 1).sum())
+
+
+def _worker(rank, world, port, n_bases, k, seed, out):
+    for p in (ROOT, PKG):
+        sys.path.insert(0, p)
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from dnagpu.distributed import count_sharded, shard_of
+    engine = OracleEngine(n_bases, seed)
+    shard = shard_of(n_bases, k, world, rank)
+    res = count_sharded(engine, shard, k, world)
+    if rank == 0:
+        out.put(res)
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("n_bases,k", [(20_000, 31), (4_097, 5), (64, 32)])
+def test_two_rank_exchange_equals_single_rank(n_bases, k):
+    from oracle import ref_cpu as R
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 29600 + (n_bases + k) % 300
+    procs = [ctx.Process(target=_worker, args=(r, 2, port, n_bases, k, 21, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    got = q.get(timeout=120)
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    words = R.synth_seq(21, n_bases)
+    want = R.count_query(words, 1, n_bases, words.size, k, faithful=False)
+    assert tuple(got) == want.stats
+
+
+def test_shards_tile_the_sequence_exactly_once():
+    from dnagpu.distributed import reads_shard_of, shard_of
+    for n, k, world in [(1000, 31, 2), (3_100_000_000, 31, 8), (33, 32, 4), (10, 31, 3), (100_000_007, 21, 7)]:
+        rows = max(0, n - k + 1)
+        pos = 0
+        for r in range(world):
+            first, starts = shard_of(n, k, world, r)
+            assert first % 32 == 0
+            if starts:
+                assert first == pos
+            pos += starts
+            assert first + starts <= max(rows, first)
+        assert pos == rows
+    for n, world in [(10, 3), (100_000_000, 8), (1, 4)]:
+        tot = 0
+        for r in range(world):
+            first, cnt = reads_shard_of(n, world, r)
+            assert first == tot
+            tot += cnt
+        assert tot == n
