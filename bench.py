@@ -150,9 +150,10 @@ def run_reference(args):
     n_bases, k, seed, desc = WORKLOADS[args.workload]
     threads = max(1, min(os.cpu_count() or 1, 64))
     # calibrate the per-step sample so that the whole run ends within a few minutes
-    rate, dt, _, kind, _ = cpu_reference_rate(n_bases, k, seed, threads, 1_000_000)
-    budget_s = max(1.0, min(6.0, 150.0 / max(1, args.steps + args.warmup)))
-    sample = int(max(1_000_000, min(64_000_000, rate * 1e9 * budget_s)))
+    rate, dt, _, kind, _ = cpu_reference_rate(n_bases, k, seed, threads, 4_000_000)
+    # the rate on a small (cache-friendly) sample is optimistic: keep 40 % of the time budget
+    budget_s = 0.4 * max(0.5, min(4.0, 100.0 / max(1, args.steps + args.warmup)))
+    sample = int(max(1_000_000, min(16_000_000, rate * 1e9 * budget_s)))
     for _ in range(args.warmup):
         cpu_reference_rate(n_bases, k, seed, threads, sample)
     wall, total = 0.0, 0

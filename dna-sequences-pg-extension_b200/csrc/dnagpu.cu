@@ -1259,6 +1259,10 @@ static int count_partition(dnagpu_ctx *ctx, const CountInput &in, int k, dnagpu_
     }));
     TRY(fetch_counters(ctx));
 #ifdef DNAGPU_PHASE_TIMING
+    fprintf(stderr, "count_buckets phases (cycles/bucket, thread 0): init %.0f | sync %.0f | insert %.0f | prefetch+sync %.0f | buckets %llu\n",
+            (double)ctx->h_ctr[110] / ctx->h_ctr[114], (double)ctx->h_ctr[111] / ctx->h_ctr[114],
+            (double)ctx->h_ctr[112] / ctx->h_ctr[114], (double)ctx->h_ctr[113] / ctx->h_ctr[114],
+            (unsigned long long)ctx->h_ctr[114]);
     fprintf(stderr, "scatter_seq phases (cycles/tile, thread 0): load+rank %.0f | barrier %.0f | plan %.0f | place %.0f+sync | flush %.0f | tiles %llu\n",
             (double)ctx->h_ctr[100] / ctx->h_ctr[105], (double)ctx->h_ctr[101] / ctx->h_ctr[105],
             (double)ctx->h_ctr[102] / ctx->h_ctr[105], (double)ctx->h_ctr[103] / ctx->h_ctr[105],

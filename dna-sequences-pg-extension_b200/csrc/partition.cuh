@@ -135,7 +135,6 @@ struct ScatterSmem {
     uint32_t cur[kMaxFan + 1]; /* cur[fan] = dummy bin of the keys that are not scattered */
     uint32_t warp_tot[kScatThreads / 32 + 1];
     long long gdelta[kMaxFan];
-    uint16_t dig[kTileKeys];
 };
 
 /* After counting: exclusive scan of cur[] (it becomes the stage start of every digit) and
@@ -198,14 +197,19 @@ __device__ __forceinline__ void scatter_publish(ScatterSmem &s, uint32_t fan, co
         if (base + i < fan) s.gdelta[base + i] = gd[i];
 }
 
-/* stage -> global: consecutive threads copy consecutive stage entries, i.e. whole runs */
+/* stage -> global: consecutive threads copy consecutive stage entries, i.e. whole runs.  The digit of
+ * a staged key is recomputed (one multiply) rather than kept in a side array: the kernel is bound by
+ * L1 data-pipe wavefronts (ncu: 67 % busy), not by ALU work. */
 __device__ __forceinline__ void scatter_flush(const ScatterSmem &s, const uint64_t *stage, uint32_t total,
-                                              uint64_t *__restrict__ out)
+                                              int shift, uint32_t fm, uint64_t *__restrict__ out)
 {
 #pragma unroll
     for (int u = 0; u < kScatPer; ++u) {
         const uint32_t i = (uint32_t)u * kScatThreads + threadIdx.x;
-        if (i < total) out[(uint64_t)(s.gdelta[s.dig[i]] + (long long)i)] = stage[i];
+        if (i < total) {
+            const uint64_t x = stage[i];
+            out[(uint64_t)(s.gdelta[digit_of(part_hash(x), shift, fm)] + (long long)i)] = x;
+        }
     }
 }
 
@@ -281,10 +285,7 @@ __global__ void __launch_bounds__(kScatThreads, 2) k_part_scatter_seq(SeqView sv
             const uint32_t r = (j & 1) ? (rk[j >> 1] >> 16) : (rk[j >> 1] & 0xffffu);
             const uint32_t d = digit_of(part_hash(x), shift, fm);
             const uint32_t pos = (s.cur[d] + r) & (kTileKeys - 1);
-            if (real_mask & (1u << j)) {
-                stage[pos] = x;
-                s.dig[pos] = (uint16_t)d;
-            }
+            if (real_mask & (1u << j)) stage[pos] = x;
             cur = (cur >> 2) | (nxt << 62);
             nxt >>= 2;
         }
@@ -292,7 +293,7 @@ __global__ void __launch_bounds__(kScatThreads, 2) k_part_scatter_seq(SeqView sv
     scatter_publish(s, fan, gd);
     __syncthreads();
     PHASE_MARK(4);
-    scatter_flush(s, stage, total, out);
+    scatter_flush(s, stage, total, shift, fm, out);
     PHASE_MARK(5);
 #ifdef DNAGPU_PHASE_TIMING
     if (threadIdx.x == 0) {
@@ -355,14 +356,11 @@ __global__ void __launch_bounds__(kScatThreads, 2) k_part_scatter_keys(const uin
         const uint32_t r = (u & 1) ? (rk[u >> 1] >> 16) : (rk[u >> 1] & 0xffffu);
         const uint32_t d = x[u] != kEmpty ? digit_of(part_hash(x[u]), shift, fm) : fan;
         const uint32_t pos = (s.cur[d] + r) & (kTileKeys - 1);
-        if (d != fan) {
-            stage[pos] = x[u];
-            s.dig[pos] = (uint16_t)d;
-        }
+        if (d != fan) stage[pos] = x[u];
     }
     scatter_publish(s, fan, gd);
     __syncthreads();
-    scatter_flush(s, stage, total, out);
+    scatter_flush(s, stage, total, shift, fm, out);
     if (COUNT_SIDE) {
         kept = warp_sum32(kept);
         side = warp_sum32(side);
@@ -442,7 +440,14 @@ __global__ void __launch_bounds__(kThreads) k_count_buckets(const uint64_t *__re
             pre[u] = i < end ? ld_nc(keys + i) : kEmpty;
         }
     }
+#ifdef DNAGPU_PHASE_TIMING
+    long long ph[4] = {0, 0, 0, 0}, nbk = 0;
+#define CT_MARK(v) long long v = clock64()
+#else
+#define CT_MARK(v)
+#endif
     while (b < n_buckets) {
+        CT_MARK(c0);
         const uint64_t nb = b + gridDim.x;
         uint64_t nbeg = 0, nend = 0;
         if (nb < n_buckets) {
@@ -459,16 +464,22 @@ __global__ void __launch_bounds__(kThreads) k_count_buckets(const uint64_t *__re
             for (int i = 0; i < kBucketSlots / 4 / kThreads; ++i)
                 c4[i * kThreads + threadIdx.x] = make_uint4(0, 0, 0, 0);
         }
+        CT_MARK(c1);
         __syncthreads();
+        CT_MARK(c2);
         /* EMIT re-runs the count: rows of spilled keys come from the spill table itself.
-         * First probes of all prefetched keys are issued back to back (independent shared-memory
-         * atomics in flight); only a key that met a different key walks on, in bucket_insert. */
+         * The shared-memory CAS pipe is what bounds this kernel, and a CAS issued for one lane costs as
+         * much as one issued for 32.  So probing is organised in ROUNDS: first probes of all prefetched
+         * keys go out back to back; then, while any lane of the warp still has a key that met a different
+         * key, every such lane re-probes its OLDEST pending key in the same instruction.  Rounds needed =
+         * the largest per-lane total of extra probes, not the sum of per-key maxima. */
         {
-            uint32_t sl[kPre];
+            uint32_t sl[kPre], pending = 0;
+#pragma unroll
+            for (int u = 0; u < kPre; ++u) sl[u] = bucket_slot(pre[u]);
             unsigned long long old[kPre];
 #pragma unroll
             for (int u = 0; u < kPre; ++u) {
-                sl[u] = bucket_slot(pre[u]);
                 old[u] = pre[u];
                 if (pre[u] != kEmpty)
                     old[u] = atomicCAS(&tk[sl[u]], (unsigned long long)kEmpty, (unsigned long long)pre[u]);
@@ -482,12 +493,44 @@ __global__ void __launch_bounds__(kThreads) k_count_buckets(const uint64_t *__re
                 } else if (old[u] == pre[u]) {
                     bt.unique -= (atomicAdd(&tc[sl[u]], 1u) == 0);
                 } else {
-                    bucket_insert(tk, tc, pre[u], !EMIT, spill, spill_cap, bt, ty, ctr);
+                    pending |= 1u << u;
+                }
+            }
+            uint64_t key = 0;
+            uint32_t slot = 0, probes = 0;
+            int cur = -1;
+            while (__any_sync(0xffffffffu, pending != 0)) {
+                if (pending) {
+                    const int u = __ffs(pending) - 1;
+                    if (u != cur) { /* next pending key of this lane: fetch it out of the register arrays */
+                        cur = u;
+                        probes = 0;
+#pragma unroll
+                        for (int v = 0; v < kPre; ++v)
+                            if (v == u) {
+                                key = pre[v];
+                                slot = sl[v];
+                            }
+                    }
+                    slot = (slot + 1) & (kBucketSlots - 1);
+                    const unsigned long long o = atomicCAS(&tk[slot], (unsigned long long)kEmpty, (unsigned long long)key);
+                    if (o == kEmpty) {
+                        bt.distinct++;
+                        bt.unique++;
+                        pending &= pending - 1;
+                    } else if (o == key) {
+                        bt.unique -= (atomicAdd(&tc[slot], 1u) == 0);
+                        pending &= pending - 1;
+                    } else if (++probes == kBucketSlots) { /* table full of other keys: count it in HBM */
+                        if (!EMIT) hash_insert(spill, spill_cap, key, ty, ctr);
+                        pending &= pending - 1;
+                    }
                 }
             }
         }
         for (uint64_t i = beg + (uint64_t)kPre * kThreads + threadIdx.x; i < end; i += kThreads)
             bucket_insert(tk, tc, ld_nc(keys + i), !EMIT, spill, spill_cap, bt, ty, ctr);
+        CT_MARK(c3);
         /* next bucket's keys fly while this one drains and the table is re-initialised */
 #pragma unroll
         for (int u = 0; u < kPre; ++u) {
@@ -495,6 +538,12 @@ __global__ void __launch_bounds__(kThreads) k_count_buckets(const uint64_t *__re
             pre[u] = i < nend ? ld_nc(keys + i) : kEmpty;
         }
         __syncthreads();
+#ifdef DNAGPU_PHASE_TIMING
+        {
+            long long c4 = clock64();
+            ph[0] += c1 - c0; ph[1] += c2 - c1; ph[2] += c3 - c2; ph[3] += c4 - c3; nbk++;
+        }
+#endif
         if (EMIT) {
             uint32_t mine = 0;
             for (int i = threadIdx.x; i < kBucketSlots; i += kThreads) mine += (tk[i] != kEmpty);
@@ -515,6 +564,12 @@ __global__ void __launch_bounds__(kThreads) k_count_buckets(const uint64_t *__re
         beg = nbeg;
         end = nend;
     }
+#ifdef DNAGPU_PHASE_TIMING
+    if (threadIdx.x == 0) {
+        for (int i = 0; i < 4; ++i) atomicAdd(&ctr[110 + i], (unsigned long long)ph[i]);
+        atomicAdd(&ctr[114], (unsigned long long)nbk);
+    }
+#endif
     uint32_t d = warp_sum32(bt.distinct);
     int32_t u = (int32_t)__reduce_add_sync(0xffffffffu, bt.unique);
     if ((threadIdx.x & 31) == 0) {
