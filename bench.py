@@ -38,11 +38,16 @@ for _p in (ROOT, PKG):
         sys.path.insert(0, _p)
 
 WORKLOADS = {
-    # name: (n_bases, k, seed, description)
+    # name: (n_bases, k, seed, description)      -- BASELINE.json configs[3], [1], [4]
     "c4": (3_100_000_000, 31, 4, "3.1 Gbp synthetic sequence, k=31 GROUP BY kmer count + total/distinct/unique"),
     "c2": (100_000_000, 21, 2, "100 Mbp synthetic sequence, k=21 full count + total/distinct/unique"),
     "c5": (1_000_000_000, 31, 5, "1 Gbp synthetic sequence, k=31 count"),
+    # BASELINE.json configs[2]: reads (each its own dna value), WHERE ^@ AND @> fused into the count
+    "c3": (100_000_000 * 150, 31, 3, "100M synthetic 150 bp reads, k=31, WHERE kmer ^@ 'AC' AND "
+                                     "'NNNNNNNNNNNNWSNNNNNNNNNNNNNNNRY' @> kmer, fused filter-count"),
 }
+READS = {"c3": {"n_reads": 100_000_000, "bases": 150, "stride": 5, "prefix": "AC",
+                "pattern": "NNNNNNNNNNNNWSNNNNNNNNNNNNNNNRY"}}
 REPEAT_EVERY = 8
 METRIC = "Gkmer/s counted (k=31) at 1/2/4/8 B200; extraction HBM GB/s vs peak"
 
@@ -116,7 +121,7 @@ def dist_env():
 CHUNK_BASES = 1 << 16  # the CPU arms cut the sample into overlapping chunks, one dna value each
 
 
-def cpu_reference_rate(n_bases, k, seed, threads, sample_bases):
+def cpu_reference_rate(n_bases, k, seed, threads, sample_bases, reads=None):
     """Time the reference's CPU implementation of the query on a prefix of the workload.
 
     oracle/_ref (the reference's own dna.c, compiled unmodified against the PostgreSQL API shim and
@@ -128,10 +133,24 @@ def cpu_reference_rate(n_bases, k, seed, threads, sample_bases):
     Returns (Gkmer/s, seconds, (total, distinct, unique), kind)."""
     from oracle import ref_cpu as R
     from oracle import ref_real as P
+    kind = "reference" if os.path.exists(P.SO) else "port"
+    if reads is not None:  # a prefix of the batch of reads, each read one dna value
+        n = max(threads, sample_bases // reads["bases"])
+        words = R.synth_reads(seed, n, reads["bases"], reads["stride"], REPEAT_EVERY)
+        pk = R.kmer_make(reads["prefix"])
+        t0 = time.perf_counter()
+        if kind == "reference":
+            r = P.count(words, n, reads["bases"], reads["stride"], k, prefix=pk, pattern=reads["pattern"],
+                        threads=threads, want_rows=False)
+        else:
+            r = R.count_query(words, n, reads["bases"], reads["stride"], k, prefix=pk, pattern=reads["pattern"],
+                              faithful=True, threads=threads, want_rows=False)
+        dt = time.perf_counter() - t0
+        rows = n * (reads["bases"] - k + 1)  # k-mers generated and tested, the unit of the metric
+        return rows / dt / 1e9, dt, (rows,) + tuple(r.stats[1:]), kind, n * reads["bases"]
     n_chunks = max(1, (sample_bases - (k - 1)) // CHUNK_BASES)
     sample = n_chunks * CHUNK_BASES + k - 1
     words = R.synth_seq(seed, n_bases, REPEAT_EVERY, first_word=0, n_words=(sample + 31) // 32 + 1)
-    kind = "reference" if os.path.exists(P.SO) else "port"
     t0 = time.perf_counter()
     if kind == "reference":
         r = P.count(words, n_chunks, CHUNK_BASES + k - 1, CHUNK_BASES // 32, k, threads=threads, want_rows=False)
@@ -150,15 +169,16 @@ def run_reference(args):
     n_bases, k, seed, desc = WORKLOADS[args.workload]
     threads = max(1, min(os.cpu_count() or 1, 64))
     # calibrate the per-step sample so that the whole run ends within a few minutes
-    rate, dt, _, kind, _ = cpu_reference_rate(n_bases, k, seed, threads, 4_000_000)
+    reads = READS.get(args.workload)
+    rate, dt, _, kind, _ = cpu_reference_rate(n_bases, k, seed, threads, 4_000_000, reads)
     # the rate on a small (cache-friendly) sample is optimistic: keep 40 % of the time budget
     budget_s = 0.4 * max(0.5, min(4.0, 100.0 / max(1, args.steps + args.warmup)))
     sample = int(max(1_000_000, min(16_000_000, rate * 1e9 * budget_s)))
     for _ in range(args.warmup):
-        cpu_reference_rate(n_bases, k, seed, threads, sample)
+        cpu_reference_rate(n_bases, k, seed, threads, sample, reads)
     wall, total = 0.0, 0
     for _ in range(args.steps):
-        _, dt, stats, kind, sample_used = cpu_reference_rate(n_bases, k, seed, threads, sample)
+        _, dt, stats, kind, sample_used = cpu_reference_rate(n_bases, k, seed, threads, sample, reads)
         wall += dt
         total += stats[0]
     value = total / wall / 1e9
@@ -187,12 +207,17 @@ def run_b200(args):
     import torch
     import torch.distributed as dist
     import dnagpu
-    from dnagpu.distributed import GpuEngine, count_sharded, shard_of
+    from dnagpu.distributed import GpuEngine, count_sharded, count_sharded_fused, reads_shard_of, shard_of
 
     rank, world, local = dist_env()
     n_bases, k, seed, desc = WORKLOADS[args.workload]
+    reads = READS.get(args.workload)
     if args.n_bases:
         n_bases = args.n_bases
+        if reads:
+            reads = dict(reads, n_reads=max(world, n_bases // reads["bases"]))
+            n_bases = reads["n_reads"] * reads["bases"]
+    where = {"prefix": reads["prefix"], "pattern": reads["pattern"]} if reads else {}
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     if world > 1:
@@ -202,10 +227,15 @@ def run_b200(args):
 
     with torch.cuda.stream(stream):
         ctx = dnagpu.Context(local, torch_stream=True)
-        first, starts = shard_of(n_bases, k, world, rank)
-        seq = ctx.synth_range(n_bases, seed, REPEAT_EVERY, first, starts, k)
+        if reads:
+            first, starts = reads_shard_of(reads["n_reads"], world, rank)  # first read, reads of this rank
+            seq = ctx.synth_reads(first, starts, reads["bases"], reads["stride"], seed, REPEAT_EVERY)
+            n_rows_total = reads["n_reads"] * (reads["bases"] - k + 1)
+        else:
+            first, starts = shard_of(n_bases, k, world, rank)
+            seq = ctx.synth_range(n_bases, seed, REPEAT_EVERY, first, starts, k)
+            n_rows_total = n_bases - k + 1
         n_rows_local = seq.kmer_count(k)
-        n_rows_total = n_bases - k + 1
         n_words_local = seq.n_words
         # host copy of this rank's packed words, pinned (the dna value a backend would hold)
         host = torch.empty(n_words_local + 2, dtype=torch.int64, pin_memory=True)
@@ -213,7 +243,7 @@ def run_b200(args):
         ctx.synchronize()
         rc = ctx.lib.dnagpu_seq_download(ctx.handle, seq.handle, C.c_void_p(host.data_ptr()), n_words_local)
         assert rc == 0
-        local_bases = min(n_bases - first, starts + k - 1)
+        local_bases = starts * reads["bases"] if reads else min(n_bases - first, starts + k - 1)
 
         def barrier():
             if world > 1:
@@ -221,21 +251,31 @@ def run_b200(args):
             torch.cuda.synchronize(dev)
 
         engine = GpuEngine(ctx) if world > 1 else None
+        xbuf = {}
 
         def count_resident(s):
             """One pass of the hot path with the packed words resident in HBM -> (total, distinct, unique)."""
             if world == 1:
-                st, _ = ctx.count(s, k, table=False, load_factor=args.load_factor)
+                st, _ = ctx.count(s, k, table=False, load_factor=args.load_factor, **where)
                 return st.total, st.distinct, st.unique
-            return count_sharded(engine, s, k, world, load_factor=args.load_factor)
+            if args.exchange == "fused":
+                return count_sharded_fused(ctx, s, k, n_rows_total, world, rank, xbuf, **where)
+            return count_sharded(engine, s, k, world, load_factor=args.load_factor, **where)
 
         def count_e2e():
             """The reference-facing call: host words in, aggregates out (H2D and D2H inside)."""
-            if world == 1:
-                st = ctx.count_kmers_ptr(C.c_void_p(host.data_ptr()), local_bases, k)
+            hp = C.c_void_p(host.data_ptr())
+            if world == 1 and reads:
+                st = ctx.count_reads_ptr(hp, starts, reads["bases"], reads["stride"], k, **where)
                 return st.total, st.distinct, st.unique
-            s = ctx.upload_words(C.c_void_p(host.data_ptr()), local_bases)
-            s.set_start_limit(starts)
+            if world == 1:
+                st = ctx.count_kmers_ptr(hp, local_bases, k)
+                return st.total, st.distinct, st.unique
+            if reads:
+                s = ctx.upload_reads_ptr(hp, starts, reads["bases"], reads["stride"])
+            else:
+                s = ctx.upload_words(hp, local_bases)
+                s.set_start_limit(starts)
             r = count_resident(s)
             s.free()
             return r
@@ -273,7 +313,7 @@ def run_b200(args):
 
         # ---- extraction GB/s (the second half of the metric), timed on its own ----
         extract = None
-        if not args.no_extract:
+        if not args.no_extract and not reads:
             xs_bases = min(local_bases, 1_000_000_000)
             xs = ctx.synth_range(n_bases, seed, REPEAT_EVERY, first, max(0, xs_bases - k + 1), k)
             xr = xs.kmer_count(k)
@@ -301,7 +341,7 @@ def run_b200(args):
         t = torch.tensor([ms, e2e_s], dtype=torch.float64, device=dev)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         ms, e2e_s = t.tolist()
-    assert stats[0] == n_rows_total, (stats, n_rows_total)
+    assert reads or stats[0] == n_rows_total, (stats, n_rows_total)
     assert tuple(stats) == tuple(stats_e2e), (stats, stats_e2e)
 
     if rank == 0:
@@ -310,8 +350,8 @@ def run_b200(args):
         launches = sum(v["launches"] for v in kernels.values())
         # algorithmic bytes per launch of every kernel of the count pipeline:
         # rows = k-mers one launch handles on this rank; base reads are 0.25 B/base
-        rows_r = n_rows_total / world
-        base_b = 0.25 * local_bases
+        rows_r = stats[0] / world          # keys that reach the partition / count stages (after WHERE)
+        base_b = 8.0 * n_words_local       # the packed words one launch reads (0.25 B/base)
         ALG = {
             "count_hash": base_b + 16.0 * rows_r, "count_hash_keys": 8.0 * rows_r + 16.0 * rows_r,
             "count_dense": base_b + 4.0 * rows_r, "count_dense_smem": base_b,
@@ -348,7 +388,7 @@ def run_b200(args):
                                            "frac": ALG[n] / (v["ms"] / v["launches"]) / 1e6 / peak}
                                        for n, v in timed.items()}}
         threads = max(1, min(os.cpu_count() or 1, 64))
-        cv, cdt, cstats, ckind, csample = cpu_reference_rate(n_bases, k, seed, threads, args.cpu_sample)
+        cv, cdt, cstats, ckind, csample = cpu_reference_rate(n_bases, k, seed, threads, args.cpu_sample, reads)
         cpu = {"value": cv, "unit": "Gkmer/s", "cores": threads, "kind": ckind,
                "sample": f"first {csample} bases of the workload ({cdt:.1f} s), " +
                          ("the reference's own dna.c (unmodified, PostgreSQL API shim) driven like the executor: "
@@ -361,16 +401,19 @@ def run_b200(args):
             "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True,
             "scaling": "strong", "vs_baseline": None, "dtype": "u64", "data": "synthetic",
             "config": {"workload": desc, "n_bases": n_bases, "k": k, "seed": seed,
+                       "unit_of_value": "k-mers generated and tested per second" if reads else "k-mers counted per second",
                        "repeat_every": REPEAT_EVERY, "block_bases": 1024,
                        "l2": "inputs (packed words + hash table) larger than L2; no flush needed",
                        "parallelism": "single GPU" if world == 1 else
-                       f"{world} base-range shards + owner-hash all-to-all (NCCL)",
+                       f"{world} base-range shards + owner-hash all-to-all (NCCL), exchange={args.exchange}",
                        "load_factor": args.load_factor or 0.5},
             "result": {"total": stats[0], "distinct": stats[1], "unique": stats[2]},
             "e2e": {"value": e2e_value, "unit": "Gkmer/s", "steps": args.e2e_steps,
                     "ms_per_step": 1e3 * e2e_s / args.e2e_steps,
-                    "h2d_bytes_per_step": int(8 * ((n_bases + 31) // 32)), "d2h_bytes_per_step": 24 * world,
-                    "api": "dnagpu_count_kmers(ctx, host_words, n_bases, k, NULL, &stats, NULL)"},
+                    "h2d_bytes_per_step": int(8 * reads["n_reads"] * reads["stride"]) if reads
+                    else int(8 * ((n_bases + 31) // 32)), "d2h_bytes_per_step": 24 * world,
+                    "api": ("dnagpu_count_reads(ctx, host_words, n_reads, 150, 5, k, &where, &stats, NULL)" if reads else
+                            "dnagpu_count_kmers(ctx, host_words, n_bases, k, NULL, &stats, NULL)")},
             "gpu_launches": launches, "kernels": kernels, "roofline": roofline, "cpu_baseline": cpu,
             "extract": extract, "clocks": clocks,
         }
@@ -394,6 +437,8 @@ def main():
     ap.add_argument("--load-factor", type=float, default=0.0)
     ap.add_argument("--cpu-sample", type=int, default=16_000_000)
     ap.add_argument("--no-extract", action="store_true")
+    ap.add_argument("--exchange", default="fused", choices=["fused", "routed"],
+                    help="N > 1: owner routing fused into partition level 1, or the separate dnagpu_partition pass")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
     if args.impl == "reference":

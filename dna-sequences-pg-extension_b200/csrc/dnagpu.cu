@@ -149,6 +149,8 @@ struct Scratch {
     void release(void *p) { ptrs.erase(std::remove(ptrs.begin(), ptrs.end(), p), ptrs.end()); }
 };
 
+static int scan_any(dnagpu_ctx *ctx, Scratch &sc, const uint64_t *in, uint64_t n, uint64_t *out);
+
 static inline uint64_t rows_of(uint64_t n_bases, int k)
 {
     return n_bases >= (uint64_t)k ? n_bases - (uint64_t)k + 1 : 0; /* Q2 (dna.c:781) */
@@ -638,8 +640,8 @@ static int make_view(dnagpu_ctx *ctx, const dnagpu_seq *cseq, int k, SeqView *v)
                 k_ragged_rows<<<grid_for(n, kThreads), kThreads, 0, ctx->stream>>>(seq->d_n_bases, n, k,
                                                                                   rows, items);
             }));
-        TRY(launch(ctx, "scan", [&] { k_scan_u64<<<1, 1024, 0, ctx->stream>>>(rows, n, seq->d_row_off); }));
-        TRY(launch(ctx, "scan", [&] { k_scan_u64<<<1, 1024, 0, ctx->stream>>>(items, n, seq->d_item_off); }));
+        TRY(scan_any(ctx, sc, rows, n, seq->d_row_off));
+        TRY(scan_any(ctx, sc, items, n, seq->d_item_off));
         CU(ctx, cudaMemcpyAsync(&ctx->h_ctr[0], seq->d_row_off + n, 8, cudaMemcpyDeviceToHost, ctx->stream));
         CU(ctx, cudaMemcpyAsync(&ctx->h_ctr[1], seq->d_item_off + n, 8, cudaMemcpyDeviceToHost, ctx->stream));
         CU(ctx, cudaStreamSynchronize(ctx->stream));
@@ -809,7 +811,7 @@ static int filter_scan(dnagpu_ctx *ctx, const dnagpu_seq *seq, const SeqView &v,
     DISPATCH_LAYOUT(seq->layout, TRY(launch(ctx, "filter_count", [&] {
         k_filter_count<LY><<<tiles, kThreads, 0, ctx->stream>>>(v, p, tile_cnt);
     })));
-    TRY(launch(ctx, "scan", [&] { k_scan_u64<<<1, 1024, 0, ctx->stream>>>(tile_cnt, tiles, *tile_off); }));
+    TRY(scan_any(ctx, sc, tile_cnt, tiles, *tile_off));
     return read_u64(ctx, *tile_off + tiles, n_match);
 }
 
@@ -906,7 +908,7 @@ extern "C" int dnagpu_filter_keys(dnagpu_ctx *ctx, const uint64_t *d_keys, uint6
     TRY(launch(ctx, "filter_keys_count", [&] {
         k_filter_keys_count<<<tiles, kThreads, 0, ctx->stream>>>(d_keys, n, p, tile_cnt);
     }));
-    TRY(launch(ctx, "scan", [&] { k_scan_u64<<<1, 1024, 0, ctx->stream>>>(tile_cnt, tiles, tile_off); }));
+    TRY(scan_any(ctx, sc, tile_cnt, tiles, tile_off));
     TRY(read_u64(ctx, tile_off + tiles, &n_match));
     *n_out = n_match;
     if (!d_out || n_match == 0) return DNAGPU_OK;
@@ -1144,21 +1146,31 @@ static int part_tiles(dnagpu_ctx *ctx, Scratch &sc, const uint64_t *parent_off, 
     return scan_any(ctx, sc, tiles, n_parents, *out_tile_off);
 }
 
-/* GROUP BY kmer by radix partition + shared-memory count (partition.cuh) */
-static int count_partition(dnagpu_ctx *ctx, const CountInput &in, int k, dnagpu_stats *stats,
-                           dnagpu_table **table)
+/* ---- GROUP BY kmer by radix partition + shared-memory count (partition.cuh) -------------------- */
+/* bits of the two partition levels for n keys spread over n_parts owner ranks (1 = single GPU) */
+static void plan_bits(uint64_t n, uint32_t n_parts, int *b1, int *b2)
+{
+    const int b = bucket_bits(n);
+    if (n_parts <= 1) {
+        *b1 = b <= 11 ? b : b / 2;
+        *b2 = std::max(0, std::min(11, b - *b1));
+        return;
+    }
+    /* level 1 must separate the owners; level 2 merges the pieces that arrive from the peers */
+    *b1 = std::max(std::min(11, (b + 1) / 2), std::min(11, ceil_log2(n_parts) + 2));
+    *b2 = std::max(1, std::min(11, b - *b1));
+}
+
+/* Level 1: histogram, offsets (off1: device, P1 + 1 entries) and scatter into `out` (>= n + 2 keys).
+ * The device counters C_TOTAL / C_SIDE receive the rows kept by the WHERE clause / the 'G' x 32 rows. */
+static int part_level1(dnagpu_ctx *ctx, Scratch &sc, const CountInput &in, int k, int b1, uint64_t **keys_io,
+                       uint64_t cap, uint64_t **off1_out, uint64_t *n_out)
 {
     const uint64_t mask = kmer_mask(k);
     const int psmem = kTileKeys * (int)sizeof(uint64_t) + (int)sizeof(ScatterSmem);
-    Scratch sc(ctx);
-    uint64_t n = in.n; /* upper bound; exact after the level-1 histogram when a WHERE clause is fused */
-    const int b_bound = bucket_bits(n);
-    const int b1 = b_bound <= 11 ? b_bound : b_bound / 2;
     const uint32_t P1 = 1u << b1;
     const int shift1 = 64 - b1;
-    TRY(zero_counters(ctx));
-
-    /* ---- level 1: histogram, offsets, scatter ---- */
+    uint64_t n = in.n;
     unsigned long long *hist1, *cur1;
     uint64_t *off1, *root_off;
     TRY(sc.get((void **)&hist1, (uint64_t)P1 * 8));
@@ -1177,7 +1189,7 @@ static int count_partition(dnagpu_ctx *ctx, const CountInput &in, int k, dnagpu_
         TRY(part_tiles(ctx, sc, root_off, 1, kTileKeys, &root_tiles_scat));
         TRY(launch(ctx, "part_hist", [&] {
             k_part_hist_keys<<<grid_for(n, kSuperTile), kThreads, 0, ctx->stream>>>(
-                in.d_keys, root_off, root_tiles_hist, 1, shift1, P1, hist1);
+                in.d_keys, root_off, root_tiles_hist, 1, 1, shift1, P1, hist1);
         }));
     } else {
         const unsigned hgrid = (unsigned)std::min<uint64_t>(grid_for(in.v.n_items, kThreads), (uint64_t)ctx->sm_count * 8);
@@ -1189,37 +1201,50 @@ static int count_partition(dnagpu_ctx *ctx, const CountInput &in, int k, dnagpu_
         })));
     }
     TRY(scan_any(ctx, sc, (const uint64_t *)hist1, P1, off1));
-    if (in.filtered) { /* the WHERE clause decides how many keys there are */
+    uint64_t *out = *keys_io;
+    if (in.filtered || out) /* the WHERE clause decides how many keys there are; a caller's buffer must fit them */
         TRY(read_u64(ctx, off1 + P1, &n));
+    if (!out) {
+        TRY(sc.get((void **)&out, (n + 2) * 8));
+        *keys_io = out;
+    } else if (cap < n + 2) {
+        *n_out = n;
+        return fail(ctx, DNAGPU_ECAPACITY, "partition needs room for %llu keys (+2 pad)", (unsigned long long)n);
     }
-    uint64_t *bufA;
-    TRY(sc.get((void **)&bufA, (n + 2) * 8));
     if (in.d_keys) {
         TRY(launch(ctx, "part_scatter", [&] {
-            k_part_scatter_keys<true><<<grid_for(n, kTileKeys), kScatThreads, psmem, ctx->stream>>>(
-                in.d_keys, root_off, root_tiles_scat, 1, shift1, P1, off1, cur1, bufA, ctx->d_ctr);
+            k_part_scatter_keys<true><<<grid_for(in.n, kTileKeys), kScatThreads, psmem, ctx->stream>>>(
+                in.d_keys, root_off, root_tiles_scat, 1, 1, shift1, P1, off1, cur1, out, ctx->d_ctr);
         }));
     } else {
         const unsigned grid = grid_for(in.v.n_items, kScatThreads / 2);
         DISPATCH_LAYOUT(in.seq->layout, TRY(launch(ctx, "part_scatter", [&] {
             if (in.filtered)
                 k_part_scatter_seq<LY, true><<<grid, kScatThreads, psmem, ctx->stream>>>(
-                    in.v, in.p, mask, shift1, P1, off1, cur1, bufA, ctx->d_ctr);
+                    in.v, in.p, mask, shift1, P1, off1, cur1, out, ctx->d_ctr);
             else
                 k_part_scatter_seq<LY, false><<<grid, kScatThreads, psmem, ctx->stream>>>(
-                    in.v, in.p, mask, shift1, P1, off1, cur1, bufA, ctx->d_ctr);
+                    in.v, in.p, mask, shift1, P1, off1, cur1, out, ctx->d_ctr);
         })));
     }
+    *off1_out = off1;
+    *n_out = n;
+    return DNAGPU_OK;
+}
 
-    /* ---- level 2 inside every partition, when buckets are still too big ---- */
-    const int b_exact = bucket_bits(n);
-    const int b2 = std::max(0, std::min(11, b_exact - b1));
-    const uint64_t *bucket_keys = bufA, *bucket_off = off1;
-    uint64_t n_buckets = P1;
+/* Level 2 (inside every parent; parents with equal parent % n_groups merge into the same children)
+ * and the shared-memory count of every bucket.  Leaves distinct / unique in the device counters. */
+static int part_finish(dnagpu_ctx *ctx, Scratch &sc, const uint64_t *keys, uint64_t n, const uint64_t *parent_off,
+                       uint64_t n_parents, uint64_t n_groups, int b1, int b2, int k, dnagpu_stats *stats,
+                       uint64_t total_rows, dnagpu_table **table)
+{
+    const int psmem = kTileKeys * (int)sizeof(uint64_t) + (int)sizeof(ScatterSmem);
+    const uint64_t *bucket_keys = keys, *bucket_off = parent_off;
+    uint64_t n_buckets = n_parents;
     if (b2 > 0) {
         const uint32_t P2 = 1u << b2;
         const int shift2 = 64 - b1 - b2;
-        n_buckets = (uint64_t)P1 * P2;
+        n_buckets = n_groups * P2;
         unsigned long long *hist2, *cur2;
         uint64_t *off2, *tiles_hist, *tiles_scat, *bufB;
         TRY(sc.get((void **)&hist2, n_buckets * 8));
@@ -1228,22 +1253,20 @@ static int count_partition(dnagpu_ctx *ctx, const CountInput &in, int k, dnagpu_
         TRY(sc.get((void **)&bufB, (n + 2) * 8));
         CU(ctx, cudaMemsetAsync(hist2, 0, n_buckets * 8, ctx->stream));
         CU(ctx, cudaMemsetAsync(cur2, 0, n_buckets * 8, ctx->stream));
-        TRY(part_tiles(ctx, sc, off1, P1, kSuperTile, &tiles_hist));
-        TRY(part_tiles(ctx, sc, off1, P1, kTileKeys, &tiles_scat));
+        TRY(part_tiles(ctx, sc, parent_off, n_parents, kSuperTile, &tiles_hist));
+        TRY(part_tiles(ctx, sc, parent_off, n_parents, kTileKeys, &tiles_scat));
         TRY(launch(ctx, "part_hist2", [&] {
-            k_part_hist_keys<<<grid_for(n, kSuperTile) + P1, kThreads, 0, ctx->stream>>>(
-                bufA, off1, tiles_hist, P1, shift2, P2, hist2);
+            k_part_hist_keys<<<grid_for(n, kSuperTile) + (unsigned)n_parents, kThreads, 0, ctx->stream>>>(
+                keys, parent_off, tiles_hist, n_parents, n_groups, shift2, P2, hist2);
         }));
         TRY(scan_any(ctx, sc, (const uint64_t *)hist2, n_buckets, off2));
         TRY(launch(ctx, "part_scatter2", [&] {
-            k_part_scatter_keys<false><<<grid_for(n, kTileKeys) + P1, kScatThreads, psmem, ctx->stream>>>(
-                bufA, off1, tiles_scat, P1, shift2, P2, off2, cur2, bufB, ctx->d_ctr);
+            k_part_scatter_keys<false><<<grid_for(n, kTileKeys) + (unsigned)n_parents, kScatThreads, psmem, ctx->stream>>>(
+                keys, parent_off, tiles_scat, n_parents, n_groups, shift2, P2, off2, cur2, bufB, ctx->d_ctr);
         }));
         bucket_keys = bufB;
         bucket_off = off2;
     }
-
-    /* ---- count every bucket in shared memory ---- */
     const uint64_t spill_cap = std::max<uint64_t>(1ull << 16, n / 64);
     Slot *spill;
     TRY(sc.get((void **)&spill, spill_cap * sizeof(Slot)));
@@ -1272,7 +1295,7 @@ static int count_partition(dnagpu_ctx *ctx, const CountInput &in, int k, dnagpu_
         return fail(ctx, DNAGPU_EINTERNAL, "spill table of %llu slots overflowed", (unsigned long long)spill_cap);
     const uint64_t side = ctx->h_ctr[C_SIDE];
     const uint64_t keyed = ctx->h_ctr[C_DISTINCT];
-    stats->total = ctx->h_ctr[C_TOTAL];
+    stats->total = total_rows ? total_rows : ctx->h_ctr[C_TOTAL];
     stats->distinct = keyed + (side > 0);
     stats->unique = ctx->h_ctr[C_UNIQUE] + (side == 1);
     if (table) {
@@ -1301,6 +1324,24 @@ static int count_partition(dnagpu_ctx *ctx, const CountInput &in, int k, dnagpu_
     return DNAGPU_OK;
 }
 
+static int count_partition(dnagpu_ctx *ctx, const CountInput &in, int k, dnagpu_stats *stats,
+                           dnagpu_table **table)
+{
+    Scratch sc(ctx);
+    int b1, b2;
+    plan_bits(in.n, 1, &b1, &b2);
+    TRY(zero_counters(ctx));
+    uint64_t *off1, n, *keys = nullptr;
+    TRY(part_level1(ctx, sc, in, k, b1, &keys, 0, &off1, &n));
+    if (in.filtered) { /* fewer keys than rows: the second level may not be needed any more */
+        int e1, e2;
+        plan_bits(n, 1, &e1, &e2);
+        b2 = std::max(0, std::min(11, e1 + e2 - b1));
+    }
+    const uint64_t P1 = 1ull << b1;
+    return part_finish(ctx, sc, keys, n, off1, P1, P1, b1, b2, k, stats, 0, table);
+}
+
 static int count_any(dnagpu_ctx *ctx, CountInput &in, int k, const dnagpu_count_opts *opts,
                      dnagpu_stats *stats, dnagpu_table **table)
 {
@@ -1312,26 +1353,61 @@ static int count_any(dnagpu_ctx *ctx, CountInput &in, int k, const dnagpu_count_
         if (table) TRY(table_new(ctx, k, 0, table));
         return DNAGPU_OK;
     }
-    const int method = pick_method(opts, k, in.n);
+    int method = pick_method(opts, k, in.n);
     int rc;
+    /* A selective WHERE clause: evaluate it once into an ordered key list (two cheap predicate
+     * scans: count per tile, then write) and count that list, instead of dragging the whole
+     * input through the partition / hash machinery only to drop most of it. */
+    Scratch keep(ctx);
+    CountInput listed;
+    if (in.filtered && in.seq && method != DNAGPU_COUNT_DENSE) {
+        uint64_t *tile_off, n_match = 0;
+        TRY(filter_scan(ctx, in.seq, in.v, in.p, keep, &tile_off, &n_match));
+        if (n_match == 0) {
+            if (table) TRY(table_new(ctx, k, 0, table));
+            return DNAGPU_OK;
+        }
+        if (n_match <= in.n / 4) {
+            uint64_t *keys;
+            TRY(keep.get((void **)&keys, (n_match + 2) * 8));
+            const unsigned tiles = grid_for(in.v.n_items, kThreads);
+            const int smem = kThreads * 32 * (int)sizeof(uint64_t);
+            DISPATCH_LAYOUT(in.seq->layout, TRY(launch(ctx, "filter_write", [&] {
+                k_filter_write<LY><<<tiles, kThreads, smem, ctx->stream>>>(in.v, in.p, kmer_mask(k), tile_off, keys);
+            })));
+            listed.d_keys = keys;
+            listed.n = n_match;
+            dnagpu_count_opts o2 = opts ? *opts : dnagpu_count_opts{0, 0, 0.0, 0};
+            method = pick_method(&o2, k, n_match);
+            if (method == DNAGPU_COUNT_DENSE)
+                rc = n_match < 0xffffffffull ? count_dense_t<uint32_t>(ctx, listed, k, stats, table)
+                                             : count_dense_t<unsigned long long>(ctx, listed, k, stats, table);
+            else if (method == DNAGPU_COUNT_PARTITION)
+                rc = count_partition(ctx, listed, k, stats, table);
+            else
+                rc = count_hash(ctx, listed, k, opts, n_match, stats, table);
+            if (rc != DNAGPU_OK && table && *table) {
+                dnagpu_table_free(*table);
+                *table = nullptr;
+            }
+            return rc;
+        }
+        if (method == DNAGPU_COUNT_HASH) { /* not selective: fused insert into a table sized by n_match */
+            rc = count_hash(ctx, in, k, opts, n_match, stats, table);
+            if (rc != DNAGPU_OK && table && *table) {
+                dnagpu_table_free(*table);
+                *table = nullptr;
+            }
+            return rc;
+        }
+    }
     if (method == DNAGPU_COUNT_DENSE) {
         rc = in.n < 0xffffffffull ? count_dense_t<uint32_t>(ctx, in, k, stats, table)
                                   : count_dense_t<unsigned long long>(ctx, in, k, stats, table);
     } else if (method == DNAGPU_COUNT_PARTITION) {
         rc = count_partition(ctx, in, k, stats, table);
     } else {
-        uint64_t bound = in.n;
-        if (in.filtered && !(opts && opts->expected_keys)) {
-            /* size the table from the exact number of rows the WHERE clause keeps */
-            Scratch sc(ctx);
-            uint64_t *tile_off;
-            TRY(filter_scan(ctx, in.seq, in.v, in.p, sc, &tile_off, &bound));
-            if (bound == 0) {
-                if (table) TRY(table_new(ctx, k, 0, table));
-                return DNAGPU_OK;
-            }
-        }
-        rc = count_hash(ctx, in, k, opts, bound, stats, table);
+        rc = count_hash(ctx, in, k, opts, in.n, stats, table);
     }
     if (rc != DNAGPU_OK && table && *table) {
         dnagpu_table_free(*table);
@@ -1492,6 +1568,88 @@ extern "C" int dnagpu_partition(dnagpu_ctx *ctx, const dnagpu_seq *seq, int k,
     })));
     CU(ctx, cudaStreamSynchronize(ctx->stream)); /* h_ctr staging is reused by the next call */
     return DNAGPU_OK;
+}
+
+/* ---- multi-GPU GROUP BY with the owner routing fused into partition level 1 ---------------------- */
+extern "C" int dnagpu_shuffle_plan_make(uint64_t n_rows_total, uint32_t n_parts, dnagpu_shuffle_plan *plan)
+{
+    if (!plan || n_parts < 1 || n_parts > (uint32_t)kMaxParts)
+        return fail(nullptr, DNAGPU_EARG, "dnagpu_shuffle_plan_make: bad arguments");
+    int b1, b2;
+    plan_bits(n_rows_total, n_parts, &b1, &b2);
+    plan->bits1 = b1;
+    plan->bits2 = b2;
+    plan->n_parts = n_parts;
+    plan->n_digits = 1u << b1;
+    return DNAGPU_OK;
+}
+
+extern "C" uint32_t dnagpu_shuffle_owner(const dnagpu_shuffle_plan *plan, uint32_t digit)
+{
+    return (uint32_t)(((uint64_t)digit * plan->n_parts) >> plan->bits1);
+}
+
+extern "C" int dnagpu_shuffle_send(dnagpu_ctx *ctx, const dnagpu_seq *seq, int k, const dnagpu_where *filter,
+                                   const dnagpu_shuffle_plan *plan, uint64_t *d_out, uint64_t cap,
+                                   uint64_t *digit_counts, uint64_t *rows_kept, uint64_t *side_rows)
+{
+    if (!ctx || !seq || !plan || !d_out || !digit_counts)
+        return fail(ctx, DNAGPU_EARG, "dnagpu_shuffle_send: NULL argument");
+    TRY(check_k(ctx, k));
+    TRY(check_filter_literals(ctx, filter));
+    CU(ctx, cudaSetDevice(ctx->device));
+    CountInput in;
+    in.seq = seq;
+    TRY(make_view(ctx, seq, k, &in.v));
+    in.n = in.v.n_rows;
+    TRY(build_pred(ctx, filter, k, in.n, &in.p, &in.filtered));
+    for (uint32_t d = 0; d < plan->n_digits; ++d) digit_counts[d] = 0;
+    if (rows_kept) *rows_kept = 0;
+    if (side_rows) *side_rows = 0;
+    if (in.n == 0) return DNAGPU_OK;
+    Scratch sc(ctx);
+    TRY(zero_counters(ctx));
+    uint64_t *off1, n = 0, *keys = d_out;
+    TRY(part_level1(ctx, sc, in, k, plan->bits1, &keys, cap, &off1, &n));
+    std::vector<uint64_t> off((size_t)plan->n_digits + 1);
+    CU(ctx, cudaMemcpyAsync(off.data(), off1, off.size() * 8, cudaMemcpyDeviceToHost, ctx->stream));
+    TRY(fetch_counters(ctx)); /* synchronises the stream */
+    for (uint32_t d = 0; d < plan->n_digits; ++d) digit_counts[d] = off[d + 1] - off[d];
+    if (rows_kept) *rows_kept = ctx->h_ctr[C_TOTAL];
+    if (side_rows) *side_rows = ctx->h_ctr[C_SIDE];
+    return DNAGPU_OK;
+}
+
+extern "C" int dnagpu_shuffle_count(dnagpu_ctx *ctx, const uint64_t *d_keys, const uint64_t *piece_counts,
+                                    uint32_t n_pieces, uint32_t n_groups, const dnagpu_shuffle_plan *plan, int k,
+                                    dnagpu_stats *stats, dnagpu_table **table)
+{
+    if (!ctx || !plan || !piece_counts || !stats || n_groups == 0 || n_pieces % n_groups)
+        return fail(ctx, DNAGPU_EARG, "dnagpu_shuffle_count: bad arguments");
+    TRY(check_k(ctx, k));
+    CU(ctx, cudaSetDevice(ctx->device));
+    stats->total = stats->distinct = stats->unique = 0;
+    if (table) *table = nullptr;
+    std::vector<uint64_t> off((size_t)n_pieces + 1, 0);
+    for (uint32_t i = 0; i < n_pieces; ++i) off[i + 1] = off[i] + piece_counts[i];
+    const uint64_t n = off[n_pieces];
+    if (n == 0) {
+        if (table) TRY(table_new(ctx, k, 0, table));
+        return DNAGPU_OK;
+    }
+    if (!d_keys) return fail(ctx, DNAGPU_EARG, "dnagpu_shuffle_count: d_keys is NULL");
+    Scratch sc(ctx);
+    uint64_t *d_off;
+    TRY(sc.get((void **)&d_off, off.size() * 8));
+    CU(ctx, cudaMemcpyAsync(d_off, off.data(), off.size() * 8, cudaMemcpyHostToDevice, ctx->stream));
+    CU(ctx, cudaStreamSynchronize(ctx->stream)); /* `off` is a host temporary */
+    TRY(zero_counters(ctx));
+    int rc = part_finish(ctx, sc, d_keys, n, d_off, n_pieces, n_groups, plan->bits1, plan->bits2, k, stats, n, table);
+    if (rc != DNAGPU_OK && table && *table) {
+        dnagpu_table_free(*table);
+        *table = nullptr;
+    }
+    return rc;
 }
 
 /* ---- profiling --------------------------------------------------------------------------------- */

@@ -96,11 +96,13 @@ __global__ void __launch_bounds__(kThreads) k_part_hist_seq(SeqView sv, Pred p, 
         if (h[i]) atomicAdd(&hist[i], (unsigned long long)h[i]);
 }
 
-/* children of every parent partition: hist[parent * fan + digit] */
+/* children of every parent partition: hist[(parent % n_groups) * fan + digit].  n_groups < n_parents
+ * when the same partition arrived in several pieces (one per peer rank) that must merge. */
 __global__ void __launch_bounds__(kThreads) k_part_hist_keys(const uint64_t *__restrict__ keys,
                                                              const uint64_t *__restrict__ parent_off,
                                                              const uint64_t *__restrict__ tile_off,
-                                                             uint64_t n_parents, int shift, uint32_t fan,
+                                                             uint64_t n_parents, uint64_t n_groups, int shift,
+                                                             uint32_t fan,
                                                              unsigned long long *__restrict__ hist)
 {
     __shared__ uint32_t h[kMaxFan];
@@ -122,7 +124,7 @@ __global__ void __launch_bounds__(kThreads) k_part_hist_keys(const uint64_t *__r
             if (x[u] != kEmpty) atomicAdd(&h[digit_of(part_hash(x[u]), shift, fm)], 1u);
     }
     __syncthreads();
-    unsigned long long *dst = hist + parent * fan;
+    unsigned long long *dst = hist + (parent % n_groups) * fan;
     for (uint32_t i = threadIdx.x; i < fan; i += kThreads)
         if (h[i]) atomicAdd(&dst[i], (unsigned long long)h[i]);
 }
@@ -315,7 +317,8 @@ template <bool COUNT_SIDE>
 __global__ void __launch_bounds__(kScatThreads, 2) k_part_scatter_keys(const uint64_t *__restrict__ keys,
                                                                        const uint64_t *__restrict__ parent_off,
                                                                        const uint64_t *__restrict__ tile_off,
-                                                                       uint64_t n_parents, int shift, uint32_t fan,
+                                                                       uint64_t n_parents, uint64_t n_groups, int shift,
+                                                                       uint32_t fan,
                                                                        const uint64_t *__restrict__ child_off,
                                                                        unsigned long long *__restrict__ child_cur,
                                                                        uint64_t *__restrict__ out,
@@ -350,7 +353,7 @@ __global__ void __launch_bounds__(kScatThreads, 2) k_part_scatter_keys(const uin
     }
     __syncthreads();
     long long gd[kPlanPer];
-    const uint32_t total = scatter_plan(s, fan, child_off + parent * fan, child_cur + parent * fan, gd);
+    const uint32_t total = scatter_plan(s, fan, child_off + (parent % n_groups) * fan, child_cur + (parent % n_groups) * fan, gd);
 #pragma unroll
     for (int u = 0; u < kScatPer; ++u) {
         const uint32_t r = (u & 1) ? (rk[u >> 1] >> 16) : (rk[u >> 1] & 0xffffu);

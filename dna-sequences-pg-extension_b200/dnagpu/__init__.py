@@ -14,7 +14,7 @@ from dataclasses import dataclass
 import numpy as np
 
 from . import _lib
-from ._lib import CountOpts, Stats, Where
+from ._lib import CountOpts, ShufflePlan, Stats, Where
 from .types import Dna, DnaError, Kmer, Qkmer, QKMER_ALPHABET, kmer_strings
 
 COUNT_AUTO, COUNT_DENSE, COUNT_HASH, COUNT_PARTITION = 0, 1, 2, 3
@@ -202,6 +202,13 @@ class Context:
         self._ok(self.lib.dnagpu_seq_upload(self.handle, words_ptr, n_bases, C.byref(h)))
         return Seq(self, h)
 
+    def upload_reads_ptr(self, words_ptr, n_reads, bases_per_read, stride_words):
+        """Upload a fixed-stride batch from a raw host pointer (pinned memory); asynchronous."""
+        h = C.c_void_p()
+        self._ok(self.lib.dnagpu_seq_upload_reads(self.handle, words_ptr, n_reads, bases_per_read, stride_words,
+                                                  C.byref(h)))
+        return Seq(self, h)
+
     def upload_reads(self, words, n_reads, bases_per_read, stride_words):
         words = np.ascontiguousarray(words, dtype=np.uint64)
         h = C.c_void_p()
@@ -371,6 +378,14 @@ class Context:
                                              C.byref(w) if w is not None else None, C.byref(st), None))
         return st
 
+    def count_reads_ptr(self, words_ptr, n_reads, bases_per_read, stride_words, k, prefix=None, pattern=None):
+        """The C-ABI host call for a batch of reads on a raw host pointer: stats only."""
+        w, _keep = _where(prefix, pattern)
+        st = Stats()
+        self._ok(self.lib.dnagpu_count_reads(self.handle, words_ptr, n_reads, bases_per_read, stride_words, k,
+                                             C.byref(w) if w is not None else None, C.byref(st), None))
+        return st
+
     def count_reads(self, words, n_reads, bases_per_read, stride_words, k, prefix=None, pattern=None,
                     table=True):
         words = np.ascontiguousarray(words, dtype=np.uint64)
@@ -401,6 +416,30 @@ class Context:
         self._ok(self.lib.dnagpu_partition(self.handle, seq.handle, k, wp, n_parts, out.data_ptr(), out.numel(),
                                            counts.ctypes.data_as(_lib.u64p)))
         return out[:int(counts.sum())], counts
+
+    # ---- fused owner routing (partition level 1 = exchange layout) ---------------------------------
+    def shuffle_plan(self, n_rows_total, n_parts):
+        plan = ShufflePlan()
+        self._ok(self.lib.dnagpu_shuffle_plan_make(n_rows_total, n_parts, C.byref(plan)))
+        return plan
+
+    def shuffle_send(self, seq, k, plan, out, prefix=None, pattern=None):
+        """-> (digit_counts[n_digits], rows_kept, side_rows); keys by digit in `out` (torch int64 tensor)."""
+        w, _keep = _where(prefix, pattern)
+        counts = np.zeros(plan.n_digits, dtype=np.uint64)
+        kept, side = C.c_uint64(), C.c_uint64()
+        self._ok(self.lib.dnagpu_shuffle_send(self.handle, seq.handle, k, C.byref(w) if w is not None else None,
+                                              C.byref(plan), out.data_ptr(), out.numel(),
+                                              counts.ctypes.data_as(_lib.u64p), C.byref(kept), C.byref(side)))
+        return counts, int(kept.value), int(side.value)
+
+    def shuffle_count(self, keys, piece_counts, n_groups, plan, k, table=False):
+        piece_counts = np.ascontiguousarray(piece_counts, dtype=np.uint64)
+        st, th = Stats(), C.c_void_p()
+        self._ok(self.lib.dnagpu_shuffle_count(self.handle, keys.data_ptr() if keys is not None else None,
+                                               piece_counts.ctypes.data_as(_lib.u64p), piece_counts.size, n_groups,
+                                               C.byref(plan), k, C.byref(st), C.byref(th) if table else None))
+        return st, (Table(self, th) if table else None)
 
     # ---- profiling ----------------------------------------------------------------------------
     def profile(self, on=True):

@@ -25,6 +25,10 @@ class Stats(C.Structure):
     _fields_ = [("total", C.c_uint64), ("distinct", C.c_uint64), ("unique", C.c_uint64)]
 
 
+class ShufflePlan(C.Structure):
+    _fields_ = [("bits1", C.c_int32), ("bits2", C.c_int32), ("n_parts", C.c_uint32), ("n_digits", C.c_uint32)]
+
+
 class CountOpts(C.Structure):
     _fields_ = [("method", C.c_int32), ("warp_aggregate", C.c_int32),
                 ("load_factor", C.c_double), ("expected_keys", C.c_uint64)]
@@ -75,6 +79,12 @@ SIGNATURES = {
     "dnagpu_table_free": (None, [vp]),
     "dnagpu_owner_of": (C.c_uint32, [u64, C.c_uint32]),
     "dnagpu_partition": (C.c_int, [vp, vp, C.c_int, C.POINTER(Where), C.c_uint32, vp, u64, u64p]),
+    "dnagpu_shuffle_plan_make": (C.c_int, [u64, C.c_uint32, C.POINTER(ShufflePlan)]),
+    "dnagpu_shuffle_owner": (C.c_uint32, [C.POINTER(ShufflePlan), C.c_uint32]),
+    "dnagpu_shuffle_send": (C.c_int, [vp, vp, C.c_int, C.POINTER(Where), C.POINTER(ShufflePlan), vp, u64, u64p,
+                                      u64p, u64p]),
+    "dnagpu_shuffle_count": (C.c_int, [vp, vp, u64p, C.c_uint32, C.c_uint32, C.POINTER(ShufflePlan), C.c_int,
+                                       C.POINTER(Stats), C.POINTER(vp)]),
     "dnagpu_profile_enable": (C.c_int, [vp, C.c_int]),
     "dnagpu_profile_reset": (C.c_int, [vp]),
     "dnagpu_profile_query": (C.c_int, [vp, C.c_char_p, C.POINTER(C.c_double), u64p]),

@@ -61,6 +61,49 @@ class GpuEngine:
         return self.torch.device("cuda", self.ctx.device)
 
 
+def owner_digits(plan, rank):
+    """Digits [lo, hi) of partition level 1 that `rank` owns: owner(d) = d * n_parts >> bits1."""
+    n = plan.n_digits
+    lo = (rank * n + plan.n_parts - 1) // plan.n_parts
+    hi = ((rank + 1) * n + plan.n_parts - 1) // plan.n_parts
+    return lo, hi
+
+
+def count_sharded_fused(ctx, seq, k, n_rows_total, world, rank, buffers, prefix=None, pattern=None, group=None):
+    """The same query with the owner routing fused into partition level 1 (dnagpu_shuffle_*):
+    one scatter pass lays the shard out by hash digit, each owner's digits are one contiguous
+    slice of that buffer, the all-to-all ships the slices, and the receiver finishes with
+    level 2 + count.  `buffers` is a dict reused across calls (send / recv tensors)."""
+    import torch
+    import torch.distributed as dist
+    dev = torch.device("cuda", ctx.device)
+    plan = ctx.shuffle_plan(n_rows_total, world)
+    need = seq.kmer_count(k) + 2
+    if buffers.get("send") is None or buffers["send"].numel() < need:
+        buffers["send"] = torch.empty(need, dtype=torch.int64, device=dev)
+    digit_counts, kept, side = ctx.shuffle_send(seq, k, plan, buffers["send"], prefix=prefix, pattern=pattern)
+    ranges = [owner_digits(plan, r) for r in range(world)]
+    lo, hi = ranges[rank]
+    n_mine = hi - lo
+    # every peer tells me how many keys each of MY digits holds on it (peer-major, digit order)
+    counts_dev = torch.from_numpy(digit_counts.astype(np.int64)).to(dev)
+    mine_from_all = torch.empty(world * n_mine, dtype=torch.int64, device=dev)
+    dist.all_to_all_single(mine_from_all, counts_dev, [n_mine] * world, [b - a for a, b in ranges], group=group)
+    pieces = mine_from_all.cpu().numpy().astype(np.uint64)
+    send_splits = [int(digit_counts[a:b].sum()) for a, b in ranges]
+    recv_splits = [int(pieces[p * n_mine:(p + 1) * n_mine].sum()) for p in range(world)]
+    n_recv = sum(recv_splits)
+    if buffers.get("recv") is None or buffers["recv"].numel() < n_recv + 2:
+        buffers["recv"] = torch.empty(int(n_recv * 1.05) + 2, dtype=torch.int64, device=dev)
+    recv = buffers["recv"][:n_recv]
+    dist.all_to_all_single(recv, buffers["send"][:sum(send_splits)], recv_splits, send_splits, group=group)
+    st, _ = ctx.shuffle_count(recv, pieces, n_mine, plan, k)
+    agg = torch.tensor([kept, st.distinct, st.unique, side], dtype=torch.int64, device=dev)
+    dist.all_reduce(agg, group=group)
+    total, distinct, unique, side_all = (int(x) for x in agg.cpu().tolist())
+    return total, distinct + (side_all > 0), unique + (side_all == 1)
+
+
 def count_sharded(engine, seq, k, world, prefix=None, pattern=None, group=None, load_factor=0.0):
     """One pass of the sharded query on this rank -> global (total, distinct, unique)."""
     import torch

@@ -249,6 +249,34 @@ int dnagpu_partition(dnagpu_ctx *ctx, const dnagpu_seq *seq, int k,
                      const dnagpu_where *filter, uint32_t n_parts, uint64_t *d_out,
                      uint64_t cap, uint64_t *part_counts);
 
+/*
+ * The faster multi-GPU form: the owner routing IS level 1 of the radix partition.  Every rank
+ * partitions its shard by the top `bits1` bits of the partition hash into n_digits buckets laid
+ * out in digit order; owner(digit) = digit * n_parts >> bits1, so what goes to one owner is ONE
+ * contiguous slice of d_out and the all-to-all needs no separate bucketing pass.  The receiver
+ * gets, from every peer, the pieces of the digits it owns (n_groups of them per peer, in digit
+ * order, peer-major) and finishes with level 2 + the shared-memory count; pieces of the same digit
+ * merge.  All ranks must build the plan from the same (n_rows_total, n_parts).
+ */
+typedef struct dnagpu_shuffle_plan {
+    int32_t bits1, bits2; /* hash bits of partition level 1 (exchange) and level 2 (local) */
+    uint32_t n_parts;     /* owner ranks                                                  */
+    uint32_t n_digits;    /* 1 << bits1                                                   */
+} dnagpu_shuffle_plan;
+int dnagpu_shuffle_plan_make(uint64_t n_rows_total, uint32_t n_parts, dnagpu_shuffle_plan *plan);
+uint32_t dnagpu_shuffle_owner(const dnagpu_shuffle_plan *plan, uint32_t digit);
+/* Extract (+filter) this rank's k-mers and lay them out by digit in d_out (cap >= rows + 2).
+ * digit_counts (host, n_digits entries) receives the keys per digit; rows_kept the rows that
+ * passed the WHERE clause; side_rows the 'G' x 32 rows (k = 32), which are not in d_out. */
+int dnagpu_shuffle_send(dnagpu_ctx *ctx, const dnagpu_seq *seq, int k, const dnagpu_where *filter,
+                        const dnagpu_shuffle_plan *plan, uint64_t *d_out, uint64_t cap,
+                        uint64_t *digit_counts, uint64_t *rows_kept, uint64_t *side_rows);
+/* Count what arrived: n_pieces = n_peers * n_groups pieces of piece_counts[i] keys each, stored
+ * back to back in d_keys; piece i holds digit (i % n_groups) of this owner. */
+int dnagpu_shuffle_count(dnagpu_ctx *ctx, const uint64_t *d_keys, const uint64_t *piece_counts,
+                         uint32_t n_pieces, uint32_t n_groups, const dnagpu_shuffle_plan *plan, int k,
+                         dnagpu_stats *stats, dnagpu_table **table);
+
 /* ---- per-kernel device timing (CUDA events on the ctx stream) --------------- */
 int dnagpu_profile_enable(dnagpu_ctx *ctx, int on);
 int dnagpu_profile_reset(dnagpu_ctx *ctx);

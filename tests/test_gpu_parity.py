@@ -356,6 +356,59 @@ def test_count_keys_and_partition_compose_to_the_single_gpu_answer(gpu):
     seq.free()
 
 
+@pytest.mark.parametrize("k,prefix", [(31, None), (32, None), (21, "AC")])
+def test_fused_owner_routing_composes_to_the_single_gpu_answer(gpu, k, prefix):
+    """dnagpu_shuffle_send / _count: G ranks emulated one after the other on one device.  Every shard is laid
+    out by partition digit, each owner receives its digit slices peer-major, merges and counts."""
+    import torch
+    from dnagpu.distributed import owner_digits, shard_of
+    n = 3_000_000
+    words = R.synth_seq(31, n)
+    pk = R.kmer_make(prefix) if prefix else None
+    oracle = R.count_query(words, 1, n, words.size, k, prefix=pk, faithful=False, threads=4)
+    for G in (1, 2, 3, 8):
+        plan = gpu.shuffle_plan(n - k + 1, G)
+        sends = []
+        kept_all = side_all = 0
+        for r in range(G):
+            first, starts = shard_of(n, k, G, r)
+            seq = gpu.synth_range(n, 31, 8, first, starts, k)
+            buf = torch.empty(seq.kmer_count(k) + 2, dtype=torch.int64, device="cuda")
+            counts, kept, side = gpu.shuffle_send(seq, k, plan, buf, prefix=prefix)
+            offs = np.concatenate([[0], np.cumsum(counts)]).astype(np.int64)
+            sends.append((buf, counts, offs))
+            kept_all += kept
+            side_all += side
+            seq.free()
+        assert kept_all == oracle.total
+        tot = [0, 0]
+        kk_all, cc_all = [], []
+        for o in range(G):
+            lo, hi = owner_digits(plan, o)
+            assert all(gpu.lib.dnagpu_shuffle_owner(plan, d) == o for d in (lo, hi - 1)) if hi > lo else True
+            pieces, chunks = [], []
+            for buf, counts, offs in sends:                    # peer-major, digits in order
+                pieces.extend(int(c) for c in counts[lo:hi])
+                chunks.append(buf[int(offs[lo]):int(offs[hi])])
+            recv = torch.cat(chunks) if chunks else torch.empty(0, dtype=torch.int64, device="cuda")
+            st, table = gpu.shuffle_count(recv, np.array(pieces, dtype=np.uint64), hi - lo, plan, k, table=True)
+            assert st.total == sum(pieces)
+            tot[0] += st.distinct
+            tot[1] += st.unique
+            a, b = table.fetch()
+            kk_all.append(a)
+            cc_all.append(b)
+        want_d, want_u = oracle.distinct, oracle.unique
+        assert tot[0] + (side_all > 0) == want_d and tot[1] + (side_all == 1) == want_u, (G, k)
+        kk = np.concatenate(kk_all)
+        cc = np.concatenate(cc_all)
+        if side_all:
+            kk = np.append(kk, np.uint64(2**64 - 1))
+            cc = np.append(cc, np.uint64(side_all))
+        order = np.argsort(kk)
+        assert np.array_equal(kk[order], oracle.kmers) and np.array_equal(cc[order], oracle.counts), (G, k)
+
+
 def test_shards_with_overlap_cover_the_sequence_once(gpu):
     """Base-range shards with a (k-1)-base overlap (synth_range + start limit) reproduce the
     k-mers of the whole sequence exactly once."""
