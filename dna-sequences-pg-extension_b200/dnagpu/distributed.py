@@ -74,14 +74,25 @@ def count_sharded_fused(ctx, seq, k, n_rows_total, world, rank, buffers, prefix=
     one scatter pass lays the shard out by hash digit, each owner's digits are one contiguous
     slice of that buffer, the all-to-all ships the slices, and the receiver finishes with
     level 2 + count.  `buffers` is a dict reused across calls (send / recv tensors)."""
+    import os
+    import time
     import torch
     import torch.distributed as dist
     dev = torch.device("cuda", ctx.device)
+    trace = os.environ.get("DNAGPU_TRACE") == "1" and rank == 0
+    marks = []
+
+    def mark(name):
+        if trace:
+            torch.cuda.synchronize(dev)
+            marks.append((name, time.perf_counter()))
+    mark("start")
     plan = ctx.shuffle_plan(n_rows_total, world)
     need = seq.kmer_count(k) + 2
     if buffers.get("send") is None or buffers["send"].numel() < need:
         buffers["send"] = torch.empty(need, dtype=torch.int64, device=dev)
     digit_counts, kept, side = ctx.shuffle_send(seq, k, plan, buffers["send"], prefix=prefix, pattern=pattern)
+    mark("level1")
     ranges = [owner_digits(plan, r) for r in range(world)]
     lo, hi = ranges[rank]
     n_mine = hi - lo
@@ -96,11 +107,19 @@ def count_sharded_fused(ctx, seq, k, n_rows_total, world, rank, buffers, prefix=
     if buffers.get("recv") is None or buffers["recv"].numel() < n_recv + 2:
         buffers["recv"] = torch.empty(int(n_recv * 1.05) + 2, dtype=torch.int64, device=dev)
     recv = buffers["recv"][:n_recv]
+    mark("counts")
     dist.all_to_all_single(recv, buffers["send"][:sum(send_splits)], recv_splits, send_splits, group=group)
+    mark("all_to_all")
     st, _ = ctx.shuffle_count(recv, pieces, n_mine, plan, k)
+    mark("level2+count")
     agg = torch.tensor([kept, st.distinct, st.unique, side], dtype=torch.int64, device=dev)
     dist.all_reduce(agg, group=group)
     total, distinct, unique, side_all = (int(x) for x in agg.cpu().tolist())
+    mark("all_reduce")
+    if trace:
+        import sys
+        print("trace ms: " + ", ".join(f"{b[0]} {1e3 * (b[1] - a[1]):.2f}" for a, b in zip(marks, marks[1:])),
+              file=sys.stderr, flush=True)
     return total, distinct + (side_all > 0), unique + (side_all == 1)
 
 
