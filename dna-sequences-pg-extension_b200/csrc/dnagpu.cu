@@ -809,7 +809,7 @@ static int filter_scan(dnagpu_ctx *ctx, const dnagpu_seq *seq, const SeqView &v,
     TRY(sc.get((void **)&tile_cnt, ((uint64_t)tiles + 1) * 8));
     TRY(sc.get((void **)tile_off, ((uint64_t)tiles + 1) * 8));
     DISPATCH_LAYOUT(seq->layout, TRY(launch(ctx, "filter_count", [&] {
-        k_filter_count<LY><<<tiles, kThreads, 0, ctx->stream>>>(v, p, tile_cnt);
+        k_filter_count<LY><<<(tiles + kFilterTiles - 1) / kFilterTiles, kThreads, 0, ctx->stream>>>(v, p, tile_cnt);
     })));
     TRY(scan_any(ctx, sc, tile_cnt, tiles, *tile_off));
     return read_u64(ctx, *tile_off + tiles, n_match);
@@ -847,7 +847,8 @@ extern "C" int dnagpu_filter(dnagpu_ctx *ctx, const dnagpu_seq *seq, int k,
     const unsigned tiles = grid_for(v.n_items, kThreads);
     const int smem = kThreads * 32 * (int)sizeof(uint64_t);
     DISPATCH_LAYOUT(seq->layout, TRY(launch(ctx, "filter_write", [&] {
-        k_filter_write<LY><<<tiles, kThreads, smem, ctx->stream>>>(v, p, kmer_mask(k), tile_off, d_out);
+        k_filter_write<LY><<<(tiles + kFilterTiles - 1) / kFilterTiles, kThreads, smem, ctx->stream>>>(
+            v, p, kmer_mask(k), tile_off, d_out);
     })));
     return DNAGPU_OK;
 }
@@ -1373,7 +1374,8 @@ static int count_any(dnagpu_ctx *ctx, CountInput &in, int k, const dnagpu_count_
             const unsigned tiles = grid_for(in.v.n_items, kThreads);
             const int smem = kThreads * 32 * (int)sizeof(uint64_t);
             DISPATCH_LAYOUT(in.seq->layout, TRY(launch(ctx, "filter_write", [&] {
-                k_filter_write<LY><<<tiles, kThreads, smem, ctx->stream>>>(in.v, in.p, kmer_mask(k), tile_off, keys);
+                k_filter_write<LY><<<(tiles + kFilterTiles - 1) / kFilterTiles, kThreads, smem, ctx->stream>>>(
+                    in.v, in.p, kmer_mask(k), tile_off, keys);
             })));
             listed.d_keys = keys;
             listed.n = n_match;

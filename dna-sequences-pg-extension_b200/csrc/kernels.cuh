@@ -280,6 +280,11 @@ __global__ void __launch_bounds__(kThreads) k_extract(SeqView sv, uint64_t mask,
  *   k_filter_write  recompute, rank inside the CTA, stage in shared memory, store
  *                   each CTA's matches as one contiguous, coalesced run.
  * ================================================================================= */
+/* The WHERE clause over the 32 start positions of one item, branch-free.  The low plane (the
+ * packed words themselves) and the high plane (the same 128 bits shifted right by one) are
+ * formed once; the window of start j is then two constant-amount funnel shifts per plane, and
+ * the test is three LOP3 per 32-bit half (pred_ok's select tree) + one AND + one compare.
+ * Bit j of the result is set iff start j < c passes. */
 template <int L>
 __device__ __forceinline__ uint32_t item_match_mask(const SeqView &sv, const Pred &p, uint64_t t,
                                                     uint64_t &w0, uint64_t &w1, int &c)
@@ -288,31 +293,56 @@ __device__ __forceinline__ uint32_t item_match_mask(const SeqView &sv, const Pre
     const uint64_t *w = locate_item<L>(sv, t, c, row0);
     w0 = ld_nc(w);
     w1 = ld_nc(w + 1);
+    const uint32_t a[5] = {(uint32_t)w0, (uint32_t)(w0 >> 32), (uint32_t)w1, (uint32_t)(w1 >> 32), 0u};
+    const uint32_t h[5] = {__funnelshift_r(a[0], a[1], 1), __funnelshift_r(a[1], a[2], 1),
+                           __funnelshift_r(a[2], a[3], 1), a[3] >> 1, 0u};
+    const uint32_t mal = (uint32_t)p.ma, mah = (uint32_t)(p.ma >> 32), mtl = (uint32_t)p.mt,
+                   mth = (uint32_t)(p.mt >> 32), mcl = (uint32_t)p.mc, mch = (uint32_t)(p.mc >> 32),
+                   mgl = (uint32_t)p.mg, mgh = (uint32_t)(p.mg >> 32);
     uint32_t m = 0;
-    roll_item<32>(w0, w1, c, [&](uint64_t x, int j) { m |= (uint32_t)pred_ok(p, x) << j; });
-    return m;
+#pragma unroll
+    for (int j = 0; j < 32; ++j) {
+        const int q = (2 * j) >> 5, s = (2 * j) & 31; /* compile-time after unrolling */
+        const uint32_t xl = s ? __funnelshift_r(a[q], a[q + 1], s) : a[q];
+        const uint32_t xh = s ? __funnelshift_r(a[q + 1], a[q + 2], s) : a[q + 1];
+        const uint32_t hl = s ? __funnelshift_r(h[q], h[q + 1], s) : h[q];
+        const uint32_t hh = s ? __funnelshift_r(h[q + 1], h[q + 2], s) : h[q + 1];
+        const uint32_t s0l = (xl & mtl) | (~xl & mal), s1l = (xl & mgl) | (~xl & mcl);
+        const uint32_t s0h = (xh & mth) | (~xh & mah), s1h = (xh & mgh) | (~xh & mch);
+        const uint32_t ml = (hl & s1l) | (~hl & s0l), mh = (hh & s1h) | (~hh & s0h);
+        m |= (uint32_t)((ml & mh) == 0xffffffffu) << j;
+    }
+    return c >= 32 ? m : (m & ((1u << c) - 1u));
 }
+
+constexpr int kFilterTiles = 4; /* tiles of kThreads items one CTA walks (fewer, longer-lived CTAs) */
 
 template <int L>
 __global__ void __launch_bounds__(kThreads) k_filter_count(SeqView sv, Pred p,
                                                            uint64_t *__restrict__ tile_counts)
 {
-    __shared__ uint32_t wsum[kThreads / 32];
-    uint64_t t = (uint64_t)blockIdx.x * kThreads + threadIdx.x;
-    uint32_t n = 0;
-    if (t < sv.n_items) {
-        uint64_t w0, w1;
-        int c;
-        n = __popc(item_match_mask<L>(sv, p, t, w0, w1, c));
+    __shared__ uint32_t wsum[kFilterTiles][kThreads / 32];
+    const uint64_t n_tiles = (sv.n_items + kThreads - 1) / kThreads;
+#pragma unroll
+    for (int i = 0; i < kFilterTiles; ++i) {
+        const uint64_t tile = (uint64_t)blockIdx.x * kFilterTiles + i;
+        const uint64_t t = tile * kThreads + threadIdx.x;
+        uint32_t n = 0;
+        if (t < sv.n_items) {
+            uint64_t w0, w1;
+            int c;
+            n = __popc(item_match_mask<L>(sv, p, t, w0, w1, c));
+        }
+        n = warp_sum32(n);
+        if ((threadIdx.x & 31) == 0) wsum[i][threadIdx.x >> 5] = n;
     }
-    n = warp_sum32(n);
-    if ((threadIdx.x & 31) == 0) wsum[threadIdx.x >> 5] = n;
     __syncthreads();
-    if (threadIdx.x == 0) {
+    if (threadIdx.x < kFilterTiles) {
+        const uint64_t tile = (uint64_t)blockIdx.x * kFilterTiles + threadIdx.x;
         uint32_t s = 0;
 #pragma unroll
-        for (int i = 0; i < kThreads / 32; ++i) s += wsum[i];
-        tile_counts[blockIdx.x] = s;
+        for (int w = 0; w < kThreads / 32; ++w) s += wsum[threadIdx.x][w];
+        if (tile < n_tiles) tile_counts[tile] = s;
     }
 }
 
@@ -322,21 +352,27 @@ __global__ void __launch_bounds__(kThreads) k_filter_write(SeqView sv, Pred p, u
                                                            uint64_t *__restrict__ out)
 {
     extern __shared__ uint64_t stage[]; /* kThreads * 32 entries */
-    uint64_t t = (uint64_t)blockIdx.x * kThreads + threadIdx.x;
-    uint32_t m = 0;
-    uint64_t w0 = 0, w1 = 0;
-    int c = 0;
-    if (t < sv.n_items) m = item_match_mask<L>(sv, p, t, w0, w1, c);
-    uint32_t total;
-    uint32_t rank = block_exscan(__popc(m), &total);
-    while (m) {
-        int j = __ffs(m) - 1;
-        m &= m - 1;
-        stage[rank++] = window(w0, w1, 2 * j) & mask;
+    const uint64_t n_tiles = (sv.n_items + kThreads - 1) / kThreads;
+    for (int i = 0; i < kFilterTiles; ++i) {
+        const uint64_t tile = (uint64_t)blockIdx.x * kFilterTiles + i;
+        if (tile >= n_tiles) break; /* uniform */
+        const uint64_t t = tile * kThreads + threadIdx.x;
+        uint32_t m = 0;
+        uint64_t w0 = 0, w1 = 0;
+        int c = 0;
+        if (t < sv.n_items) m = item_match_mask<L>(sv, p, t, w0, w1, c);
+        uint32_t total;
+        uint32_t rank = block_exscan(__popc(m), &total);
+        while (m) {
+            int j = __ffs(m) - 1;
+            m &= m - 1;
+            stage[rank++] = window(w0, w1, 2 * j) & mask;
+        }
+        __syncthreads();
+        uint64_t *dst = out + tile_off[tile];
+        for (uint32_t q = threadIdx.x; q < total; q += kThreads) st_cs(dst + q, stage[q]);
+        __syncthreads();
     }
-    __syncthreads();
-    uint64_t *dst = out + tile_off[blockIdx.x];
-    for (uint32_t i = threadIdx.x; i < total; i += kThreads) st_cs(dst + i, stage[i]);
 }
 
 /* the same predicates over a materialised kmer column (seq scan of test.sql:220-262) */
