@@ -207,7 +207,8 @@ def run_b200(args):
     import torch
     import torch.distributed as dist
     import dnagpu
-    from dnagpu.distributed import GpuEngine, count_sharded, count_sharded_fused, reads_shard_of, shard_of
+    from dnagpu.distributed import (GpuEngine, PeerExchange, count_sharded, count_sharded_fused, count_sharded_peer,
+                                    reads_shard_of, shard_of)
 
     rank, world, local = dist_env()
     n_bases, k, seed, desc = WORKLOADS[args.workload]
@@ -252,14 +253,24 @@ def run_b200(args):
 
         engine = GpuEngine(ctx) if world > 1 else None
         xbuf = {}
+        px = None
+        if world > 1 and args.exchange == "peer":
+            try:  # collective: raises on every rank or on none
+                px = PeerExchange(ctx, world, rank, int(n_rows_total / world * 1.15) + (1 << 20))
+            except RuntimeError as e:
+                if rank == 0:
+                    print(f"bench: {e}; falling back to --exchange fused", file=sys.stderr)
+                args.exchange = "fused"
 
         def count_resident(s):
             """One pass of the hot path with the packed words resident in HBM -> (total, distinct, unique)."""
             if world == 1:
                 st, _ = ctx.count(s, k, table=False, load_factor=args.load_factor, **where)
                 return st.total, st.distinct, st.unique
+            if args.exchange == "peer":
+                return count_sharded_peer(ctx, s, k, n_rows_total, world, rank, px, **where)
             if args.exchange == "fused":
-                return count_sharded_fused(ctx, s, k, n_rows_total, world, rank, xbuf, **where)
+                return count_sharded_fused(ctx, s, k, n_rows_total, world, rank, xbuf, chunks=args.chunks, **where)
             return count_sharded(engine, s, k, world, load_factor=args.load_factor, **where)
 
         def count_e2e():
@@ -405,7 +416,10 @@ def run_b200(args):
                        "repeat_every": REPEAT_EVERY, "block_bases": 1024,
                        "l2": "inputs (packed words + hash table) larger than L2; no flush needed",
                        "parallelism": "single GPU" if world == 1 else
-                       f"{world} base-range shards + owner-hash all-to-all (NCCL), exchange={args.exchange}",
+                       f"{world} base-range shards, k-mers routed to owner GPUs by hash; exchange={args.exchange} (" +
+                       {"peer": "level-1 scatter kernel stores into the owners' memory over NVLink, no all-to-all",
+                        "fused": "level-1 layout + one NCCL all-to-all",
+                        "routed": "dnagpu_partition + NCCL all-to-all + dnagpu_count_keys"}[args.exchange] + ")",
                        "load_factor": args.load_factor or 0.5},
             "result": {"total": stats[0], "distinct": stats[1], "unique": stats[2]},
             "e2e": {"value": e2e_value, "unit": "Gkmer/s", "steps": args.e2e_steps,
@@ -418,6 +432,8 @@ def run_b200(args):
             "extract": extract, "clocks": clocks,
         }
         print(json.dumps(line), flush=True)
+    if px is not None:
+        px.close()
     seq.free()
     ctx.close()
     if world > 1:
@@ -437,8 +453,10 @@ def main():
     ap.add_argument("--load-factor", type=float, default=0.0)
     ap.add_argument("--cpu-sample", type=int, default=16_000_000)
     ap.add_argument("--no-extract", action="store_true")
-    ap.add_argument("--exchange", default="fused", choices=["fused", "routed"],
-                    help="N > 1: owner routing fused into partition level 1, or the separate dnagpu_partition pass")
+    ap.add_argument("--chunks", type=int, default=4, help="N > 1: digit sub-ranges the exchange is pipelined in")
+    ap.add_argument("--exchange", default="peer", choices=["peer", "fused", "routed"],
+                    help="N > 1: peer = scatter kernel stores into the owners' memory over NVLink (no all-to-all); "
+                         "fused = level-1 layout + NCCL all-to-all; routed = separate dnagpu_partition pass")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
     if args.impl == "reference":

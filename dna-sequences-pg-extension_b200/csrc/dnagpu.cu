@@ -256,6 +256,17 @@ extern "C" int dnagpu_create(dnagpu_ctx **out, int device)
         PSMEM_ATTR((k_part_scatter_seq<kRagged, false>));
         PSMEM_ATTR((k_part_scatter_seq<kRagged, true>));
         PSMEM_ATTR(k_part_scatter_keys<false>);
+        {
+            const int psmem32 = 32 * kScatThreads * (int)sizeof(uint64_t) + (int)sizeof(ScatterSmem);
+#define PSMEM32_ATTR(kern) cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, psmem32)
+            PSMEM32_ATTR((k_part_scatter_seq<kSingle, false, 32>));
+            PSMEM32_ATTR((k_part_scatter_seq<kSingle, true, 32>));
+            PSMEM32_ATTR((k_part_scatter_seq<kFixed, false, 32>));
+            PSMEM32_ATTR((k_part_scatter_seq<kFixed, true, 32>));
+            PSMEM32_ATTR((k_part_scatter_seq<kRagged, false, 32>));
+            PSMEM32_ATTR((k_part_scatter_seq<kRagged, true, 32>));
+#undef PSMEM32_ATTR
+        }
         PSMEM_ATTR(k_part_scatter_keys<true>);
 #undef PSMEM_ATTR
         const int bsmem = kBucketSlots * 12;
@@ -1157,8 +1168,9 @@ static void plan_bits(uint64_t n, uint32_t n_parts, int *b1, int *b2)
         *b2 = std::max(0, std::min(11, b - *b1));
         return;
     }
-    /* level 1 must separate the owners; level 2 merges the pieces that arrive from the peers */
-    *b1 = std::max(std::min(11, (b + 1) / 2), std::min(11, ceil_log2(n_parts) + 2));
+    /* level 1 must separate the owners; level 2 merges the pieces that arrive from the peers.  Level 1
+     * gets as FEW bits as two levels allow: its runs are what crosses NVLink, and they should be long. */
+    *b1 = std::min(11, std::max(b - 11, ceil_log2(n_parts) + 2));
     *b2 = std::max(1, std::min(11, b - *b1));
 }
 
@@ -1218,15 +1230,29 @@ static int part_level1(dnagpu_ctx *ctx, Scratch &sc, const CountInput &in, int k
                 in.d_keys, root_off, root_tiles_scat, 1, 1, shift1, P1, off1, cur1, out, ctx->d_ctr);
         }));
     } else {
-        const unsigned grid = grid_for(in.v.n_items, kScatThreads / 2);
-        DISPATCH_LAYOUT(in.seq->layout, TRY(launch(ctx, "part_scatter", [&] {
-            if (in.filtered)
-                k_part_scatter_seq<LY, true><<<grid, kScatThreads, psmem, ctx->stream>>>(
-                    in.v, in.p, mask, shift1, P1, off1, cur1, out, ctx->d_ctr);
-            else
-                k_part_scatter_seq<LY, false><<<grid, kScatThreads, psmem, ctx->stream>>>(
-                    in.v, in.p, mask, shift1, P1, off1, cur1, out, ctx->d_ctr);
-        })));
+        static const bool per32 = getenv("DNAGPU_SCATTER_PER") && atoi(getenv("DNAGPU_SCATTER_PER")) == 32;
+        if (per32) { /* experiment: 16384-key tiles, one CTA per SM */
+            const int psmem32 = 32 * kScatThreads * (int)sizeof(uint64_t) + (int)sizeof(ScatterSmem);
+            const unsigned grid = grid_for(in.v.n_items, kScatThreads);
+            DISPATCH_LAYOUT(in.seq->layout, TRY(launch(ctx, "part_scatter", [&] {
+                if (in.filtered)
+                    k_part_scatter_seq<LY, true, 32><<<grid, kScatThreads, psmem32, ctx->stream>>>(
+                        in.v, in.p, mask, shift1, P1, off1, cur1, out, ctx->d_ctr);
+                else
+                    k_part_scatter_seq<LY, false, 32><<<grid, kScatThreads, psmem32, ctx->stream>>>(
+                        in.v, in.p, mask, shift1, P1, off1, cur1, out, ctx->d_ctr);
+            })));
+        } else {
+            const unsigned grid = grid_for(in.v.n_items, kScatThreads / 2);
+            DISPATCH_LAYOUT(in.seq->layout, TRY(launch(ctx, "part_scatter", [&] {
+                if (in.filtered)
+                    k_part_scatter_seq<LY, true><<<grid, kScatThreads, psmem, ctx->stream>>>(
+                        in.v, in.p, mask, shift1, P1, off1, cur1, out, ctx->d_ctr);
+                else
+                    k_part_scatter_seq<LY, false><<<grid, kScatThreads, psmem, ctx->stream>>>(
+                        in.v, in.p, mask, shift1, P1, off1, cur1, out, ctx->d_ctr);
+            })));
+        }
     }
     *off1_out = off1;
     *n_out = n;
@@ -1652,6 +1678,150 @@ extern "C" int dnagpu_shuffle_count(dnagpu_ctx *ctx, const uint64_t *d_keys, con
         *table = nullptr;
     }
     return rc;
+}
+
+/* ---- the exchange fused into the scatter kernel: stores straight into peer memory ---------------- */
+extern "C" int dnagpu_peer_alloc(dnagpu_ctx *ctx, uint64_t bytes, void **d_ptr, unsigned char handle[64])
+{
+    if (!ctx || !d_ptr || !handle) return fail(ctx, DNAGPU_EARG, "dnagpu_peer_alloc: NULL argument");
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
+    CU(ctx, cudaSetDevice(ctx->device));
+    *d_ptr = nullptr;
+    cudaError_t e = cudaMalloc(d_ptr, bytes ? bytes : 16); /* IPC needs a plain allocation, not the pool */
+    if (e != cudaSuccess) {
+        cudaGetLastError();
+        return fail(ctx, DNAGPU_ENOMEM, "peer allocation of %llu bytes failed: %s", (unsigned long long)bytes,
+                    cudaGetErrorString(e));
+    }
+    cudaIpcMemHandle_t h;
+    e = cudaIpcGetMemHandle(&h, *d_ptr);
+    if (e != cudaSuccess) {
+        cudaFree(*d_ptr);
+        *d_ptr = nullptr;
+        cudaGetLastError();
+        return fail(ctx, DNAGPU_ECUDA, "cudaIpcGetMemHandle: %s", cudaGetErrorString(e));
+    }
+    memcpy(handle, &h, 64);
+    return DNAGPU_OK;
+}
+
+extern "C" int dnagpu_peer_open(dnagpu_ctx *ctx, const unsigned char handle[64], void **d_ptr)
+{
+    if (!ctx || !d_ptr || !handle) return fail(ctx, DNAGPU_EARG, "dnagpu_peer_open: NULL argument");
+    CU(ctx, cudaSetDevice(ctx->device));
+    cudaIpcMemHandle_t h;
+    memcpy(&h, handle, 64);
+    cudaError_t e = cudaIpcOpenMemHandle(d_ptr, h, cudaIpcMemLazyEnablePeerAccess);
+    if (e != cudaSuccess) {
+        cudaGetLastError();
+        return fail(ctx, DNAGPU_ECUDA, "cudaIpcOpenMemHandle: %s (is peer access available between the GPUs?)",
+                    cudaGetErrorString(e));
+    }
+    return DNAGPU_OK;
+}
+
+extern "C" int dnagpu_peer_close(dnagpu_ctx *ctx, void *d_ptr)
+{
+    if (!ctx) return fail(ctx, DNAGPU_EARG, "ctx is NULL");
+    CU(ctx, cudaSetDevice(ctx->device));
+    if (d_ptr) CU(ctx, cudaIpcCloseMemHandle(d_ptr));
+    return DNAGPU_OK;
+}
+
+extern "C" int dnagpu_peer_free(dnagpu_ctx *ctx, void *d_ptr)
+{
+    if (!ctx) return fail(ctx, DNAGPU_EARG, "ctx is NULL");
+    CU(ctx, cudaSetDevice(ctx->device));
+    CU(ctx, cudaStreamSynchronize(ctx->stream));
+    if (d_ptr) CU(ctx, cudaFree(d_ptr));
+    return DNAGPU_OK;
+}
+
+/* shared front end of the two fused-exchange calls */
+static int shuffle_input(dnagpu_ctx *ctx, const dnagpu_seq *seq, int k, const dnagpu_where *filter, CountInput *in)
+{
+    TRY(check_k(ctx, k));
+    TRY(check_filter_literals(ctx, filter));
+    CU(ctx, cudaSetDevice(ctx->device));
+    in->seq = seq;
+    TRY(make_view(ctx, seq, k, &in->v));
+    in->n = in->v.n_rows;
+    return build_pred(ctx, filter, k, in->n, &in->p, &in->filtered);
+}
+
+extern "C" int dnagpu_shuffle_hist(dnagpu_ctx *ctx, const dnagpu_seq *seq, int k, const dnagpu_where *filter,
+                                   const dnagpu_shuffle_plan *plan, uint64_t *digit_counts)
+{
+    if (!ctx || !seq || !plan || !digit_counts) return fail(ctx, DNAGPU_EARG, "dnagpu_shuffle_hist: NULL argument");
+    CountInput in;
+    TRY(shuffle_input(ctx, seq, k, filter, &in));
+    for (uint32_t d = 0; d < plan->n_digits; ++d) digit_counts[d] = 0;
+    if (in.n == 0) return DNAGPU_OK;
+    Scratch sc(ctx);
+    const uint32_t P1 = plan->n_digits;
+    unsigned long long *hist1;
+    TRY(sc.get((void **)&hist1, (uint64_t)P1 * 8));
+    CU(ctx, cudaMemsetAsync(hist1, 0, (uint64_t)P1 * 8, ctx->stream));
+    const uint64_t mask = kmer_mask(k);
+    const int shift1 = 64 - plan->bits1;
+    const unsigned hgrid = (unsigned)std::min<uint64_t>(grid_for(in.v.n_items, kThreads), (uint64_t)ctx->sm_count * 8);
+    DISPATCH_LAYOUT(seq->layout, TRY(launch(ctx, "part_hist", [&] {
+        if (in.filtered)
+            k_part_hist_seq<LY, true><<<hgrid, kThreads, 0, ctx->stream>>>(in.v, in.p, mask, shift1, P1, hist1);
+        else
+            k_part_hist_seq<LY, false><<<hgrid, kThreads, 0, ctx->stream>>>(in.v, in.p, mask, shift1, P1, hist1);
+    })));
+    CU(ctx, cudaMemcpyAsync(digit_counts, hist1, (uint64_t)P1 * 8, cudaMemcpyDeviceToHost, ctx->stream));
+    CU(ctx, cudaStreamSynchronize(ctx->stream));
+    return DNAGPU_OK;
+}
+
+extern "C" int dnagpu_shuffle_scatter_to(dnagpu_ctx *ctx, const dnagpu_seq *seq, int k, const dnagpu_where *filter,
+                                         const dnagpu_shuffle_plan *plan, const uint64_t *digit_dest,
+                                         uint64_t *rows_kept, uint64_t *side_rows)
+{
+    if (!ctx || !seq || !plan || !digit_dest)
+        return fail(ctx, DNAGPU_EARG, "dnagpu_shuffle_scatter_to: NULL argument");
+    CountInput in;
+    TRY(shuffle_input(ctx, seq, k, filter, &in));
+    if (rows_kept) *rows_kept = 0;
+    if (side_rows) *side_rows = 0;
+    if (in.n == 0) return DNAGPU_OK;
+    Scratch sc(ctx);
+    const uint32_t P1 = plan->n_digits;
+    /* the kernel adds "index of the run" to a base pointer; with a NULL base and addresses / 8
+     * as indices the same kernel stores to arbitrary (peer) destinations per digit */
+    std::vector<uint64_t> idx(P1);
+    for (uint32_t d = 0; d < P1; ++d) {
+        if (digit_dest[d] & 7) return fail(ctx, DNAGPU_EARG, "destination of digit %u is not 8-byte aligned", d);
+        idx[d] = digit_dest[d] >> 3;
+    }
+    uint64_t *d_idx;
+    unsigned long long *cur1;
+    TRY(sc.get((void **)&d_idx, ((uint64_t)P1 + 1) * 8));
+    TRY(sc.get((void **)&cur1, (uint64_t)P1 * 8));
+    CU(ctx, cudaMemcpyAsync(d_idx, idx.data(), (uint64_t)P1 * 8, cudaMemcpyHostToDevice, ctx->stream));
+    CU(ctx, cudaMemsetAsync(cur1, 0, (uint64_t)P1 * 8, ctx->stream));
+    CU(ctx, cudaStreamSynchronize(ctx->stream)); /* idx is a host temporary */
+    TRY(zero_counters(ctx));
+    const uint64_t mask = kmer_mask(k);
+    const int shift1 = 64 - plan->bits1;
+    /* 16384-key tiles (one CTA per SM): a (tile, digit) run is twice as long as in the local scatter,
+     * which is what the NVLink stores want */
+    const int psmem = 32 * kScatThreads * (int)sizeof(uint64_t) + (int)sizeof(ScatterSmem);
+    const unsigned grid = grid_for(in.v.n_items, kScatThreads);
+    DISPATCH_LAYOUT(seq->layout, TRY(launch(ctx, "part_scatter_peer", [&] {
+        if (in.filtered)
+            k_part_scatter_seq<LY, true, 32><<<grid, kScatThreads, psmem, ctx->stream>>>(
+                in.v, in.p, mask, shift1, P1, d_idx, cur1, (uint64_t *)nullptr, ctx->d_ctr);
+        else
+            k_part_scatter_seq<LY, false, 32><<<grid, kScatThreads, psmem, ctx->stream>>>(
+                in.v, in.p, mask, shift1, P1, d_idx, cur1, (uint64_t *)nullptr, ctx->d_ctr);
+    })));
+    TRY(fetch_counters(ctx)); /* synchronises: every store of this rank has been issued and retired */
+    if (rows_kept) *rows_kept = ctx->h_ctr[C_TOTAL];
+    if (side_rows) *side_rows = ctx->h_ctr[C_SIDE];
+    return DNAGPU_OK;
 }
 
 /* ---- profiling --------------------------------------------------------------------------------- */

@@ -202,11 +202,12 @@ __device__ __forceinline__ void scatter_publish(ScatterSmem &s, uint32_t fan, co
 /* stage -> global: consecutive threads copy consecutive stage entries, i.e. whole runs.  The digit of
  * a staged key is recomputed (one multiply) rather than kept in a side array: the kernel is bound by
  * L1 data-pipe wavefronts (ncu: 67 % busy), not by ALU work. */
+template <int PER = kScatPer>
 __device__ __forceinline__ void scatter_flush(const ScatterSmem &s, const uint64_t *stage, uint32_t total,
                                               int shift, uint32_t fm, uint64_t *__restrict__ out)
 {
 #pragma unroll
-    for (int u = 0; u < kScatPer; ++u) {
+    for (int u = 0; u < PER; ++u) {
         const uint32_t i = (uint32_t)u * kScatThreads + threadIdx.x;
         if (i < total) {
             const uint64_t x = stage[i];
@@ -215,12 +216,14 @@ __device__ __forceinline__ void scatter_flush(const ScatterSmem &s, const uint64
     }
 }
 
-/* one thread = HALF an item: 16 consecutive start positions of one packed word.
+/* one thread = PER consecutive start positions of one packed word (PER = 16: half an item, a tile of
+ * 8192 keys, two CTAs per SM; PER = 32: a whole item, a tile of 16384 keys, one CTA per SM -- twice the
+ * run length per (tile, digit), used when the runs are stored into peer memory over NVLink).
  * Straight-line code: a key that is not scattered (past the end, rejected by the WHERE
  * clause, or the k = 32 sentinel) is ranked into the dummy bin cur[fan] and its stores
- * are predicated off, so the 16-step loops carry no branches. */
-template <int L, bool FILTER>
-__global__ void __launch_bounds__(kScatThreads, 2) k_part_scatter_seq(SeqView sv, Pred p, uint64_t mask, int shift,
+ * are predicated off, so the unrolled loops carry no branches. */
+template <int L, bool FILTER, int PER = kScatPer>
+__global__ void __launch_bounds__(kScatThreads, (PER == 16 ? 2 : 1)) k_part_scatter_seq(SeqView sv, Pred p, uint64_t mask, int shift,
                                                                       uint32_t fan,
                                                                       const uint64_t *__restrict__ child_off,
                                                                       unsigned long long *__restrict__ child_cur,
@@ -229,7 +232,7 @@ __global__ void __launch_bounds__(kScatThreads, 2) k_part_scatter_seq(SeqView sv
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     uint64_t *stage = reinterpret_cast<uint64_t *>(smem_raw);
-    ScatterSmem &s = *reinterpret_cast<ScatterSmem *>(smem_raw + sizeof(uint64_t) * kTileKeys);
+    ScatterSmem &s = *reinterpret_cast<ScatterSmem *>(smem_raw + sizeof(uint64_t) * (PER * kScatThreads));
 #ifdef DNAGPU_PHASE_TIMING
     long long tq[6];
     tq[0] = clock64();
@@ -240,12 +243,14 @@ __global__ void __launch_bounds__(kScatThreads, 2) k_part_scatter_seq(SeqView sv
     for (uint32_t i = threadIdx.x; i <= fan; i += kScatThreads) s.cur[i] = 0;
     __syncthreads();
     const uint32_t fm = fan - 1;
-    const uint64_t t = (uint64_t)blockIdx.x * (kScatThreads / 2) + (threadIdx.x >> 1);
-    const int half = threadIdx.x & 1;
-    uint64_t a0 = 0, a1 = 0; /* the 16 windows of this half start at bit 0 of a0 */
+    constexpr int SPLIT = 32 / PER; /* threads sharing one packed word */
+    constexpr uint32_t TILE = PER * kScatThreads;
+    const uint64_t t = (uint64_t)blockIdx.x * (kScatThreads / SPLIT) + (threadIdx.x / SPLIT);
+    const int half = threadIdx.x % SPLIT;
+    uint64_t a0 = 0, a1 = 0; /* the PER windows of this thread start at bit 0 of a0 */
     int c = 0;
     uint32_t side = 0, kept = 0;
-    uint32_t rk[kScatPer / 2]; /* two 16-bit ranks per register; the digit is recomputed */
+    uint32_t rk[PER / 2]; /* two 16-bit ranks per register; the digit is recomputed */
     if (t < sv.n_items) {
         uint64_t row0;
         int cc;
@@ -253,13 +258,13 @@ __global__ void __launch_bounds__(kScatThreads, 2) k_part_scatter_seq(SeqView sv
         uint64_t w0 = ld_nc(w), w1 = ld_nc(w + 1);
         a0 = half ? (w0 >> 32) | (w1 << 32) : w0;
         a1 = half ? (w1 >> 32) : w1;
-        c = min(16, max(0, cc - 16 * half));
+        c = min(PER, max(0, cc - PER * half));
     }
     uint32_t real_mask = 0; /* bit j: start j is scattered */
     {
         uint64_t cur = a0, nxt = a1;
 #pragma unroll
-        for (int j = 0; j < kScatPer; ++j) {
+        for (int j = 0; j < PER; ++j) {
             const uint64_t x = cur & mask;
             const bool keep = (j < c) & (!FILTER || pred_ok(p, cur));
             const bool real = keep & (x != kEmpty);
@@ -282,11 +287,11 @@ __global__ void __launch_bounds__(kScatThreads, 2) k_part_scatter_seq(SeqView sv
     {
         uint64_t cur = a0, nxt = a1;
 #pragma unroll
-        for (int j = 0; j < kScatPer; ++j) {
+        for (int j = 0; j < PER; ++j) {
             const uint64_t x = cur & mask;
             const uint32_t r = (j & 1) ? (rk[j >> 1] >> 16) : (rk[j >> 1] & 0xffffu);
             const uint32_t d = digit_of(part_hash(x), shift, fm);
-            const uint32_t pos = (s.cur[d] + r) & (kTileKeys - 1);
+            const uint32_t pos = (s.cur[d] + r) & (TILE - 1);
             if (real_mask & (1u << j)) stage[pos] = x;
             cur = (cur >> 2) | (nxt << 62);
             nxt >>= 2;
@@ -295,7 +300,7 @@ __global__ void __launch_bounds__(kScatThreads, 2) k_part_scatter_seq(SeqView sv
     scatter_publish(s, fan, gd);
     __syncthreads();
     PHASE_MARK(4);
-    scatter_flush(s, stage, total, shift, fm, out);
+    scatter_flush<PER>(s, stage, total, shift, fm, out);
     PHASE_MARK(5);
 #ifdef DNAGPU_PHASE_TIMING
     if (threadIdx.x == 0) {

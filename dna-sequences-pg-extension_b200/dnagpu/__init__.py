@@ -441,6 +441,48 @@ class Context:
                                                C.byref(plan), k, C.byref(st), C.byref(th) if table else None))
         return st, (Table(self, th) if table else None)
 
+    # ---- exchange fused into the scatter kernel (peer memory) ------------------------------------
+    def peer_alloc(self, n_bytes):
+        """-> (device address, 64-byte IPC handle) of a receive buffer other ranks can map."""
+        p, h = C.c_void_p(), C.create_string_buffer(64)
+        self._ok(self.lib.dnagpu_peer_alloc(self.handle, n_bytes, C.byref(p), h))
+        return int(p.value), h.raw
+
+    def peer_open(self, handle):
+        p = C.c_void_p()
+        self._ok(self.lib.dnagpu_peer_open(self.handle, handle, C.byref(p)))
+        return int(p.value)
+
+    def peer_close(self, addr):
+        self._ok(self.lib.dnagpu_peer_close(self.handle, C.c_void_p(addr)))
+
+    def peer_free(self, addr):
+        self._ok(self.lib.dnagpu_peer_free(self.handle, C.c_void_p(addr)))
+
+    def shuffle_hist(self, seq, k, plan, prefix=None, pattern=None):
+        w, _keep = _where(prefix, pattern)
+        counts = np.zeros(plan.n_digits, dtype=np.uint64)
+        self._ok(self.lib.dnagpu_shuffle_hist(self.handle, seq.handle, k, C.byref(w) if w is not None else None,
+                                              C.byref(plan), counts.ctypes.data_as(_lib.u64p)))
+        return counts
+
+    def shuffle_scatter_to(self, seq, k, plan, digit_dest, prefix=None, pattern=None):
+        w, _keep = _where(prefix, pattern)
+        digit_dest = np.ascontiguousarray(digit_dest, dtype=np.uint64)
+        kept, side = C.c_uint64(), C.c_uint64()
+        self._ok(self.lib.dnagpu_shuffle_scatter_to(self.handle, seq.handle, k, C.byref(w) if w is not None else None,
+                                                    C.byref(plan), digit_dest.ctypes.data_as(_lib.u64p),
+                                                    C.byref(kept), C.byref(side)))
+        return int(kept.value), int(side.value)
+
+    def shuffle_count_addr(self, addr, piece_counts, n_groups, plan, k):
+        """dnagpu_shuffle_count on a raw device address (a peer-allocated receive buffer)."""
+        piece_counts = np.ascontiguousarray(piece_counts, dtype=np.uint64)
+        st = Stats()
+        self._ok(self.lib.dnagpu_shuffle_count(self.handle, C.c_void_p(addr), piece_counts.ctypes.data_as(_lib.u64p),
+                                               piece_counts.size, n_groups, C.byref(plan), k, C.byref(st), None))
+        return st
+
     # ---- profiling ----------------------------------------------------------------------------
     def profile(self, on=True):
         self._ok(self.lib.dnagpu_profile_enable(self.handle, 1 if on else 0))

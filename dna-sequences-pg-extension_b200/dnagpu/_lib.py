@@ -85,6 +85,13 @@ SIGNATURES = {
                                       u64p, u64p]),
     "dnagpu_shuffle_count": (C.c_int, [vp, vp, u64p, C.c_uint32, C.c_uint32, C.POINTER(ShufflePlan), C.c_int,
                                        C.POINTER(Stats), C.POINTER(vp)]),
+    "dnagpu_peer_alloc": (C.c_int, [vp, u64, C.POINTER(vp), C.c_char_p]),
+    "dnagpu_peer_open": (C.c_int, [vp, C.c_char_p, C.POINTER(vp)]),
+    "dnagpu_peer_close": (C.c_int, [vp, vp]),
+    "dnagpu_peer_free": (C.c_int, [vp, vp]),
+    "dnagpu_shuffle_hist": (C.c_int, [vp, vp, C.c_int, C.POINTER(Where), C.POINTER(ShufflePlan), u64p]),
+    "dnagpu_shuffle_scatter_to": (C.c_int, [vp, vp, C.c_int, C.POINTER(Where), C.POINTER(ShufflePlan), u64p, u64p,
+                                            u64p]),
     "dnagpu_profile_enable": (C.c_int, [vp, C.c_int]),
     "dnagpu_profile_reset": (C.c_int, [vp]),
     "dnagpu_profile_query": (C.c_int, [vp, C.c_char_p, C.POINTER(C.c_double), u64p]),

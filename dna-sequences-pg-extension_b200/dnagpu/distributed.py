@@ -69,11 +69,17 @@ def owner_digits(plan, rank):
     return lo, hi
 
 
-def count_sharded_fused(ctx, seq, k, n_rows_total, world, rank, buffers, prefix=None, pattern=None, group=None):
+def count_sharded_fused(ctx, seq, k, n_rows_total, world, rank, buffers, prefix=None, pattern=None, group=None,
+                        chunks=4):
     """The same query with the owner routing fused into partition level 1 (dnagpu_shuffle_*):
     one scatter pass lays the shard out by hash digit, each owner's digits are one contiguous
     slice of that buffer, the all-to-all ships the slices, and the receiver finishes with
-    level 2 + count.  `buffers` is a dict reused across calls (send / recv tensors)."""
+    level 2 + count.
+
+    The exchange is cut into `chunks` digit sub-ranges: all of them are enqueued up front on
+    NCCL's stream, and the level 2 + count of sub-range c runs (on the library's stream) while
+    sub-range c+1 is still crossing NVLink.  Digits are disjoint across sub-ranges, so the
+    aggregates just add.  `buffers` is a dict reused across calls (send / recv tensors)."""
     import os
     import time
     import torch
@@ -91,7 +97,8 @@ def count_sharded_fused(ctx, seq, k, n_rows_total, world, rank, buffers, prefix=
     need = seq.kmer_count(k) + 2
     if buffers.get("send") is None or buffers["send"].numel() < need:
         buffers["send"] = torch.empty(need, dtype=torch.int64, device=dev)
-    digit_counts, kept, side = ctx.shuffle_send(seq, k, plan, buffers["send"], prefix=prefix, pattern=pattern)
+    send = buffers["send"]
+    digit_counts, kept, side = ctx.shuffle_send(seq, k, plan, send, prefix=prefix, pattern=pattern)
     mark("level1")
     ranges = [owner_digits(plan, r) for r in range(world)]
     lo, hi = ranges[rank]
@@ -100,19 +107,40 @@ def count_sharded_fused(ctx, seq, k, n_rows_total, world, rank, buffers, prefix=
     counts_dev = torch.from_numpy(digit_counts.astype(np.int64)).to(dev)
     mine_from_all = torch.empty(world * n_mine, dtype=torch.int64, device=dev)
     dist.all_to_all_single(mine_from_all, counts_dev, [n_mine] * world, [b - a for a, b in ranges], group=group)
-    pieces = mine_from_all.cpu().numpy().astype(np.uint64)
-    send_splits = [int(digit_counts[a:b].sum()) for a, b in ranges]
-    recv_splits = [int(pieces[p * n_mine:(p + 1) * n_mine].sum()) for p in range(world)]
-    n_recv = sum(recv_splits)
+    pieces = mine_from_all.cpu().numpy().astype(np.uint64).reshape(world, n_mine)
+    digit_off = np.concatenate([[0], np.cumsum(digit_counts)]).astype(np.int64)
+    n_recv = int(pieces.sum())
     if buffers.get("recv") is None or buffers["recv"].numel() < n_recv + 2:
         buffers["recv"] = torch.empty(int(n_recv * 1.05) + 2, dtype=torch.int64, device=dev)
-    recv = buffers["recv"][:n_recv]
     mark("counts")
-    dist.all_to_all_single(recv, buffers["send"][:sum(send_splits)], recv_splits, send_splits, group=group)
-    mark("all_to_all")
-    st, _ = ctx.shuffle_count(recv, pieces, n_mine, plan, k)
-    mark("level2+count")
-    agg = torch.tensor([kept, st.distinct, st.unique, side], dtype=torch.int64, device=dev)
+    chunks = max(1, min(chunks, min(b - a for a, b in ranges)))  # every owner has >= 1 digit per sub-range
+    jobs, recv_pos = [], 0
+    for c in range(chunks):
+        # sub-range c of every owner r: digits [a + c*(b-a)//chunks, a + (c+1)*(b-a)//chunks)
+        sub = [(a + c * (b - a) // chunks, a + (c + 1) * (b - a) // chunks) for a, b in ranges]
+        send_splits = [int(digit_off[y] - digit_off[x]) for x, y in sub]
+        mlo, mhi = sub[rank][0] - lo, sub[rank][1] - lo
+        my_pieces = np.ascontiguousarray(pieces[:, mlo:mhi])
+        recv_splits = [int(v) for v in my_pieces.sum(axis=1)]
+        n_c = sum(recv_splits)
+        recv_c = buffers["recv"][recv_pos:recv_pos + n_c]
+        recv_pos += n_c
+        # list form of the all-to-all: the slices of the owners are not adjacent in `send`, no packing copy
+        src_list = [send[int(digit_off[x]):int(digit_off[x]) + n] for (x, _), n in zip(sub, send_splits)]
+        dst_list, pos = [], 0
+        for n in recv_splits:
+            dst_list.append(recv_c[pos:pos + n])
+            pos += n
+        work = dist.all_to_all(dst_list, src_list, group=group, async_op=True)
+        jobs.append((work, recv_c, my_pieces.reshape(-1), mhi - mlo))
+    distinct = unique = 0
+    for work, recv_c, my_pieces, groups in jobs:
+        work.wait()
+        st, _ = ctx.shuffle_count(recv_c, my_pieces, groups, plan, k)
+        distinct += st.distinct
+        unique += st.unique
+    mark("exchange+level2+count")
+    agg = torch.tensor([kept, distinct, unique, side], dtype=torch.int64, device=dev)
     dist.all_reduce(agg, group=group)
     total, distinct, unique, side_all = (int(x) for x in agg.cpu().tolist())
     mark("all_reduce")
@@ -120,6 +148,87 @@ def count_sharded_fused(ctx, seq, k, n_rows_total, world, rank, buffers, prefix=
         import sys
         print("trace ms: " + ", ".join(f"{b[0]} {1e3 * (b[1] - a[1]):.2f}" for a, b in zip(marks, marks[1:])),
               file=sys.stderr, flush=True)
+    return total, distinct + (side_all > 0), unique + (side_all == 1)
+
+
+class PeerExchange:
+    """Receive buffers mapped across the ranks of one node (CUDA IPC), for the exchange that is fused
+    into the scatter kernel.  One per process; `capacity_keys` keys per rank."""
+
+    def __init__(self, ctx, world, rank, capacity_keys, group=None):
+        """Collective.  Raises on EVERY rank if any rank cannot allocate or map (no IPC / no peer access),
+        so that the callers can all fall back to the NCCL exchange together."""
+        import torch.distributed as dist
+        self.ctx, self.world, self.rank, self.capacity = ctx, world, rank, int(capacity_keys)
+        self.local, self.base, handle, err = 0, [], None, None
+        try:
+            self.local, handle = ctx.peer_alloc(8 * (self.capacity + 2))
+        except Exception as e:  # noqa: BLE001 - reported collectively below
+            err = str(e)
+        got = [None] * world
+        dist.all_gather_object(got, (err, handle), group=group)
+        if any(e for e, _ in got):
+            if self.local:
+                ctx.peer_free(self.local)
+            raise RuntimeError("peer exchange unavailable: " + "; ".join(e for e, _ in got if e))
+        opened = []
+        try:
+            for r in range(world):
+                self.base.append(self.local if r == rank else ctx.peer_open(got[r][1]))
+                if r != rank:
+                    opened.append(self.base[-1])
+        except Exception as e:  # noqa: BLE001
+            err = str(e)
+        got = [None] * world
+        dist.all_gather_object(got, err, group=group)
+        if any(got):
+            for a in opened:
+                ctx.peer_close(a)
+            ctx.peer_free(self.local)
+            raise RuntimeError("peer exchange unavailable: " + "; ".join(e for e in got if e))
+
+    def close(self):
+        import torch.distributed as dist
+        dist.barrier()
+        for r, a in enumerate(self.base):
+            if r != self.rank:
+                self.ctx.peer_close(a)
+        dist.barrier()
+        self.ctx.peer_free(self.local)
+
+
+def count_sharded_peer(ctx, seq, k, n_rows_total, world, rank, px, prefix=None, pattern=None, group=None):
+    """The sharded query with the exchange fused into the level-1 scatter kernel: no all-to-all.
+
+    hist (per-digit counts) -> all-gather of the counts (world x n_digits int64, the only
+    collective besides a barrier and the final all-reduce) -> every rank scatters its k-mers
+    straight into the owners' receive buffers over NVLink (peer-mapped addresses, one contiguous
+    run per (tile, digit)) -> barrier -> level 2 + count of the local receive buffer."""
+    import torch
+    import torch.distributed as dist
+    dev = torch.device("cuda", ctx.device)
+    plan = ctx.shuffle_plan(n_rows_total, world)
+    mine = ctx.shuffle_hist(seq, k, plan, prefix=prefix, pattern=pattern)
+    counts = torch.empty(world * plan.n_digits, dtype=torch.int64, device=dev)
+    dist.all_gather_into_tensor(counts, torch.from_numpy(mine.astype(np.int64)).to(dev), group=group)
+    counts = counts.cpu().numpy().astype(np.uint64).reshape(world, plan.n_digits)
+    ranges = [owner_digits(plan, r) for r in range(world)]
+    # receive layout of owner o: pieces peer-major, digits of o in order
+    dest = np.zeros(plan.n_digits, dtype=np.uint64)
+    for o, (a, b) in enumerate(ranges):
+        block = counts[:, a:b]                                  # [peer, digit of o]
+        before_me = int(block[:rank].sum())
+        within = np.concatenate([[0], np.cumsum(block[rank])[:-1]]).astype(np.uint64) if b > a else np.zeros(0, np.uint64)
+        if int(block.sum()) > px.capacity:
+            raise RuntimeError(f"rank {o} would receive {int(block.sum())} keys, above the peer buffer of {px.capacity}")
+        dest[a:b] = np.uint64(px.base[o]) + np.uint64(8) * (np.uint64(before_me) + within)
+    kept, side = ctx.shuffle_scatter_to(seq, k, plan, dest, prefix=prefix, pattern=pattern)
+    dist.barrier(group=group)                                   # every rank's stores have landed
+    lo, hi = ranges[rank]
+    st = ctx.shuffle_count_addr(px.local, counts[:, lo:hi].reshape(-1), hi - lo, plan, k)
+    agg = torch.tensor([kept, st.distinct, st.unique, side], dtype=torch.int64, device=dev)
+    dist.all_reduce(agg, group=group)                           # also fences the buffers for the next step
+    total, distinct, unique, side_all = (int(x) for x in agg.cpu().tolist())
     return total, distinct + (side_all > 0), unique + (side_all == 1)
 
 

@@ -277,6 +277,29 @@ int dnagpu_shuffle_count(dnagpu_ctx *ctx, const uint64_t *d_keys, const uint64_t
                          uint32_t n_pieces, uint32_t n_groups, const dnagpu_shuffle_plan *plan, int k,
                          dnagpu_stats *stats, dnagpu_table **table);
 
+/*
+ * The exchange fused INTO the scatter kernel (no all-to-all at all): each rank allocates its
+ * receive buffer with dnagpu_peer_alloc, the ranks swap the 64-byte handles (any side channel,
+ * e.g. torch.distributed.all_gather_object) and map each other's buffers with dnagpu_peer_open.
+ * A step is then: dnagpu_shuffle_hist -> all-gather of the per-digit counts (so that every rank
+ * can compute where its piece of every digit starts inside the owner's buffer, pieces laid out
+ * peer-major in digit order) -> dnagpu_shuffle_scatter_to, whose kernel stores every run of keys
+ * straight into the owner's memory over NVLink (st.global on peer-mapped addresses) ->
+ * a barrier -> dnagpu_shuffle_count on the local receive buffer.
+ */
+int dnagpu_peer_alloc(dnagpu_ctx *ctx, uint64_t bytes, void **d_ptr, unsigned char handle[64]);
+int dnagpu_peer_open(dnagpu_ctx *ctx, const unsigned char handle[64], void **d_ptr);
+int dnagpu_peer_close(dnagpu_ctx *ctx, void *d_ptr);
+int dnagpu_peer_free(dnagpu_ctx *ctx, void *d_ptr);
+/* keys per digit of this rank's shard (host array of plan->n_digits entries) */
+int dnagpu_shuffle_hist(dnagpu_ctx *ctx, const dnagpu_seq *seq, int k, const dnagpu_where *filter,
+                        const dnagpu_shuffle_plan *plan, uint64_t *digit_counts);
+/* scatter: the keys of digit d go to the device address digit_dest[d] (local or peer-mapped,
+ * 8-byte aligned), digit_counts[d] of them */
+int dnagpu_shuffle_scatter_to(dnagpu_ctx *ctx, const dnagpu_seq *seq, int k, const dnagpu_where *filter,
+                              const dnagpu_shuffle_plan *plan, const uint64_t *digit_dest,
+                              uint64_t *rows_kept, uint64_t *side_rows);
+
 /* ---- per-kernel device timing (CUDA events on the ctx stream) --------------- */
 int dnagpu_profile_enable(dnagpu_ctx *ctx, int on);
 int dnagpu_profile_reset(dnagpu_ctx *ctx);
