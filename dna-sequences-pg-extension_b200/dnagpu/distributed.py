@@ -61,6 +61,34 @@ class GpuEngine:
         return self.torch.device("cuda", self.ctx.device)
 
 
+class _PairwiseWork:
+    """all-to-all over point-to-point sends (backends without a list all-to-all, i.e. gloo on CPU)."""
+
+    def __init__(self, dst_list, src_list, group):
+        import torch.distributed as dist
+        rank = dist.get_rank(group)
+        self.reqs = []
+        for r, (d, s_) in enumerate(zip(dst_list, src_list)):
+            if r == rank:
+                d.copy_(s_)
+            else:
+                if d.numel():
+                    self.reqs.append(dist.irecv(d, src=r, group=group))
+                if s_.numel():
+                    self.reqs.append(dist.isend(s_.contiguous(), dst=r, group=group))
+
+    def wait(self):
+        for q in self.reqs:
+            q.wait()
+
+
+def _all_to_all_list(dst_list, src_list, group):
+    import torch.distributed as dist
+    if dist.get_backend(group) == "nccl":
+        return dist.all_to_all(dst_list, src_list, group=group, async_op=True)
+    return _PairwiseWork(dst_list, src_list, group)
+
+
 def owner_digits(plan, rank):
     """Digits [lo, hi) of partition level 1 that `rank` owns: owner(d) = d * n_parts >> bits1."""
     n = plan.n_digits
@@ -84,8 +112,8 @@ def count_sharded_fused(ctx, seq, k, n_rows_total, world, rank, buffers, prefix=
     import time
     import torch
     import torch.distributed as dist
-    dev = torch.device("cuda", ctx.device)
-    trace = os.environ.get("DNAGPU_TRACE") == "1" and rank == 0
+    dev = getattr(ctx, "torch_device", None) or torch.device("cuda", ctx.device)
+    trace = os.environ.get("DNAGPU_TRACE") == "1" and rank == 0 and dev.type == "cuda"
     marks = []
 
     def mark(name):
@@ -131,7 +159,7 @@ def count_sharded_fused(ctx, seq, k, n_rows_total, world, rank, buffers, prefix=
         for n in recv_splits:
             dst_list.append(recv_c[pos:pos + n])
             pos += n
-        work = dist.all_to_all(dst_list, src_list, group=group, async_op=True)
+        work = _all_to_all_list(dst_list, src_list, group)
         jobs.append((work, recv_c, my_pieces.reshape(-1), mhi - mlo))
     distinct = unique = 0
     for work, recv_c, my_pieces, groups in jobs:

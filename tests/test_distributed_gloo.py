@@ -42,6 +42,68 @@ class OracleEngine:
         return int(c.sum()), int(u.size), int((c == 1).sum())
 
 
+class OracleShuffleCtx:
+    """Test double for dnagpu.Context in count_sharded_fused: the plan comes from libdnagpu's host-callable
+    dnagpu_shuffle_plan_make, extraction / counting from the CPU oracle and numpy."""
+    MUL = 0xD6E8FEB86659FD93
+
+    def __init__(self, n_bases, seed):
+        self.n_bases, self.seed, self.device = n_bases, seed, 0
+        self.torch_device = torch.device("cpu")
+
+    def shuffle_plan(self, n_rows_total, n_parts):
+        import ctypes as C
+        from dnagpu import _lib
+        plan = _lib.ShufflePlan()
+        assert _lib.load().dnagpu_shuffle_plan_make(n_rows_total, n_parts, C.byref(plan)) == 0
+        return plan
+
+    def shuffle_send(self, seq, k, plan, out, prefix=None, pattern=None):
+        from oracle import ref_cpu as R
+        first, starts = seq.shard
+        n_local = min(self.n_bases - first, starts + k - 1)
+        words = R.synth_seq(self.seed, self.n_bases, first_word=first // 32, n_words=(n_local + 31) // 32 + 1)
+        rows = R.generate_kmers(words, n_local, k, window=True)[:starts]
+        side = int((rows == np.uint64(2**64 - 1)).sum())
+        rows = rows[rows != np.uint64(2**64 - 1)]
+        digits = np.array([((int(x) * self.MUL) & (2**64 - 1)) >> (64 - plan.bits1) for x in rows], dtype=np.int64)
+        order = np.argsort(digits, kind="stable")
+        out[:rows.size] = torch.from_numpy(rows[order].view(np.int64).copy())
+        return np.bincount(digits, minlength=plan.n_digits).astype(np.uint64), rows.size + side, side
+
+    def shuffle_count(self, keys, piece_counts, n_groups, plan, k, table=False):
+        assert int(np.sum(piece_counts)) == keys.numel() and len(piece_counts) % n_groups == 0
+
+        class St:
+            pass
+        u, c = np.unique(keys.numpy().view(np.uint64), return_counts=True)
+        st = St()
+        st.total, st.distinct, st.unique = int(c.sum()), int(u.size), int((c == 1).sum())
+        return st, None
+
+
+class FakeSeq:
+    def __init__(self, shard, k):
+        self.shard, self.k = shard, k
+
+    def kmer_count(self, k):
+        return self.shard[1]
+
+
+def _worker_fused(rank, world, port, n_bases, k, seed, chunks, out):
+    for p in (ROOT, PKG):
+        sys.path.insert(0, p)
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from dnagpu.distributed import count_sharded_fused, shard_of
+    ctx = OracleShuffleCtx(n_bases, seed)
+    seq = FakeSeq(shard_of(n_bases, k, world, rank), k)
+    res = count_sharded_fused(ctx, seq, k, n_bases - k + 1, world, rank, {}, chunks=chunks)
+    if rank == 0:
+        out.put(res)
+    dist.destroy_process_group()
+
+
 def _worker(rank, world, port, n_bases, k, seed, out):
     for p in (ROOT, PKG):
         sys.path.insert(0, p)
@@ -72,6 +134,43 @@ def test_two_rank_exchange_equals_single_rank(n_bases, k):
     words = R.synth_seq(21, n_bases)
     want = R.count_query(words, 1, n_bases, words.size, k, faithful=False)
     assert tuple(got) == want.stats
+
+
+@pytest.mark.parametrize("n_bases,k,chunks", [(30_000, 31, 1), (30_000, 21, 3), (100, 32, 2)])
+def test_two_rank_fused_exchange_equals_single_rank(n_bases, k, chunks):
+    """count_sharded_fused: level-1 digit layout, owner digit ranges, peer-major pieces, chunked all-to-all."""
+    from oracle import ref_cpu as R
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 29900 + (n_bases + k + chunks) % 90
+    procs = [ctx.Process(target=_worker_fused, args=(r, 2, port, n_bases, k, 23, chunks, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    got = q.get(timeout=120)
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    words = R.synth_seq(23, n_bases)
+    want = R.count_query(words, 1, n_bases, words.size, k, faithful=False)
+    assert tuple(got) == want.stats
+
+
+def test_owner_digit_ranges_agree_with_the_library():
+    import ctypes as C
+    from dnagpu import _lib
+    from dnagpu.distributed import owner_digits
+    lib = _lib.load()
+    for n, parts in [(3_100_000_000, 8), (3_100_000_000, 2), (1_000_000, 3), (5_000_000_000, 7), (100, 4)]:
+        plan = _lib.ShufflePlan()
+        assert lib.dnagpu_shuffle_plan_make(n, parts, C.byref(plan)) == 0
+        assert plan.n_digits == 1 << plan.bits1 and plan.bits2 >= 1 and plan.n_digits >= parts
+        seen = 0
+        for r in range(parts):
+            lo, hi = owner_digits(plan, r)
+            assert lo == seen and hi > lo
+            assert all(lib.dnagpu_shuffle_owner(C.byref(plan), d) == r for d in (lo, hi - 1))
+            seen = hi
+        assert seen == plan.n_digits
 
 
 def test_shards_tile_the_sequence_exactly_once():
