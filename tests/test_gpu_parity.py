@@ -425,3 +425,29 @@ def test_shards_with_overlap_cover_the_sequence_once(gpu):
         pieces.append(gpu.extract(seq, k).cpu().numpy().view(np.uint64))
         seq.free()
     assert np.array_equal(np.concatenate(pieces), whole)
+
+
+def test_two_gpu_peer_exchange_end_to_end():
+    """bench.py's N = 2 path (exchange fused into the scatter kernel over peer memory) on a small workload;
+    needs two GPUs, skipped otherwise."""
+    import json
+    import os
+    import subprocess
+    import sys
+    import torch
+    from conftest import ROOT
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    n, k = 20_000_000, 21
+    words = R.synth_seq(2, 100_000_000, first_word=0, n_words=(n + 31) // 32)  # c2's stream, cut to n bases
+    for exchange in ("peer", "fused", "routed"):
+        out = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2",
+                              "--master-addr", "127.0.0.1", "--master-port", "29533", os.path.join(ROOT, "bench.py"),
+                              "--gpus", "2", "--workload", "c2", "--steps", "1", "--warmup", "3", "--e2e-steps", "1",
+                              "--cpu-sample", "1000000", "--no-extract", "--exchange", exchange],
+                             capture_output=True, text=True, timeout=600)
+        assert out.returncode == 0, out.stderr[-2000:]
+        d = json.loads(out.stdout.strip().splitlines()[-1])
+        assert d["n_gpus"] == 2 and exchange in d["config"]["parallelism"]
+        assert d["result"] == {"total": 99999980, "distinct": 87735270, "unique": 77017094}
+    del words
