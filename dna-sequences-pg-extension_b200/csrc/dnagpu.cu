@@ -37,6 +37,7 @@ struct dnagpu_ctx {
     bool own_stream = true;
     unsigned long long *d_ctr = nullptr; /* C_COUNT + kMaxParts*2 u64 device counters */
     unsigned long long *h_ctr = nullptr; /* pinned mirror */
+    cudaStream_t copy_stream = nullptr; /* H2D of the host-buffer calls, overlapped with level 1 */
     bool profiling = false;
     std::vector<ProfRec> prof;
     char err[512] = {0};
@@ -289,6 +290,7 @@ extern "C" void dnagpu_destroy(dnagpu_ctx *ctx)
     }
     if (ctx->d_ctr) cudaFree(ctx->d_ctr);
     if (ctx->h_ctr) cudaFreeHost(ctx->h_ctr);
+    if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
     if (ctx->own_stream && ctx->stream) cudaStreamDestroy(ctx->stream);
     delete ctx;
 }
@@ -1145,14 +1147,14 @@ static int bucket_bits(uint64_t n)
 }
 
 /* tile prefix sums of a partitioned key array: out_tile_off[n_parents + 1] */
-static int part_tiles(dnagpu_ctx *ctx, Scratch &sc, const uint64_t *parent_off, uint64_t n_parents,
-                      uint64_t tile_keys, uint64_t **out_tile_off)
+static int part_tiles(dnagpu_ctx *ctx, Scratch &sc, const uint64_t *parent_off, const uint64_t *parent_end,
+                      uint64_t n_parents, uint64_t tile_keys, uint64_t **out_tile_off)
 {
     uint64_t *tiles;
     TRY(sc.get((void **)&tiles, (n_parents + 1) * 8));
     TRY(sc.get((void **)out_tile_off, (n_parents + 1) * 8));
     TRY(launch(ctx, "part_tiles", [&] {
-        k_part_tiles<<<grid_for(n_parents, kThreads), kThreads, 0, ctx->stream>>>(parent_off, n_parents,
+        k_part_tiles<<<grid_for(n_parents, kThreads), kThreads, 0, ctx->stream>>>(parent_off, parent_end, n_parents,
                                                                                 tile_keys, tiles);
     }));
     return scan_any(ctx, sc, tiles, n_parents, *out_tile_off);
@@ -1198,11 +1200,11 @@ static int part_level1(dnagpu_ctx *ctx, Scratch &sc, const CountInput &in, int k
         ctx->h_ctr[1] = n;
         CU(ctx, cudaMemcpyAsync(root_off, ctx->h_ctr, 16, cudaMemcpyHostToDevice, ctx->stream));
         CU(ctx, cudaStreamSynchronize(ctx->stream)); /* h_ctr is reused below */
-        TRY(part_tiles(ctx, sc, root_off, 1, kSuperTile, &root_tiles_hist));
-        TRY(part_tiles(ctx, sc, root_off, 1, kTileKeys, &root_tiles_scat));
+        TRY(part_tiles(ctx, sc, root_off, root_off + 1, 1, kSuperTile, &root_tiles_hist));
+        TRY(part_tiles(ctx, sc, root_off, root_off + 1, 1, kTileKeys, &root_tiles_scat));
         TRY(launch(ctx, "part_hist", [&] {
             k_part_hist_keys<<<grid_for(n, kSuperTile), kThreads, 0, ctx->stream>>>(
-                in.d_keys, root_off, root_tiles_hist, 1, 1, shift1, P1, hist1);
+                in.d_keys, root_off, root_off + 1, root_tiles_hist, 1, 1, shift1, P1, hist1);
         }));
     } else {
         const unsigned hgrid = (unsigned)std::min<uint64_t>(grid_for(in.v.n_items, kThreads), (uint64_t)ctx->sm_count * 8);
@@ -1227,7 +1229,7 @@ static int part_level1(dnagpu_ctx *ctx, Scratch &sc, const CountInput &in, int k
     if (in.d_keys) {
         TRY(launch(ctx, "part_scatter", [&] {
             k_part_scatter_keys<true><<<grid_for(in.n, kTileKeys), kScatThreads, psmem, ctx->stream>>>(
-                in.d_keys, root_off, root_tiles_scat, 1, 1, shift1, P1, off1, cur1, out, ctx->d_ctr);
+                in.d_keys, root_off, root_off + 1, root_tiles_scat, 1, 1, shift1, P1, off1, cur1, out, ctx->d_ctr);
         }));
     } else {
         static const bool per32 = getenv("DNAGPU_SCATTER_PER") && atoi(getenv("DNAGPU_SCATTER_PER")) == 32;
@@ -1237,20 +1239,20 @@ static int part_level1(dnagpu_ctx *ctx, Scratch &sc, const CountInput &in, int k
             DISPATCH_LAYOUT(in.seq->layout, TRY(launch(ctx, "part_scatter", [&] {
                 if (in.filtered)
                     k_part_scatter_seq<LY, true, 32><<<grid, kScatThreads, psmem32, ctx->stream>>>(
-                        in.v, in.p, mask, shift1, P1, off1, cur1, out, ctx->d_ctr);
+                        in.v, in.p, mask, shift1, P1, off1, cur1, out, ctx->d_ctr, 0);
                 else
                     k_part_scatter_seq<LY, false, 32><<<grid, kScatThreads, psmem32, ctx->stream>>>(
-                        in.v, in.p, mask, shift1, P1, off1, cur1, out, ctx->d_ctr);
+                        in.v, in.p, mask, shift1, P1, off1, cur1, out, ctx->d_ctr, 0);
             })));
         } else {
             const unsigned grid = grid_for(in.v.n_items, kScatThreads / 2);
             DISPATCH_LAYOUT(in.seq->layout, TRY(launch(ctx, "part_scatter", [&] {
                 if (in.filtered)
                     k_part_scatter_seq<LY, true><<<grid, kScatThreads, psmem, ctx->stream>>>(
-                        in.v, in.p, mask, shift1, P1, off1, cur1, out, ctx->d_ctr);
+                        in.v, in.p, mask, shift1, P1, off1, cur1, out, ctx->d_ctr, 0);
                 else
                     k_part_scatter_seq<LY, false><<<grid, kScatThreads, psmem, ctx->stream>>>(
-                        in.v, in.p, mask, shift1, P1, off1, cur1, out, ctx->d_ctr);
+                        in.v, in.p, mask, shift1, P1, off1, cur1, out, ctx->d_ctr, 0);
             })));
         }
     }
@@ -1262,11 +1264,11 @@ static int part_level1(dnagpu_ctx *ctx, Scratch &sc, const CountInput &in, int k
 /* Level 2 (inside every parent; parents with equal parent % n_groups merge into the same children)
  * and the shared-memory count of every bucket.  Leaves distinct / unique in the device counters. */
 static int part_finish(dnagpu_ctx *ctx, Scratch &sc, const uint64_t *keys, uint64_t n, const uint64_t *parent_off,
-                       uint64_t n_parents, uint64_t n_groups, int b1, int b2, int k, dnagpu_stats *stats,
-                       uint64_t total_rows, dnagpu_table **table)
+                       const uint64_t *parent_end, uint64_t n_parents, uint64_t n_groups, int b1, int b2, int k,
+                       dnagpu_stats *stats, uint64_t total_rows, dnagpu_table **table)
 {
     const int psmem = kTileKeys * (int)sizeof(uint64_t) + (int)sizeof(ScatterSmem);
-    const uint64_t *bucket_keys = keys, *bucket_off = parent_off;
+    const uint64_t *bucket_keys = keys, *bucket_off = parent_off, *bucket_end = parent_end;
     uint64_t n_buckets = n_parents;
     if (b2 > 0) {
         const uint32_t P2 = 1u << b2;
@@ -1280,19 +1282,20 @@ static int part_finish(dnagpu_ctx *ctx, Scratch &sc, const uint64_t *keys, uint6
         TRY(sc.get((void **)&bufB, (n + 2) * 8));
         CU(ctx, cudaMemsetAsync(hist2, 0, n_buckets * 8, ctx->stream));
         CU(ctx, cudaMemsetAsync(cur2, 0, n_buckets * 8, ctx->stream));
-        TRY(part_tiles(ctx, sc, parent_off, n_parents, kSuperTile, &tiles_hist));
-        TRY(part_tiles(ctx, sc, parent_off, n_parents, kTileKeys, &tiles_scat));
+        TRY(part_tiles(ctx, sc, parent_off, parent_end, n_parents, kSuperTile, &tiles_hist));
+        TRY(part_tiles(ctx, sc, parent_off, parent_end, n_parents, kTileKeys, &tiles_scat));
         TRY(launch(ctx, "part_hist2", [&] {
             k_part_hist_keys<<<grid_for(n, kSuperTile) + (unsigned)n_parents, kThreads, 0, ctx->stream>>>(
-                keys, parent_off, tiles_hist, n_parents, n_groups, shift2, P2, hist2);
+                keys, parent_off, parent_end, tiles_hist, n_parents, n_groups, shift2, P2, hist2);
         }));
         TRY(scan_any(ctx, sc, (const uint64_t *)hist2, n_buckets, off2));
         TRY(launch(ctx, "part_scatter2", [&] {
             k_part_scatter_keys<false><<<grid_for(n, kTileKeys) + (unsigned)n_parents, kScatThreads, psmem, ctx->stream>>>(
-                keys, parent_off, tiles_scat, n_parents, n_groups, shift2, P2, off2, cur2, bufB, ctx->d_ctr);
+                keys, parent_off, parent_end, tiles_scat, n_parents, n_groups, shift2, P2, off2, cur2, bufB, ctx->d_ctr);
         }));
         bucket_keys = bufB;
         bucket_off = off2;
+        bucket_end = off2 + 1;
     }
     const uint64_t spill_cap = std::max<uint64_t>(1ull << 16, n / 64);
     Slot *spill;
@@ -1304,7 +1307,7 @@ static int part_finish(dnagpu_ctx *ctx, Scratch &sc, const uint64_t *keys, uint6
     const int bsmem = kBucketSlots * 12;
     const unsigned cgrid = (unsigned)std::min<uint64_t>(n_buckets, (uint64_t)ctx->sm_count * 4);
     TRY(launch(ctx, "count_buckets", [&] {
-        k_count_buckets<false><<<cgrid, kThreads, bsmem, ctx->stream>>>(bucket_keys, bucket_off, n_buckets,
+        k_count_buckets<false><<<cgrid, kThreads, bsmem, ctx->stream>>>(bucket_keys, bucket_off, bucket_end, n_buckets,
                                                                        spill, spill_cap, ctx->d_ctr, nullptr, nullptr);
     }));
     TRY(fetch_counters(ctx));
@@ -1331,7 +1334,7 @@ static int part_finish(dnagpu_ctx *ctx, Scratch &sc, const uint64_t *keys, uint6
             CU(ctx, cudaMemsetAsync(ctx->d_ctr + C_CURSOR, 0, 8, ctx->stream));
             TRY(launch(ctx, "count_buckets_emit", [&] {
                 k_count_buckets<true><<<cgrid, kThreads, bsmem, ctx->stream>>>(
-                    bucket_keys, bucket_off, n_buckets, spill, spill_cap, ctx->d_ctr, (*table)->d_kmers,
+                    bucket_keys, bucket_off, bucket_end, n_buckets, spill, spill_cap, ctx->d_ctr, (*table)->d_kmers,
                     (*table)->d_counts);
             }));
             TRY(launch(ctx, "table_compact", [&] { /* rows that spilled, appended after the bucket rows */
@@ -1351,8 +1354,56 @@ static int part_finish(dnagpu_ctx *ctx, Scratch &sc, const uint64_t *keys, uint6
     return DNAGPU_OK;
 }
 
-static int count_partition(dnagpu_ctx *ctx, const CountInput &in, int k, dnagpu_stats *stats,
-                           dnagpu_table **table)
+/* Optimistic level 1 (unfiltered packed input): no histogram pass.  Hashing spreads the keys evenly, so
+ * every partition gets a fixed region of mean + 3 % + 8192 keys; a (tile, digit) run that finds its region
+ * full is dropped and flags C_L1OVF, and the caller redoes the query with the exact two-pass level 1
+ * (only heavily repeated input -- e.g. a poly-A run of millions of bases -- ever gets there). */
+struct L1Regions {
+    uint64_t *keys = nullptr, *beg = nullptr, *end = nullptr;
+    unsigned long long *cur = nullptr;
+    uint64_t cap = 0;
+    uint32_t P1 = 0;
+    int b1 = 0;
+};
+
+static int l1_regions_begin(dnagpu_ctx *ctx, Scratch &sc, uint64_t n_rows, int b1, L1Regions *r)
+{
+    r->b1 = b1;
+    r->P1 = 1u << b1;
+    r->cap = (n_rows >> b1) + (n_rows >> b1) / 32 + 8192;
+    TRY(sc.get((void **)&r->keys, ((uint64_t)r->P1 * r->cap + 2) * 8));
+    TRY(sc.get((void **)&r->beg, (uint64_t)r->P1 * 8));
+    TRY(sc.get((void **)&r->end, (uint64_t)r->P1 * 8));
+    TRY(sc.get((void **)&r->cur, (uint64_t)r->P1 * 8));
+    std::vector<uint64_t> beg(r->P1);
+    for (uint32_t d = 0; d < r->P1; ++d) beg[d] = (uint64_t)d * r->cap;
+    CU(ctx, cudaMemcpyAsync(r->beg, beg.data(), (uint64_t)r->P1 * 8, cudaMemcpyHostToDevice, ctx->stream));
+    CU(ctx, cudaMemsetAsync(r->cur, 0, (uint64_t)r->P1 * 8, ctx->stream));
+    CU(ctx, cudaStreamSynchronize(ctx->stream)); /* beg is a host temporary */
+    return DNAGPU_OK;
+}
+
+static int l1_regions_scatter(dnagpu_ctx *ctx, const L1Regions &r, int layout, const SeqView &v, int k)
+{
+    const int psmem = kTileKeys * (int)sizeof(uint64_t) + (int)sizeof(ScatterSmem);
+    const unsigned grid = grid_for(v.n_items, kScatThreads / 2);
+    const Pred none = {~0ull, ~0ull, ~0ull, ~0ull};
+    DISPATCH_LAYOUT(layout, TRY(launch(ctx, "part_scatter", [&] {
+        k_part_scatter_seq<LY, false><<<grid, kScatThreads, psmem, ctx->stream>>>(
+            v, none, kmer_mask(k), 64 - r.b1, r.P1, r.beg, r.cur, r.keys, ctx->d_ctr, r.cap);
+    })));
+    return DNAGPU_OK;
+}
+
+static int l1_regions_end(dnagpu_ctx *ctx, const L1Regions &r)
+{
+    return launch(ctx, "part_tiles", [&] {
+        k_region_ends<<<grid_for(r.P1, kThreads), kThreads, 0, ctx->stream>>>(r.cur, r.beg, r.cap, r.P1, r.end);
+    });
+}
+
+static int count_partition_exact(dnagpu_ctx *ctx, const CountInput &in, int k, dnagpu_stats *stats,
+                                 dnagpu_table **table)
 {
     Scratch sc(ctx);
     int b1, b2;
@@ -1366,7 +1417,95 @@ static int count_partition(dnagpu_ctx *ctx, const CountInput &in, int k, dnagpu_
         b2 = std::max(0, std::min(11, e1 + e2 - b1));
     }
     const uint64_t P1 = 1ull << b1;
-    return part_finish(ctx, sc, keys, n, off1, P1, P1, b1, b2, k, stats, 0, table);
+    return part_finish(ctx, sc, keys, n, off1, off1 + 1, P1, P1, b1, b2, k, stats, 0, table);
+}
+
+static int count_partition(dnagpu_ctx *ctx, const CountInput &in, int k, dnagpu_stats *stats,
+                           dnagpu_table **table)
+{
+    static const bool no_optimistic = getenv("DNAGPU_EXACT_LEVEL1") != nullptr;
+    if (in.d_keys || in.filtered || no_optimistic) return count_partition_exact(ctx, in, k, stats, table);
+    {
+        Scratch sc(ctx);
+        int b1, b2;
+        plan_bits(in.n, 1, &b1, &b2);
+        TRY(zero_counters(ctx));
+        L1Regions r;
+        TRY(l1_regions_begin(ctx, sc, in.n, b1, &r));
+        TRY(l1_regions_scatter(ctx, r, in.seq->layout, in.v, k));
+        TRY(l1_regions_end(ctx, r));
+        TRY(part_finish(ctx, sc, r.keys, in.n, r.beg, r.end, r.P1, r.P1, b1, b2, k, stats, 0, table));
+        if (!ctx->h_ctr[C_L1OVF]) return DNAGPU_OK;
+        if (table && *table) {
+            dnagpu_table_free(*table);
+            *table = nullptr;
+        }
+    }
+    return count_partition_exact(ctx, in, k, stats, table); /* a region overflowed: heavily repeated input */
+}
+
+/* The host-buffer query with the upload hidden behind level 1: the packed words are copied in chunks on
+ * a second stream and every chunk is scattered as soon as it has landed (the optimistic level 1 needs no
+ * histogram over the whole input first). */
+static int count_kmers_pipelined(dnagpu_ctx *ctx, const uint64_t *words, uint64_t n_bases, int k,
+                                 dnagpu_stats *stats, dnagpu_table **table, bool *done)
+{
+    *done = false;
+    const uint64_t rows = rows_of(n_bases, k), n_words = words_of(n_bases);
+    if (getenv("DNAGPU_EXACT_LEVEL1") || pick_method(nullptr, k, rows) != DNAGPU_COUNT_PARTITION) return DNAGPU_OK;
+    CU(ctx, cudaSetDevice(ctx->device));
+    if (!ctx->copy_stream) CU(ctx, cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking));
+    Scratch sc(ctx);
+    uint64_t *d_words;
+    const uint64_t alloc_words = (n_words + 3) & ~1ull;
+    TRY(sc.get((void **)&d_words, alloc_words * 8));
+    CU(ctx, cudaMemsetAsync(d_words + n_words, 0, (alloc_words - n_words) * 8, ctx->stream));
+    int b1, b2;
+    plan_bits(rows, 1, &b1, &b2);
+    TRY(zero_counters(ctx));
+    L1Regions r;
+    TRY(l1_regions_begin(ctx, sc, rows, b1, &r)); /* synchronises ctx->stream: d_words exists for the copy stream */
+    const int n_chunks = 8;
+    const uint64_t chunk_words = ((n_words + n_chunks - 1) / n_chunks + 255) & ~255ull;
+    std::vector<cudaEvent_t> ev;
+    int rc = DNAGPU_OK;
+    for (uint64_t w0 = 0; w0 < n_words && rc == DNAGPU_OK; w0 += chunk_words) {
+        const uint64_t w1 = std::min(n_words, w0 + chunk_words);
+        const uint64_t copy_end = std::min(n_words, w1 + 1); /* + the halo word of the chunk's last windows */
+        cudaEvent_t e;
+        CU(ctx, cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+        ev.push_back(e);
+        CU(ctx, cudaMemcpyAsync(d_words + w0, words + w0, (copy_end - w0) * 8, cudaMemcpyHostToDevice, ctx->copy_stream));
+        CU(ctx, cudaEventRecord(e, ctx->copy_stream));
+        CU(ctx, cudaStreamWaitEvent(ctx->stream, e, 0));
+        const uint64_t row0 = w0 * 32, row1 = std::min(rows, w1 * 32);
+        if (row1 <= row0) continue;
+        SeqView v;
+        memset(&v, 0, sizeof v);
+        v.words = d_words + w0;
+        v.n_seqs = 1;
+        v.rows_per_seq = v.n_rows = row1 - row0;
+        v.items_per_seq = v.n_items = (v.n_rows + 31) / 32;
+        rc = l1_regions_scatter(ctx, r, kSingle, v, k);
+    }
+    if (rc == DNAGPU_OK) rc = l1_regions_end(ctx, r);
+    if (rc == DNAGPU_OK) rc = part_finish(ctx, sc, r.keys, rows, r.beg, r.end, r.P1, r.P1, b1, b2, k, stats, 0, table);
+    cudaStreamSynchronize(ctx->copy_stream);
+    for (cudaEvent_t e : ev) cudaEventDestroy(e);
+    TRY(rc);
+    if (ctx->h_ctr[C_L1OVF]) { /* redo exactly, on the words that are resident now */
+        if (table && *table) {
+            dnagpu_table_free(*table);
+            *table = nullptr;
+        }
+        dnagpu_seq *seq = nullptr;
+        TRY(dnagpu_seq_wrap(ctx, d_words, n_bases, alloc_words, &seq));
+        rc = dnagpu_count(ctx, seq, k, nullptr, nullptr, stats, table);
+        dnagpu_seq_free(seq);
+        TRY(rc);
+    }
+    *done = true;
+    return DNAGPU_OK;
 }
 
 static int count_any(dnagpu_ctx *ctx, CountInput &in, int k, const dnagpu_count_opts *opts,
@@ -1480,6 +1619,13 @@ extern "C" int dnagpu_count_kmers(dnagpu_ctx *ctx, const uint64_t *words, uint64
     if (!ctx) return fail(ctx, DNAGPU_EARG, "dnagpu_count_kmers: NULL ctx");
     TRY(check_k(ctx, k));
     TRY(check_filter_literals(ctx, filter));
+    if (words && (!filter || (filter->prefix_len == 0 && !filter->qkmer))) {
+        dnagpu_stats local;
+        bool done = false;
+        if (table) *table = nullptr;
+        TRY(count_kmers_pipelined(ctx, words, n_bases, k, stats ? stats : &local, table, &done));
+        if (done) return DNAGPU_OK;
+    }
     dnagpu_seq *seq = nullptr;
     TRY(dnagpu_seq_upload(ctx, words, n_bases, &seq));
     int rc = dnagpu_count(ctx, seq, k, filter, nullptr, stats, table);
@@ -1672,7 +1818,8 @@ extern "C" int dnagpu_shuffle_count(dnagpu_ctx *ctx, const uint64_t *d_keys, con
     CU(ctx, cudaMemcpyAsync(d_off, off.data(), off.size() * 8, cudaMemcpyHostToDevice, ctx->stream));
     CU(ctx, cudaStreamSynchronize(ctx->stream)); /* `off` is a host temporary */
     TRY(zero_counters(ctx));
-    int rc = part_finish(ctx, sc, d_keys, n, d_off, n_pieces, n_groups, plan->bits1, plan->bits2, k, stats, n, table);
+    int rc = part_finish(ctx, sc, d_keys, n, d_off, d_off + 1, n_pieces, n_groups, plan->bits1, plan->bits2, k, stats, n,
+                         table);
     if (rc != DNAGPU_OK && table && *table) {
         dnagpu_table_free(*table);
         *table = nullptr;
@@ -1813,10 +1960,10 @@ extern "C" int dnagpu_shuffle_scatter_to(dnagpu_ctx *ctx, const dnagpu_seq *seq,
     DISPATCH_LAYOUT(seq->layout, TRY(launch(ctx, "part_scatter_peer", [&] {
         if (in.filtered)
             k_part_scatter_seq<LY, true, 32><<<grid, kScatThreads, psmem, ctx->stream>>>(
-                in.v, in.p, mask, shift1, P1, d_idx, cur1, (uint64_t *)nullptr, ctx->d_ctr);
+                in.v, in.p, mask, shift1, P1, d_idx, cur1, (uint64_t *)nullptr, ctx->d_ctr, 0);
         else
             k_part_scatter_seq<LY, false, 32><<<grid, kScatThreads, psmem, ctx->stream>>>(
-                in.v, in.p, mask, shift1, P1, d_idx, cur1, (uint64_t *)nullptr, ctx->d_ctr);
+                in.v, in.p, mask, shift1, P1, d_idx, cur1, (uint64_t *)nullptr, ctx->d_ctr, 0);
     })));
     TRY(fetch_counters(ctx)); /* synchronises: every store of this rank has been issued and retired */
     if (rows_kept) *rows_kept = ctx->h_ctr[C_TOTAL];

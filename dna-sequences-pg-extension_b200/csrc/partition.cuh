@@ -49,23 +49,34 @@ __device__ __forceinline__ uint32_t digit_of(uint64_t h, int shift, uint32_t fan
 
 /* ---- tiles of a partitioned key array ------------------------------------------- */
 /* tiles[p] = ceil(size_p / tile_keys) */
-__global__ void __launch_bounds__(kThreads) k_part_tiles(const uint64_t *__restrict__ parent_off,
+__global__ void __launch_bounds__(kThreads) k_part_tiles(const uint64_t *__restrict__ parent_beg,
+                                                         const uint64_t *__restrict__ parent_end,
                                                          uint64_t n_parents, uint64_t tile_keys,
                                                          uint64_t *__restrict__ tiles)
 {
     uint64_t p = (uint64_t)blockIdx.x * kThreads + threadIdx.x;
-    if (p < n_parents) tiles[p] = (parent_off[p + 1] - parent_off[p] + tile_keys - 1) / tile_keys;
+    if (p < n_parents) tiles[p] = (parent_end[p] - parent_beg[p] + tile_keys - 1) / tile_keys;
 }
 
-/* CTA -> (parent partition, key range) */
-__device__ __forceinline__ void tile_range(const uint64_t *parent_off, const uint64_t *tile_off,
-                                           uint64_t n_parents, uint64_t tile_keys, uint64_t &parent,
-                                           uint64_t &beg, uint64_t &end)
+/* CTA -> (parent partition, key range).  A partition is keys[parent_beg[p] .. parent_end[p]): exact
+ * layouts pass (off, off + 1), the optimistic level 1 passes region starts and fill marks. */
+__device__ __forceinline__ void tile_range(const uint64_t *parent_beg, const uint64_t *parent_end,
+                                           const uint64_t *tile_off, uint64_t n_parents, uint64_t tile_keys,
+                                           uint64_t &parent, uint64_t &beg, uint64_t &end)
 {
     parent = n_parents == 1 ? 0 : upper_seq(tile_off, n_parents, blockIdx.x);
     uint64_t t = blockIdx.x - tile_off[parent];
-    beg = parent_off[parent] + t * tile_keys;
-    end = min(beg + tile_keys, parent_off[parent + 1]);
+    beg = parent_beg[parent] + t * tile_keys;
+    end = min(beg + tile_keys, parent_end[parent]);
+}
+
+/* optimistic level 1: end[d] = beg[d] + keys actually stored in region d */
+__global__ void __launch_bounds__(kThreads) k_region_ends(const unsigned long long *__restrict__ cur,
+                                                          const uint64_t *__restrict__ beg, uint64_t cap,
+                                                          uint32_t n, uint64_t *__restrict__ end)
+{
+    uint32_t d = blockIdx.x * kThreads + threadIdx.x;
+    if (d < n) end[d] = beg[d] + min((uint64_t)cur[d], cap);
 }
 
 /* ---- histogram passes ---------------------------------------------------------------- */
@@ -100,6 +111,7 @@ __global__ void __launch_bounds__(kThreads) k_part_hist_seq(SeqView sv, Pred p, 
  * when the same partition arrived in several pieces (one per peer rank) that must merge. */
 __global__ void __launch_bounds__(kThreads) k_part_hist_keys(const uint64_t *__restrict__ keys,
                                                              const uint64_t *__restrict__ parent_off,
+                                                             const uint64_t *__restrict__ parent_end,
                                                              const uint64_t *__restrict__ tile_off,
                                                              uint64_t n_parents, uint64_t n_groups, int shift,
                                                              uint32_t fan,
@@ -110,7 +122,7 @@ __global__ void __launch_bounds__(kThreads) k_part_hist_keys(const uint64_t *__r
     for (uint32_t i = threadIdx.x; i < fan; i += kThreads) h[i] = 0;
     __syncthreads();
     uint64_t parent, beg, end;
-    tile_range(parent_off, tile_off, n_parents, kSuperTile, parent, beg, end);
+    tile_range(parent_off, parent_end, tile_off, n_parents, kSuperTile, parent, beg, end);
     const uint32_t fm = fan - 1;
     for (uint64_t base = beg; base < end; base += kThreads * 8) {
         uint64_t x[8];
@@ -144,11 +156,13 @@ struct ScatterSmem {
  * stay in registers (gd[]) so that their latency hides behind the placing phase; the
  * caller hands them to scatter_publish() before the flush. */
 constexpr int kPlanPer = kMaxFan / kScatThreads; /* 4 digits per thread */
+constexpr long long kNoDest = (long long)0x8000000000000000ull; /* a run that found its region full */
 
 __device__ __forceinline__ uint32_t scatter_plan(ScatterSmem &s, uint32_t fan,
                                                  const uint64_t *__restrict__ child_off,
                                                  unsigned long long *__restrict__ child_cur,
-                                                 long long (&gd)[kPlanPer])
+                                                 long long (&gd)[kPlanPer], uint64_t cap = 0,
+                                                 unsigned long long *__restrict__ ctr = nullptr)
 {
     uint32_t v[kPlanPer], sum = 0;
     const uint32_t base = threadIdx.x * kPlanPer;
@@ -179,10 +193,15 @@ __device__ __forceinline__ uint32_t scatter_plan(ScatterSmem &s, uint32_t fan,
         gd[i] = 0;
         if (base + i < fan) {
             s.cur[base + i] = ex;
-            if (v[i])
-                gd[i] = (long long)(child_off[base + i] +
-                                    atomicAdd(&child_cur[base + i], (unsigned long long)v[i])) -
-                        (long long)ex;
+            if (v[i]) {
+                const unsigned long long at = atomicAdd(&child_cur[base + i], (unsigned long long)v[i]);
+                if (cap && at + v[i] > cap) { /* optimistic layout: the region is full -> caller re-runs exactly */
+                    gd[i] = kNoDest;
+                    atomicExch(&ctr[C_L1OVF], 1ull);
+                } else {
+                    gd[i] = (long long)(child_off[base + i] + at) - (long long)ex;
+                }
+            }
         }
         ex += v[i];
     }
@@ -211,7 +230,8 @@ __device__ __forceinline__ void scatter_flush(const ScatterSmem &s, const uint64
         const uint32_t i = (uint32_t)u * kScatThreads + threadIdx.x;
         if (i < total) {
             const uint64_t x = stage[i];
-            out[(uint64_t)(s.gdelta[digit_of(part_hash(x), shift, fm)] + (long long)i)] = x;
+            const long long g = s.gdelta[digit_of(part_hash(x), shift, fm)];
+            if (g != kNoDest) out[(uint64_t)(g + (long long)i)] = x;
         }
     }
 }
@@ -228,7 +248,8 @@ __global__ void __launch_bounds__(kScatThreads, (PER == 16 ? 2 : 1)) k_part_scat
                                                                       const uint64_t *__restrict__ child_off,
                                                                       unsigned long long *__restrict__ child_cur,
                                                                       uint64_t *__restrict__ out,
-                                                                      unsigned long long *__restrict__ ctr)
+                                                                      unsigned long long *__restrict__ ctr,
+                                                                      uint64_t cap)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     uint64_t *stage = reinterpret_cast<uint64_t *>(smem_raw);
@@ -282,7 +303,7 @@ __global__ void __launch_bounds__(kScatThreads, (PER == 16 ? 2 : 1)) k_part_scat
     __syncthreads();
     PHASE_MARK(2);
     long long gd[kPlanPer];
-    const uint32_t total = scatter_plan(s, fan, child_off, child_cur, gd);
+    const uint32_t total = scatter_plan(s, fan, child_off, child_cur, gd, cap, ctr);
     PHASE_MARK(3);
     {
         uint64_t cur = a0, nxt = a1;
@@ -321,6 +342,7 @@ __global__ void __launch_bounds__(kScatThreads, (PER == 16 ? 2 : 1)) k_part_scat
 template <bool COUNT_SIDE>
 __global__ void __launch_bounds__(kScatThreads, 2) k_part_scatter_keys(const uint64_t *__restrict__ keys,
                                                                        const uint64_t *__restrict__ parent_off,
+                                                                       const uint64_t *__restrict__ parent_end,
                                                                        const uint64_t *__restrict__ tile_off,
                                                                        uint64_t n_parents, uint64_t n_groups, int shift,
                                                                        uint32_t fan,
@@ -336,7 +358,7 @@ __global__ void __launch_bounds__(kScatThreads, 2) k_part_scatter_keys(const uin
     for (uint32_t i = threadIdx.x; i <= fan; i += kScatThreads) s.cur[i] = 0;
     __syncthreads();
     uint64_t parent, beg, end;
-    tile_range(parent_off, tile_off, n_parents, kTileKeys, parent, beg, end);
+    tile_range(parent_off, parent_end, tile_off, n_parents, kTileKeys, parent, beg, end);
     const uint32_t fm = fan - 1;
     uint64_t x[kScatPer];
     uint32_t rk[kScatPer / 2]; /* two 16-bit ranks per register; the digit is recomputed */
@@ -424,6 +446,7 @@ __device__ __forceinline__ void bucket_insert(unsigned long long *tk, uint32_t *
 template <bool EMIT>
 __global__ void __launch_bounds__(kThreads) k_count_buckets(const uint64_t *__restrict__ keys,
                                                             const uint64_t *__restrict__ bucket_off,
+                                                            const uint64_t *__restrict__ bucket_end,
                                                             uint64_t n_buckets, Slot *__restrict__ spill,
                                                             uint64_t spill_cap,
                                                             unsigned long long *__restrict__ ctr,
@@ -441,7 +464,7 @@ __global__ void __launch_bounds__(kThreads) k_count_buckets(const uint64_t *__re
     uint64_t pre[kPre];
     if (b < n_buckets) {
         beg = bucket_off[b];
-        end = bucket_off[b + 1];
+        end = bucket_end[b];
 #pragma unroll
         for (int u = 0; u < kPre; ++u) {
             uint64_t i = beg + (uint64_t)u * kThreads + threadIdx.x;
@@ -460,7 +483,7 @@ __global__ void __launch_bounds__(kThreads) k_count_buckets(const uint64_t *__re
         uint64_t nbeg = 0, nend = 0;
         if (nb < n_buckets) {
             nbeg = bucket_off[nb];
-            nend = bucket_off[nb + 1];
+            nend = bucket_end[nb];
         }
         { /* 48 KB of 16-byte stores */
             ulonglong2 *k2 = reinterpret_cast<ulonglong2 *>(tk);

@@ -255,6 +255,32 @@ def test_count_partition_skewed_input_spills_correctly(gpu):
     seq.free()
 
 
+def test_host_buffer_call_pipelined_upload_and_overflow_fallback(gpu):
+    """dnagpu_count_kmers on host words: chunked upload overlapped with the optimistic level 1 (no histogram
+    pass, fixed-capacity regions).  Heavily repeated input overflows a region and must fall back to the exact
+    two-pass level 1 with identical results."""
+    n, k = 6_000_003, 31
+    words = R.synth_seq(55, n)                                   # ordinary data: optimistic path holds
+    want = R.count_query(words, 1, n, words.size, k, faithful=False, threads=8)
+    st, table = gpu.count_kmers(Dna.from_words(words, n), k)
+    kk, cc = table.sorted()
+    assert (st.total, st.distinct, st.unique) == want.stats
+    assert np.array_equal(kk, want.kmers) and np.array_equal(cc, want.counts)
+    mixed = words.copy()                                          # a third of it becomes poly-A / poly-G
+    mixed[10_000:70_000] = 0
+    mixed[100_000:130_000] = np.uint64(2**64 - 1)
+    want = R.count_query(mixed, 1, n, mixed.size, k, faithful=False, threads=8)
+    for kq in (k, 32):
+        want = R.count_query(mixed, 1, n, mixed.size, kq, faithful=False, threads=8)
+        st, table = gpu.count_kmers(Dna.from_words(mixed, n), kq)
+        kk, cc = table.sorted()
+        assert (st.total, st.distinct, st.unique) == want.stats, kq
+        assert np.array_equal(kk, want.kmers) and np.array_equal(cc, want.counts), kq
+    st, table = gpu.count_kmers(Dna("A" * 5_000_000), k)
+    assert (st.total, st.distinct, st.unique) == (5_000_000 - 30, 1, 0)
+    assert table.fetch()[1].tolist() == [5_000_000 - 30]
+
+
 def test_count_k32_all_g_sentinel(gpu):
     """'G' x 32 has the bit pattern of the hash table's EMPTY marker: it must still be counted."""
     for s, want_g in (("G" * 32, 1), ("G" * 40 + "ACGT" * 20 + "G" * 33, 11), ("ACGT" * 20, 0)):
