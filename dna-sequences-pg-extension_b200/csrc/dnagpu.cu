@@ -228,6 +228,9 @@ extern "C" int dnagpu_create(dnagpu_ctx **out, int device)
     SMEM_ATTR(k_filter_write<kSingle>);
     SMEM_ATTR(k_filter_write<kFixed>);
     SMEM_ATTR(k_filter_write<kRagged>);
+    SMEM_ATTR(k_filter_collect<kSingle>);
+    SMEM_ATTR(k_filter_collect<kFixed>);
+    SMEM_ATTR(k_filter_collect<kRagged>);
     SMEM_ATTR((k_partition_write<kSingle, false>));
     SMEM_ATTR((k_partition_write<kSingle, true>));
     SMEM_ATTR((k_partition_write<kFixed, false>));
@@ -1138,12 +1141,12 @@ static int ceil_log2(uint64_t x)
     while (b < 63 && (1ull << b) < x) ++b;
     return b;
 }
-/* number of hash bits so that a bucket averages (1024, 2048] keys (4096-slot table) */
+/* number of hash bits so that a bucket averages at most half the slots of the shared-memory table */
 static int bucket_bits(uint64_t n)
 {
     if (const char *e = getenv("DNAGPU_BUCKET_BITS")) /* profiling aid: force the fan-out */
         if (atoi(e) >= 1 && atoi(e) <= 22) return atoi(e);
-    return std::max(1, std::min(22, ceil_log2((n + 2047) / 2048)));
+    return std::max(1, std::min(22, ceil_log2((n + kBucketSlots / 2 - 1) / (kBucketSlots / 2)))); /* mean <= slots / 2 */
 }
 
 /* tile prefix sums of a partitioned key array: out_tile_off[n_parents + 1] */
@@ -1305,7 +1308,7 @@ static int part_finish(dnagpu_ctx *ctx, Scratch &sc, const uint64_t *keys, uint6
                        kThreads, 0, ctx->stream>>>(spill, spill_cap);
     }));
     const int bsmem = kBucketSlots * 12;
-    const unsigned cgrid = (unsigned)std::min<uint64_t>(n_buckets, (uint64_t)ctx->sm_count * 4);
+    const unsigned cgrid = (unsigned)std::min<uint64_t>(n_buckets, (uint64_t)ctx->sm_count * (16384 / kBucketSlots));
     TRY(launch(ctx, "count_buckets", [&] {
         k_count_buckets<false><<<cgrid, kThreads, bsmem, ctx->stream>>>(bucket_keys, bucket_off, bucket_end, n_buckets,
                                                                        spill, spill_cap, ctx->d_ctr, nullptr, nullptr);
@@ -1527,21 +1530,31 @@ static int count_any(dnagpu_ctx *ctx, CountInput &in, int k, const dnagpu_count_
     Scratch keep(ctx);
     CountInput listed;
     if (in.filtered && in.seq && method != DNAGPU_COUNT_DENSE) {
-        uint64_t *tile_off, n_match = 0;
-        TRY(filter_scan(ctx, in.seq, in.v, in.p, keep, &tile_off, &n_match));
+        /* one predicate scan: matches are appended (unordered -- GROUP BY does not care) to a buffer sized
+         * for a selectivity of 1/8; only a less selective clause needs the second, exactly sized scan */
+        uint64_t n_match = 0, cap0 = std::min<uint64_t>(in.n, std::max<uint64_t>(1ull << 20, in.n / 8));
+        uint64_t *keys;
+        TRY(keep.get((void **)&keys, (cap0 + 2) * 8));
+        const unsigned tiles = grid_for(in.v.n_items, kThreads);
+        const int smem = kThreads * 32 * (int)sizeof(uint64_t);
+        for (int attempt = 0; attempt < 2; ++attempt) {
+            TRY(zero_counters(ctx));
+            DISPATCH_LAYOUT(in.seq->layout, TRY(launch(ctx, "filter_collect", [&] {
+                k_filter_collect<LY><<<(tiles + kFilterTiles - 1) / kFilterTiles, kThreads, smem, ctx->stream>>>(
+                    in.v, in.p, kmer_mask(k), cap0, ctx->d_ctr + C_CURSOR, keys);
+            })));
+            TRY(read_u64(ctx, (const uint64_t *)(ctx->d_ctr + C_CURSOR), &n_match));
+            if (n_match <= cap0) break;
+            keep.release(keys);
+            dfree(ctx, keys);
+            cap0 = n_match;
+            TRY(keep.get((void **)&keys, (cap0 + 2) * 8));
+        }
         if (n_match == 0) {
             if (table) TRY(table_new(ctx, k, 0, table));
             return DNAGPU_OK;
         }
-        if (n_match <= in.n / 4) {
-            uint64_t *keys;
-            TRY(keep.get((void **)&keys, (n_match + 2) * 8));
-            const unsigned tiles = grid_for(in.v.n_items, kThreads);
-            const int smem = kThreads * 32 * (int)sizeof(uint64_t);
-            DISPATCH_LAYOUT(in.seq->layout, TRY(launch(ctx, "filter_write", [&] {
-                k_filter_write<LY><<<(tiles + kFilterTiles - 1) / kFilterTiles, kThreads, smem, ctx->stream>>>(
-                    in.v, in.p, kmer_mask(k), tile_off, keys);
-            })));
+        if (n_match <= in.n / 2 || method == DNAGPU_COUNT_PARTITION) {
             listed.d_keys = keys;
             listed.n = n_match;
             dnagpu_count_opts o2 = opts ? *opts : dnagpu_count_opts{0, 0, 0.0, 0};

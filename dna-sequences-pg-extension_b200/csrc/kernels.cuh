@@ -375,6 +375,42 @@ __global__ void __launch_bounds__(kThreads) k_filter_write(SeqView sv, Pred p, u
     }
 }
 
+/* Unordered single-pass form for GROUP BY (row order is irrelevant there): a tile claims its output range
+ * with one atomicAdd on a cursor.  Tiles that would run past `cap` write nothing; the cursor still ends at
+ * the exact number of matches, so the caller can re-run with a buffer of the right size. */
+template <int L>
+__global__ void __launch_bounds__(kThreads) k_filter_collect(SeqView sv, Pred p, uint64_t mask, uint64_t cap,
+                                                             unsigned long long *__restrict__ cursor,
+                                                             uint64_t *__restrict__ out)
+{
+    extern __shared__ uint64_t stage[]; /* kThreads * 32 entries */
+    __shared__ unsigned long long base_s;
+    const uint64_t n_tiles = (sv.n_items + kThreads - 1) / kThreads;
+    for (int i = 0; i < kFilterTiles; ++i) {
+        const uint64_t tile = (uint64_t)blockIdx.x * kFilterTiles + i;
+        if (tile >= n_tiles) break; /* uniform */
+        const uint64_t t = tile * kThreads + threadIdx.x;
+        uint32_t m = 0;
+        uint64_t w0 = 0, w1 = 0;
+        int c = 0;
+        if (t < sv.n_items) m = item_match_mask<L>(sv, p, t, w0, w1, c);
+        uint32_t total;
+        uint32_t rank = block_exscan(__popc(m), &total);
+        if (threadIdx.x == 0 && total) base_s = atomicAdd(cursor, (unsigned long long)total);
+        while (m) {
+            int j = __ffs(m) - 1;
+            m &= m - 1;
+            stage[rank++] = window(w0, w1, 2 * j) & mask;
+        }
+        __syncthreads();
+        if (total && base_s + total <= cap) {
+            uint64_t *dst = out + base_s;
+            for (uint32_t q = threadIdx.x; q < total; q += kThreads) st_cs(dst + q, stage[q]);
+        }
+        __syncthreads();
+    }
+}
+
 /* the same predicates over a materialised kmer column (seq scan of test.sql:220-262) */
 constexpr int kKeysPerThread = 8;
 __global__ void __launch_bounds__(kThreads) k_filter_keys_count(const uint64_t *__restrict__ keys,

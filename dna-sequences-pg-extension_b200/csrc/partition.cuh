@@ -35,7 +35,12 @@ constexpr int kScatPer = 16;
 constexpr int kTileKeys = kScatThreads * kScatPer; /* 8192 keys staged per scatter tile (64 KB) */
 constexpr int kSuperTile = kTileKeys * 8;  /* keys per CTA in a histogram pass              */
 constexpr int kMaxFan = 2048;              /* partitions per level                          */
-constexpr int kBucketSlots = 4096;         /* shared-memory table of the count kernel       */
+#ifndef DNAGPU_BUCKET_SLOTS
+#define DNAGPU_BUCKET_SLOTS 4096
+#endif
+constexpr int kBucketSlots = DNAGPU_BUCKET_SLOTS; /* shared-memory table of the count kernel (power of two) */
+constexpr int kBucketSlotBits = kBucketSlots == 4096 ? 12 : kBucketSlots == 8192 ? 13 : kBucketSlots == 2048 ? 11 : -1;
+static_assert(kBucketSlotBits > 0, "DNAGPU_BUCKET_SLOTS must be 2048, 4096 or 8192");
 constexpr uint64_t kSlotMul = 0x9E3779B97F4A7C15ull;
 constexpr uint64_t kPartMul = 0xD6E8FEB86659FD93ull;
 
@@ -402,13 +407,13 @@ __global__ void __launch_bounds__(kScatThreads, 2) k_part_scatter_keys(const uin
 }
 
 /* ---- count: one bucket at a time in a shared-memory table ------------------------------------- */
-constexpr int kPre = 8; /* keys per thread fetched one bucket ahead (covers buckets up to 2048 keys) */
+constexpr int kPre = kBucketSlots / 2 / kThreads; /* keys per thread fetched one bucket ahead (covers the mean bucket) */
 
 /* slot inside a bucket: fold the key and multiply once (32-bit); the digits came from
  * a different multiplier over the unfolded key, so the two are independent in practice */
 __device__ __forceinline__ uint32_t bucket_slot(uint64_t x)
 {
-    return (((uint32_t)x ^ (uint32_t)(x >> 32)) * 0x9E3779B1u) >> 20; /* 12 bits */
+    return (((uint32_t)x ^ (uint32_t)(x >> 32)) * 0x9E3779B1u) >> (32 - kBucketSlotBits);
 }
 
 struct BucketTally {
