@@ -263,6 +263,7 @@ extern "C" int dnagpu_create(dnagpu_ctx **out, int device)
         {
             const int psmem32 = 32 * kScatThreads * (int)sizeof(uint64_t) + (int)sizeof(ScatterSmem);
 #define PSMEM32_ATTR(kern) cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, psmem32)
+            PSMEM32_ATTR((k_part_scatter_keys<false, 32>));
             PSMEM32_ATTR((k_part_scatter_seq<kSingle, false, 32>));
             PSMEM32_ATTR((k_part_scatter_seq<kSingle, true, 32>));
             PSMEM32_ATTR((k_part_scatter_seq<kFixed, false, 32>));
@@ -1120,6 +1121,13 @@ static int count_hash(dnagpu_ctx *ctx, const CountInput &in, int k, const dnagpu
     return DNAGPU_OK;
 }
 
+/* scatter tile: 16384 keys (one CTA per SM) when the fan-out makes 8192-key runs too short */
+static inline bool scatter_tile32(uint32_t fan)
+{
+    if (const char *e = getenv("DNAGPU_SCATTER_TILE")) return atoi(e) == 16384;
+    return fan >= 2048;
+}
+
 /* exclusive scan of n u64 (out has n + 1 entries); multi-CTA above 16 K entries */
 static int scan_any(dnagpu_ctx *ctx, Scratch &sc, const uint64_t *in, uint64_t n, uint64_t *out)
 {
@@ -1235,8 +1243,8 @@ static int part_level1(dnagpu_ctx *ctx, Scratch &sc, const CountInput &in, int k
                 in.d_keys, root_off, root_off + 1, root_tiles_scat, 1, 1, shift1, P1, off1, cur1, out, ctx->d_ctr);
         }));
     } else {
-        static const bool per32 = getenv("DNAGPU_SCATTER_PER") && atoi(getenv("DNAGPU_SCATTER_PER")) == 32;
-        if (per32) { /* experiment: 16384-key tiles, one CTA per SM */
+        const bool per32 = scatter_tile32(P1);
+        if (per32) {
             const int psmem32 = 32 * kScatThreads * (int)sizeof(uint64_t) + (int)sizeof(ScatterSmem);
             const unsigned grid = grid_for(in.v.n_items, kScatThreads);
             DISPATCH_LAYOUT(in.seq->layout, TRY(launch(ctx, "part_scatter", [&] {
@@ -1286,15 +1294,25 @@ static int part_finish(dnagpu_ctx *ctx, Scratch &sc, const uint64_t *keys, uint6
         CU(ctx, cudaMemsetAsync(hist2, 0, n_buckets * 8, ctx->stream));
         CU(ctx, cudaMemsetAsync(cur2, 0, n_buckets * 8, ctx->stream));
         TRY(part_tiles(ctx, sc, parent_off, parent_end, n_parents, kSuperTile, &tiles_hist));
-        TRY(part_tiles(ctx, sc, parent_off, parent_end, n_parents, kTileKeys, &tiles_scat));
+        /* measured on the headline workload: at a fan-out of 2048 a (tile, digit) run of an 8192-key tile
+         * is only 4 keys; 16384-key tiles (one CTA per SM) win 13 % there, are even at 1024 and lose 10 % at 256 */
+        const bool per32 = scatter_tile32(P2);
+        TRY(part_tiles(ctx, sc, parent_off, parent_end, n_parents, per32 ? 2 * kTileKeys : kTileKeys, &tiles_scat));
         TRY(launch(ctx, "part_hist2", [&] {
             k_part_hist_keys<<<grid_for(n, kSuperTile) + (unsigned)n_parents, kThreads, 0, ctx->stream>>>(
                 keys, parent_off, parent_end, tiles_hist, n_parents, n_groups, shift2, P2, hist2);
         }));
         TRY(scan_any(ctx, sc, (const uint64_t *)hist2, n_buckets, off2));
         TRY(launch(ctx, "part_scatter2", [&] {
-            k_part_scatter_keys<false><<<grid_for(n, kTileKeys) + (unsigned)n_parents, kScatThreads, psmem, ctx->stream>>>(
-                keys, parent_off, parent_end, tiles_scat, n_parents, n_groups, shift2, P2, off2, cur2, bufB, ctx->d_ctr);
+            if (per32) {
+                const int psmem32 = 32 * kScatThreads * (int)sizeof(uint64_t) + (int)sizeof(ScatterSmem);
+                k_part_scatter_keys<false, 32><<<grid_for(n, 2 * kTileKeys) + (unsigned)n_parents, kScatThreads, psmem32,
+                                                 ctx->stream>>>(keys, parent_off, parent_end, tiles_scat, n_parents, n_groups,
+                                                                shift2, P2, off2, cur2, bufB, ctx->d_ctr);
+            } else {
+                k_part_scatter_keys<false><<<grid_for(n, kTileKeys) + (unsigned)n_parents, kScatThreads, psmem, ctx->stream>>>(
+                    keys, parent_off, parent_end, tiles_scat, n_parents, n_groups, shift2, P2, off2, cur2, bufB, ctx->d_ctr);
+            }
         }));
         bucket_keys = bufB;
         bucket_off = off2;
@@ -1388,9 +1406,18 @@ static int l1_regions_begin(dnagpu_ctx *ctx, Scratch &sc, uint64_t n_rows, int b
 
 static int l1_regions_scatter(dnagpu_ctx *ctx, const L1Regions &r, int layout, const SeqView &v, int k)
 {
+    const Pred none = {~0ull, ~0ull, ~0ull, ~0ull};
+    if (scatter_tile32(r.P1)) {
+        const int psmem = 32 * kScatThreads * (int)sizeof(uint64_t) + (int)sizeof(ScatterSmem);
+        const unsigned grid = grid_for(v.n_items, kScatThreads);
+        DISPATCH_LAYOUT(layout, TRY(launch(ctx, "part_scatter", [&] {
+            k_part_scatter_seq<LY, false, 32><<<grid, kScatThreads, psmem, ctx->stream>>>(
+                v, none, kmer_mask(k), 64 - r.b1, r.P1, r.beg, r.cur, r.keys, ctx->d_ctr, r.cap);
+        })));
+        return DNAGPU_OK;
+    }
     const int psmem = kTileKeys * (int)sizeof(uint64_t) + (int)sizeof(ScatterSmem);
     const unsigned grid = grid_for(v.n_items, kScatThreads / 2);
-    const Pred none = {~0ull, ~0ull, ~0ull, ~0ull};
     DISPATCH_LAYOUT(layout, TRY(launch(ctx, "part_scatter", [&] {
         k_part_scatter_seq<LY, false><<<grid, kScatThreads, psmem, ctx->stream>>>(
             v, none, kmer_mask(k), 64 - r.b1, r.P1, r.beg, r.cur, r.keys, ctx->d_ctr, r.cap);

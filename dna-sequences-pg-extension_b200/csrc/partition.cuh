@@ -344,8 +344,8 @@ __global__ void __launch_bounds__(kScatThreads, (PER == 16 ? 2 : 1)) k_part_scat
 
 /* scatter the keys of every parent partition into its children: out[child_off[parent*fan+d] ...].
  * COUNT_SIDE: first level over a raw key list (the caller's keys may hold 'G' x 32). */
-template <bool COUNT_SIDE>
-__global__ void __launch_bounds__(kScatThreads, 2) k_part_scatter_keys(const uint64_t *__restrict__ keys,
+template <bool COUNT_SIDE, int PER = kScatPer>
+__global__ void __launch_bounds__(kScatThreads, (PER == 16 ? 2 : 1)) k_part_scatter_keys(const uint64_t *__restrict__ keys,
                                                                        const uint64_t *__restrict__ parent_off,
                                                                        const uint64_t *__restrict__ parent_end,
                                                                        const uint64_t *__restrict__ tile_off,
@@ -358,18 +358,19 @@ __global__ void __launch_bounds__(kScatThreads, 2) k_part_scatter_keys(const uin
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     uint64_t *stage = reinterpret_cast<uint64_t *>(smem_raw);
-    ScatterSmem &s = *reinterpret_cast<ScatterSmem *>(smem_raw + sizeof(uint64_t) * kTileKeys);
+    ScatterSmem &s = *reinterpret_cast<ScatterSmem *>(smem_raw + sizeof(uint64_t) * (PER * kScatThreads));
+    constexpr uint32_t TILE = PER * kScatThreads;
     if (blockIdx.x >= tile_off[n_parents]) return; /* the grid is an upper bound on the tiles */
     for (uint32_t i = threadIdx.x; i <= fan; i += kScatThreads) s.cur[i] = 0;
     __syncthreads();
     uint64_t parent, beg, end;
-    tile_range(parent_off, parent_end, tile_off, n_parents, kTileKeys, parent, beg, end);
+    tile_range(parent_off, parent_end, tile_off, n_parents, TILE, parent, beg, end);
     const uint32_t fm = fan - 1;
-    uint64_t x[kScatPer];
-    uint32_t rk[kScatPer / 2]; /* two 16-bit ranks per register; the digit is recomputed */
+    uint64_t x[PER];
+    uint32_t rk[PER / 2]; /* two 16-bit ranks per register; the digit is recomputed */
     uint32_t side = 0, kept = 0;
 #pragma unroll
-    for (int u = 0; u < kScatPer; ++u) {
+    for (int u = 0; u < PER; ++u) {
         uint64_t i = beg + (uint64_t)u * kScatThreads + threadIdx.x;
         x[u] = i < end ? ld_nc(keys + i) : kEmpty;
         if (COUNT_SIDE) {
@@ -378,7 +379,7 @@ __global__ void __launch_bounds__(kScatThreads, 2) k_part_scatter_keys(const uin
         }
     }
 #pragma unroll
-    for (int u = 0; u < kScatPer; ++u) {
+    for (int u = 0; u < PER; ++u) {
         const uint32_t d = x[u] != kEmpty ? digit_of(part_hash(x[u]), shift, fm) : fan;
         const uint32_t r = atomicAdd(&s.cur[d], 1u);
         rk[u >> 1] = (u & 1) ? __byte_perm(rk[u >> 1], r, 0x5410) : r;
@@ -387,15 +388,15 @@ __global__ void __launch_bounds__(kScatThreads, 2) k_part_scatter_keys(const uin
     long long gd[kPlanPer];
     const uint32_t total = scatter_plan(s, fan, child_off + (parent % n_groups) * fan, child_cur + (parent % n_groups) * fan, gd);
 #pragma unroll
-    for (int u = 0; u < kScatPer; ++u) {
+    for (int u = 0; u < PER; ++u) {
         const uint32_t r = (u & 1) ? (rk[u >> 1] >> 16) : (rk[u >> 1] & 0xffffu);
         const uint32_t d = x[u] != kEmpty ? digit_of(part_hash(x[u]), shift, fm) : fan;
-        const uint32_t pos = (s.cur[d] + r) & (kTileKeys - 1);
+        const uint32_t pos = (s.cur[d] + r) & (TILE - 1);
         if (d != fan) stage[pos] = x[u];
     }
     scatter_publish(s, fan, gd);
     __syncthreads();
-    scatter_flush(s, stage, total, shift, fm, out);
+    scatter_flush<PER>(s, stage, total, shift, fm, out);
     if (COUNT_SIDE) {
         kept = warp_sum32(kept);
         side = warp_sum32(side);
