@@ -1376,7 +1376,7 @@ static int part_finish(dnagpu_ctx *ctx, Scratch &sc, const uint64_t *keys, uint6
 }
 
 /* Optimistic level 1 (unfiltered packed input): no histogram pass.  Hashing spreads the keys evenly, so
- * every partition gets a fixed region of mean + 3 % + 8192 keys; a (tile, digit) run that finds its region
+ * every partition gets a fixed region of mean + 12.5 % + 65536 keys; a (tile, digit) run that finds its region
  * full is dropped and flags C_L1OVF, and the caller redoes the query with the exact two-pass level 1
  * (only heavily repeated input -- e.g. a poly-A run of millions of bases -- ever gets there). */
 struct L1Regions {
@@ -1391,7 +1391,7 @@ static int l1_regions_begin(dnagpu_ctx *ctx, Scratch &sc, uint64_t n_rows, int b
 {
     r->b1 = b1;
     r->P1 = 1u << b1;
-    r->cap = (n_rows >> b1) + (n_rows >> b1) / 32 + 8192;
+    r->cap = (n_rows >> b1) + (n_rows >> b1) / 8 + 65536; /* hashing is even; the slack is for k-mers with ~1e5-1e6 copies */
     TRY(sc.get((void **)&r->keys, ((uint64_t)r->P1 * r->cap + 2) * 8));
     TRY(sc.get((void **)&r->beg, (uint64_t)r->P1 * 8));
     TRY(sc.get((void **)&r->end, (uint64_t)r->P1 * 8));
