@@ -441,22 +441,50 @@ __global__ void __launch_bounds__(kThreads) k_filter_keys_write(const uint64_t *
                                                                 const uint64_t *__restrict__ tile_off,
                                                                 uint64_t *__restrict__ out)
 {
-    /* thread owns kKeysPerThread CONSECUTIVE keys so that ranks keep input order */
-    uint64_t base = ((uint64_t)blockIdx.x * kThreads + threadIdx.x) * kKeysPerThread;
+    /* loads are coalesced (key u * 256 + t of the tile sits with thread t); output order must follow INPUT
+     * order, i.e. row-major over (u, t): per-warp match counts of every row go to shared memory once, each
+     * thread then walks the 8 x 8 counts for its offsets; matches are staged and stored as one run */
+    __shared__ uint64_t stage[kThreads * kKeysPerThread];
+    __shared__ uint32_t wc[kKeysPerThread * (kThreads / 32)]; /* 64 (row, warp) counts, then their prefix */
+    __shared__ uint32_t total_s;
+    static_assert(kKeysPerThread * (kThreads / 32) == 64, "one warp scans two counts per lane");
+    const uint64_t base = (uint64_t)blockIdx.x * (kThreads * kKeysPerThread);
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
     uint64_t x[kKeysPerThread];
-    uint32_t m = 0;
+    uint32_t bal[kKeysPerThread];
 #pragma unroll
     for (int u = 0; u < kKeysPerThread; ++u) {
-        uint64_t i = base + u;
+        const uint64_t i = base + (uint64_t)u * kThreads + threadIdx.x;
         x[u] = i < n ? ld_nc(keys + i) : 0;
-        if (i < n && pred_ok(p, x[u])) m |= 1u << u;
     }
-    uint32_t total;
-    uint32_t rank = block_exscan(__popc(m), &total);
-    uint64_t *dst = out + tile_off[blockIdx.x] + rank;
+#pragma unroll
+    for (int u = 0; u < kKeysPerThread; ++u) {
+        const uint64_t i = base + (uint64_t)u * kThreads + threadIdx.x;
+        bal[u] = __ballot_sync(0xffffffffu, i < n && pred_ok(p, x[u]));
+        if (lane == 0) wc[u * (kThreads / 32) + wid] = __popc(bal[u]);
+    }
+    __syncthreads();
+    if (wid == 0) { /* exclusive scan of the 64 counts, row-major = input order */
+        const uint32_t a = wc[2 * lane], b = wc[2 * lane + 1];
+        uint32_t inc = a + b;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const uint32_t y = __shfl_up_sync(0xffffffffu, inc, o);
+            if (lane >= o) inc += y;
+        }
+        wc[2 * lane] = inc - a - b;
+        wc[2 * lane + 1] = inc - b;
+        if (lane == 31) total_s = inc;
+    }
+    __syncthreads();
 #pragma unroll
     for (int u = 0; u < kKeysPerThread; ++u)
-        if (m & (1u << u)) *dst++ = x[u];
+        if (bal[u] & (1u << lane))
+            stage[wc[u * (kThreads / 32) + wid] + __popc(bal[u] & ((1u << lane) - 1u))] = x[u];
+    __syncthreads();
+    const uint32_t total = total_s;
+    uint64_t *dst = out + tile_off[blockIdx.x];
+    for (uint32_t q = threadIdx.x; q < total; q += kThreads) st_cs(dst + q, stage[q]);
 }
 
 /* exclusive scan of n u64 values by ONE CTA of 1024 threads walking chunks with a
