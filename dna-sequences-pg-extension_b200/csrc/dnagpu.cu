@@ -151,6 +151,7 @@ struct Scratch {
 };
 
 static int scan_any(dnagpu_ctx *ctx, Scratch &sc, const uint64_t *in, uint64_t n, uint64_t *out);
+static int read_u64(dnagpu_ctx *ctx, const uint64_t *d, uint64_t *h);
 
 static inline uint64_t rows_of(uint64_t n_bases, int k)
 {
@@ -178,6 +179,8 @@ extern "C" const char *dnagpu_strerror(int code)
     case DNAGPU_EQKMER_EMPTY: return "qkmer pattern cannot be empty";                /* dna.c:878 */
     case DNAGPU_EQKMER_TOOLONG: return "Qkmer pattern length cannot exceed 32 characters"; /* dna.c:884 */
     case DNAGPU_EPREFIX_BITS: return "prefix kmer has bits set beyond its length";
+    case DNAGPU_EDNA_CHAR: return "Invalid character in DNA sequence";                /* dna.c:166 */
+    case DNAGPU_EDNA_EMPTY: return "DNA sequence cannot be empty";                    /* dna.c:161 */
     case DNAGPU_EARG: return "invalid argument";
     case DNAGPU_ECAPACITY: return "output buffer too small";
     case DNAGPU_ENOMEM: return "out of device or pinned host memory";
@@ -759,6 +762,77 @@ static int check_k(dnagpu_ctx *ctx, int k)
     case kFixed: { constexpr int LY = kFixed; CALL; } break;   \
     default: { constexpr int LY = kRagged; CALL; } break;      \
     }
+
+/* ---- ingest codec: dna_in / dna_out -------------------------------------------------------------- */
+/* text (host) -> packed words resident on the device; the reference's checks and messages */
+static int encode_to_device(dnagpu_ctx *ctx, const char *text, uint64_t n_bases, uint64_t *d_words /* n_words */)
+{
+    if (!text || n_bases == 0) /* dna.c:160-161 */
+        return fail(ctx, DNAGPU_EDNA_EMPTY, "%s", dnagpu_strerror(DNAGPU_EDNA_EMPTY));
+    Scratch sc(ctx);
+    unsigned char *d_text;
+    TRY(sc.get((void **)&d_text, n_bases + 32));
+    CU(ctx, cudaMemcpyAsync(d_text, text, n_bases, cudaMemcpyHostToDevice, ctx->stream));
+    unsigned long long *d_bad = ctx->d_ctr;
+    CU(ctx, cudaMemsetAsync(d_bad, 0xff, 8, ctx->stream));
+    TRY(launch(ctx, "encode_dna", [&] {
+        k_encode_dna<<<grid_for(words_of(n_bases), kThreads), kThreads, 0, ctx->stream>>>(d_text, n_bases, d_words, d_bad);
+    }));
+    uint64_t bad;
+    TRY(read_u64(ctx, (const uint64_t *)d_bad, &bad));
+    if (bad != ~0ull) /* dna.c:165-166: the first offender, scanning left to right */
+        return fail(ctx, DNAGPU_EDNA_CHAR, "Invalid character in DNA sequence: %c", text[bad]);
+    return DNAGPU_OK;
+}
+
+extern "C" int dnagpu_encode_dna(dnagpu_ctx *ctx, const char *text, uint64_t n_bases, uint64_t *words)
+{
+    if (!ctx || !words) return fail(ctx, DNAGPU_EARG, "dnagpu_encode_dna: NULL argument");
+    CU(ctx, cudaSetDevice(ctx->device));
+    Scratch sc(ctx);
+    uint64_t *d_words;
+    TRY(sc.get((void **)&d_words, (words_of(n_bases) + 1) * 8));
+    TRY(encode_to_device(ctx, text, n_bases, d_words));
+    CU(ctx, cudaMemcpyAsync(words, d_words, words_of(n_bases) * 8, cudaMemcpyDeviceToHost, ctx->stream));
+    CU(ctx, cudaStreamSynchronize(ctx->stream));
+    return DNAGPU_OK;
+}
+
+extern "C" int dnagpu_seq_from_text(dnagpu_ctx *ctx, const char *text, uint64_t n_bases, dnagpu_seq **out)
+{
+    dnagpu_seq *s;
+    TRY(seq_new(ctx, out, &s));
+    s->layout = kSingle;
+    s->bases = n_bases;
+    int rc = seq_alloc_words(s, words_of(n_bases));
+    if (rc == DNAGPU_OK) rc = encode_to_device(ctx, text, n_bases, s->d_words);
+    if (rc != DNAGPU_OK) {
+        dnagpu_seq_free(s);
+        return rc;
+    }
+    *out = s;
+    return DNAGPU_OK;
+}
+
+extern "C" int dnagpu_decode_dna(dnagpu_ctx *ctx, const uint64_t *words, uint64_t n_bases, char *text)
+{
+    if (!ctx || !text || (!words && n_bases)) return fail(ctx, DNAGPU_EARG, "dnagpu_decode_dna: NULL argument");
+    CU(ctx, cudaSetDevice(ctx->device));
+    text[n_bases] = '\0';
+    if (n_bases == 0) return DNAGPU_OK;
+    Scratch sc(ctx);
+    uint64_t *d_words;
+    unsigned char *d_text;
+    TRY(sc.get((void **)&d_words, words_of(n_bases) * 8));
+    TRY(sc.get((void **)&d_text, n_bases + 32));
+    CU(ctx, cudaMemcpyAsync(d_words, words, words_of(n_bases) * 8, cudaMemcpyHostToDevice, ctx->stream));
+    TRY(launch(ctx, "decode_dna", [&] {
+        k_decode_dna<<<grid_for(words_of(n_bases), kThreads), kThreads, 0, ctx->stream>>>(d_words, n_bases, d_text);
+    }));
+    CU(ctx, cudaMemcpyAsync(text, d_text, n_bases, cudaMemcpyDeviceToHost, ctx->stream));
+    CU(ctx, cudaStreamSynchronize(ctx->stream));
+    return DNAGPU_OK;
+}
 
 /* ---- generate_kmers ----------------------------------------------------------------- */
 extern "C" int dnagpu_extract(dnagpu_ctx *ctx, const dnagpu_seq *seq, int k, uint64_t *d_out,

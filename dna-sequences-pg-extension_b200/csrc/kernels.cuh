@@ -915,6 +915,89 @@ __global__ void __launch_bounds__(kThreads) k_ragged_rows(const uint64_t *__rest
     items[s] = (r + 31) >> 5;
 }
 
+/* =================================================================================
+ * Ingest codec: dna_in / dna_out on the device.
+ *   encode  validate_dna_sequence + encode_dna (dna.c:159-171, 114-128): one thread packs 32 ASCII
+ *           bases into one word (two 16-byte loads, 8 B stored); the position of the first byte that
+ *           is not one of A T C G goes to *first_bad through atomicMin (the reference reports the first).
+ *   decode  decode_dna (dna.c:135-152): one thread unpacks one word into 32 characters.
+ * 1 B read + 0.25 B written per base: HBM-bound streaming.
+ * ================================================================================= */
+__device__ __forceinline__ uint32_t base_code(uint32_t c, bool &ok)
+{
+    const uint32_t idx = (c >> 1) & 3u;                      /* A 0, C 1, T 2, G 3 */
+    ok = ((0x47544341u >> (8 * idx)) & 0xffu) == c;           /* exactly 'A' 'C' 'T' 'G' (upper case only) */
+    return (0xD8u >> (2 * idx)) & 3u;                         /* -> A 00, T 01, C 10, G 11 (dna.c:119-123) */
+}
+
+__global__ void __launch_bounds__(kThreads) k_encode_dna(const unsigned char *__restrict__ text, uint64_t n_bases,
+                                                         uint64_t *__restrict__ words,
+                                                         unsigned long long *__restrict__ first_bad)
+{
+    const uint64_t w = (uint64_t)blockIdx.x * kThreads + threadIdx.x;
+    const uint64_t n_words = (n_bases + 31) >> 5;
+    if (w >= n_words) return;
+    const uint64_t first = w << 5;
+    uint32_t chunk[8]; /* 32 characters */
+    if (first + 32 <= n_bases) {
+        const uint4 a = __ldg(reinterpret_cast<const uint4 *>(text + first));
+        const uint4 b = __ldg(reinterpret_cast<const uint4 *>(text + first + 16));
+        chunk[0] = a.x; chunk[1] = a.y; chunk[2] = a.z; chunk[3] = a.w;
+        chunk[4] = b.x; chunk[5] = b.y; chunk[6] = b.z; chunk[7] = b.w;
+    } else { /* the last, partial word: the tail reads as 'A' (code 00), i.e. zero padding (dna.c:186) */
+#pragma unroll
+        for (int q = 0; q < 8; ++q) {
+            uint32_t v = 0;
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const uint64_t i = first + 4 * q + j;
+                v |= (uint32_t)(i < n_bases ? text[i] : (unsigned char)'A') << (8 * j);
+            }
+            chunk[q] = v;
+        }
+    }
+    uint64_t word = 0;
+    uint32_t bad = 32;
+#pragma unroll
+    for (int q = 7; q >= 0; --q) {
+#pragma unroll
+        for (int j = 3; j >= 0; --j) {
+            bool ok;
+            const uint32_t code = base_code((chunk[q] >> (8 * j)) & 0xffu, ok);
+            word = (word << 2) | code;
+            if (!ok) bad = 4 * q + j; /* descending loop: the smallest offending index survives */
+        }
+    }
+    words[w] = word;
+    if (bad < 32 && first + bad < n_bases) atomicMin(first_bad, (unsigned long long)(first + bad));
+}
+
+__global__ void __launch_bounds__(kThreads) k_decode_dna(const uint64_t *__restrict__ words, uint64_t n_bases,
+                                                         unsigned char *__restrict__ text)
+{
+    const uint64_t w = (uint64_t)blockIdx.x * kThreads + threadIdx.x;
+    const uint64_t n_words = (n_bases + 31) >> 5;
+    if (w >= n_words) return;
+    const uint64_t word = ld_nc(words + w), first = w << 5;
+    uint32_t chunk[8];
+#pragma unroll
+    for (int q = 0; q < 8; ++q) {
+        uint32_t v = 0;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const uint32_t code = (uint32_t)(word >> (2 * (4 * q + j))) & 3u;
+            v |= ((0x47435441u >> (8 * code)) & 0xffu) << (8 * j); /* 00 A, 01 T, 10 C, 11 G (dna.c:142-147) */
+        }
+        chunk[q] = v;
+    }
+    if (first + 32 <= n_bases) {
+        *reinterpret_cast<uint4 *>(text + first) = make_uint4(chunk[0], chunk[1], chunk[2], chunk[3]);
+        *reinterpret_cast<uint4 *>(text + first + 16) = make_uint4(chunk[4], chunk[5], chunk[6], chunk[7]);
+    } else {
+        for (uint64_t i = first; i < n_bases; ++i) text[i] = (unsigned char)(chunk[(i - first) >> 2] >> (8 * ((i - first) & 3)));
+    }
+}
+
 /* ---- synthetic inputs on the device (include/dnagpu_synth.h) ----------------- */
 __global__ void __launch_bounds__(kThreads) k_synth_seq(uint64_t seed, uint32_t R, uint64_t n_bases,
                                                         uint64_t first_word, uint64_t n_words,

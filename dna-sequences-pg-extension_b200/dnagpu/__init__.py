@@ -262,6 +262,25 @@ class Context:
                                                 stride_words, tensor.numel(), C.byref(h)))
         return Seq(self, h, keep=tensor)
 
+    # ---- ingest codec (dna_in / dna_out on the device) --------------------------------------
+    def encode_dna(self, text):
+        """ASCII -> Dna, validated and packed on the GPU (dna_make, dna.c:178-202)."""
+        raw = text if isinstance(text, (bytes, bytearray)) else text.encode("ascii", "replace")
+        words = np.empty((len(raw) + 31) // 32, dtype=np.uint64)
+        self._ok(self.lib.dnagpu_encode_dna(self.handle, bytes(raw), len(raw), words.ctypes.data))
+        return Dna.from_words(words, len(raw))
+
+    def seq_from_text(self, text):
+        raw = text if isinstance(text, (bytes, bytearray)) else text.encode("ascii", "replace")
+        h = C.c_void_p()
+        self._ok(self.lib.dnagpu_seq_from_text(self.handle, bytes(raw), len(raw), C.byref(h)))
+        return Seq(self, h)
+
+    def decode_dna(self, dna):
+        buf = C.create_string_buffer(dna.length + 1)
+        self._ok(self.lib.dnagpu_decode_dna(self.handle, dna.words.ctypes.data, dna.length, buf))
+        return buf.raw[:dna.length].decode()
+
     # ---- generate_kmers ----------------------------------------------------------
     def generate_kmers(self, dna, k):
         """Host in, host out: `SELECT * FROM generate_kmers(dna, k)` (dna.c:743-837)."""

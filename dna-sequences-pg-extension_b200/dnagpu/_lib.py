@@ -60,6 +60,9 @@ SIGNATURES = {
     "dnagpu_seq_device_words": (vp, [vp]),
     "dnagpu_seq_kmer_count": (u64, [vp, C.c_int]),
     "dnagpu_seq_free": (None, [vp]),
+    "dnagpu_encode_dna": (C.c_int, [vp, C.c_char_p, u64, vp]),
+    "dnagpu_seq_from_text": (C.c_int, [vp, C.c_char_p, u64, C.POINTER(vp)]),
+    "dnagpu_decode_dna": (C.c_int, [vp, vp, u64, C.c_char_p]),
     "dnagpu_generate_kmers": (C.c_int, [vp, vp, u64, C.c_int, vp, u64, u64p]),
     "dnagpu_extract": (C.c_int, [vp, vp, C.c_int, vp, u64, u64p]),
     "dnagpu_filter_kmers": (C.c_int, [vp, vp, u64, C.c_int, C.POINTER(Where), vp, u64, u64p]),

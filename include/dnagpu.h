@@ -64,6 +64,8 @@ enum {
     DNAGPU_EQKMER_EMPTY = 5,  /* dna.c:877-879  "qkmer pattern cannot be empty" */
     DNAGPU_EQKMER_TOOLONG = 6,/* dna.c:883-885  "Qkmer pattern length cannot exceed 32 characters" */
     DNAGPU_EPREFIX_BITS = 7,  /* prefix has bits set above 2*prefix_len (cannot come from kmer_make) */
+    DNAGPU_EDNA_CHAR = 8,     /* dna.c:165-166  "Invalid character in DNA sequence: %c" (first offender) */
+    DNAGPU_EDNA_EMPTY = 9,    /* dna.c:160-161  "DNA sequence cannot be empty" */
     /* library errors */
     DNAGPU_EARG = 20,         /* NULL pointer, misaligned device pointer, bad size ... */
     DNAGPU_ECAPACITY = 21,    /* caller's output buffer is too small; *n_out holds the need */
@@ -181,6 +183,15 @@ const void *dnagpu_seq_device_words(const dnagpu_seq *seq);
  * (0 where length < k, never the reference's unsigned wrap of dna.c:781). */
 uint64_t dnagpu_seq_kmer_count(const dnagpu_seq *seq, int k);
 void dnagpu_seq_free(dnagpu_seq *seq);
+
+/* ---- ingest codec: dna_in / dna_out (dna.c:114-171, 135-152) ------------------------ */
+/* text (n_bases ASCII bytes, no NUL needed) -> packed words, validated like dna_make: upper-case A T C G
+ * only, not empty; on DNAGPU_EDNA_CHAR the message names the first offending character. */
+int dnagpu_encode_dna(dnagpu_ctx *ctx, const char *text, uint64_t n_bases, uint64_t *words);
+/* the same, leaving the packed sequence on the device ready for the calls below (COPY ... FROM) */
+int dnagpu_seq_from_text(dnagpu_ctx *ctx, const char *text, uint64_t n_bases, dnagpu_seq **out);
+/* packed words -> text; writes n_bases characters and a terminating NUL */
+int dnagpu_decode_dna(dnagpu_ctx *ctx, const uint64_t *words, uint64_t n_bases, char *text);
 
 /* ---- generate_kmers -------------------------------------------------------- */
 /* Host in, host out: what the fmgr glue calls on the SRF's first call.

@@ -477,3 +477,36 @@ def test_two_gpu_peer_exchange_end_to_end():
         assert d["n_gpus"] == 2 and exchange in d["config"]["parallelism"]
         assert d["result"] == {"total": 99999980, "distinct": 87735270, "unique": 77017094}
     del words
+
+
+# ---- ingest codec (dna_in / dna_out on the device) -------------------------------------------------
+def test_encode_decode_dna_match_the_oracle(gpu):
+    rng = np.random.default_rng(77)
+    for n in (1, 15, 31, 32, 33, 64, 100, 4097, 1_000_003):
+        s = "".join(rng.choice(list("ATCG"), size=n))
+        d = gpu.encode_dna(s)
+        words, length = R.encode_dna(s)
+        assert d.length == length and np.array_equal(d.words, words), n
+        assert gpu.decode_dna(d) == s == R.decode_dna(words, n)
+    seq = gpu.seq_from_text("ATCGATCGATCGATCGACG")
+    st, table = gpu.count(seq, 5, table=True)
+    kk, cc = table.sorted()
+    assert dict(zip(dnagpu.kmer_strings(kk, 5), cc.tolist())) == {"ATCGA": 4, "CGATC": 3, "GATCG": 3, "TCGAT": 3,
+                                                                  "TCGAC": 1, "CGACG": 1}   # test.sql:95-104
+
+
+def test_encode_dna_errors_are_the_references(gpu):
+    with pytest.raises(DnaError, match="DNA sequence cannot be empty") as e:
+        gpu.encode_dna("")
+    assert e.value.code == 9
+    good = "ACGT" * 5000
+    for pos, ch in ((0, "N"), (31, "x"), (32, "U"), (19_999, "a"), (7777, " ")):
+        bad = good[:pos] + ch + good[pos + 1:]
+        with pytest.raises(DnaError, match=f"Invalid character in DNA sequence: {ch}") as e:
+            gpu.encode_dna(bad)
+        assert e.value.code == 8
+    two = good[:100] + "Z" + good[101:5000] + "Q" + good[5001:]          # the FIRST offender is reported
+    with pytest.raises(DnaError, match="Invalid character in DNA sequence: Z"):
+        gpu.encode_dna(two)
+    with pytest.raises(R.RefError):
+        R.encode_dna(two)
