@@ -344,7 +344,31 @@ def run_b200(args):
             extract = {"rows": xr, "ms": xms, "gkmer_s": xr / xms / 1e6, "gbs": xbytes / xms / 1e6,
                        "frac": xbytes / xms / 1e6 / peak, "bytes_per_row": 8.25,
                        "note": "output (8 B/row) larger than L2; 10 back-to-back launches"}
-            del xout
+            # ... and the WHERE clause over those materialised rows (kmer ^@ 'AC': 1/16 of them pass), rows kept in order
+            from dnagpu import _where
+            fw, _keep = _where("AC", None)
+            fres = torch.empty(xr // 8 + 2, dtype=torch.int64, device=dev)
+            fn = C.c_uint64()
+
+            def scan():
+                rc_ = ctx.lib.dnagpu_filter_keys(ctx.handle, xout.data_ptr(), xr, k, C.byref(fw), fres.data_ptr(),
+                                                 fres.numel(), C.byref(fn))
+                assert rc_ == 0, rc_
+            for _ in range(2):
+                scan()
+            torch.cuda.synchronize(dev)
+            x0.record(stream)
+            for _ in range(xn):
+                scan()
+            x1.record(stream)
+            torch.cuda.synchronize(dev)
+            fms = x0.elapsed_time(x1) / xn
+            fbytes = 2 * 8.0 * xr + 8.0 * fn.value  # the column is read twice (count per tile, ordered write)
+            extract["filter_keys"] = {"predicate": "kmer ^@ 'AC'", "rows": xr, "matches": int(fn.value), "ms": fms,
+                                      "gkmer_s": xr / fms / 1e6, "gbs": fbytes / fms / 1e6,
+                                      "frac": fbytes / fms / 1e6 / peak,
+                                      "note": "bytes = 2 passes over the 8 B rows + rows written"}
+            del xout, fres
             xs.free()
 
     # ---- reduce over ranks ----
