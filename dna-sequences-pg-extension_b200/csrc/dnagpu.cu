@@ -849,6 +849,13 @@ extern "C" int dnagpu_extract(dnagpu_ctx *ctx, const dnagpu_seq *seq, int k, uin
         return fail(ctx, DNAGPU_ECAPACITY, "generate_kmers needs room for %llu rows",
                     (unsigned long long)v.n_rows);
     if ((uintptr_t)d_out & 15) return fail(ctx, DNAGPU_EARG, "d_out must be 16-byte aligned");
+    if (((uintptr_t)d_out & 31) == 0 && !getenv("DNAGPU_EXTRACT_PAIRS_ONLY")) { /* 256-bit stores */
+        const unsigned grid = grid_for((v.n_rows + 3) / 4, (uint64_t)kThreads * kQuadsPerThread);
+        DISPATCH_LAYOUT(seq->layout, TRY(launch(ctx, "extract", [&] {
+            k_extract4<LY><<<grid, kThreads, 0, ctx->stream>>>(v, kmer_mask(k), d_out);
+        })));
+        return DNAGPU_OK;
+    }
     const unsigned grid = grid_for((v.n_rows + 1) / 2, (uint64_t)kThreads * kPairsPerThread);
     DISPATCH_LAYOUT(seq->layout, TRY(launch(ctx, "extract", [&] {
         k_extract<LY><<<grid, kThreads, 0, ctx->stream>>>(v, kmer_mask(k), d_out);

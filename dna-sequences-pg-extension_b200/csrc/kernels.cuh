@@ -83,9 +83,12 @@ __device__ __forceinline__ bool pred_ok(const Pred &p, uint64_t x)
 
 __device__ __forceinline__ uint64_t ld_nc(const uint64_t *p) { return __ldg(p); }
 
+#ifndef DNAGPU_EXTRACT_ST
+#define DNAGPU_EXTRACT_ST "st.global.cs.v2.u64"
+#endif
 __device__ __forceinline__ void st_cs_v2(uint64_t *p, uint64_t a, uint64_t b)
 {
-    asm volatile("st.global.cs.v2.u64 [%0], {%1, %2};" ::"l"(p), "l"(a), "l"(b) : "memory");
+    asm volatile(DNAGPU_EXTRACT_ST " [%0], {%1, %2};" ::"l"(p), "l"(a), "l"(b) : "memory");
 }
 __device__ __forceinline__ void st_cs(uint64_t *p, uint64_t a)
 {
@@ -237,7 +240,10 @@ __device__ __forceinline__ uint32_t block_exscan(uint32_t v, uint32_t *total)
  * Each thread produces kPairs pairs of consecutive rows; a warp's store
  * instruction writes 512 contiguous bytes.  8 B written + 0.25 B read per row.
  * ================================================================================= */
-constexpr int kPairsPerThread = 4;
+#ifndef DNAGPU_EXTRACT_PAIRS
+#define DNAGPU_EXTRACT_PAIRS 4
+#endif
+constexpr int kPairsPerThread = DNAGPU_EXTRACT_PAIRS;
 
 template <int L>
 __global__ void __launch_bounds__(kThreads) k_extract(SeqView sv, uint64_t mask,
@@ -270,6 +276,60 @@ __global__ void __launch_bounds__(kThreads) k_extract(SeqView sv, uint64_t mask,
         uint64_t g = 2 * (tile + (uint64_t)u * kThreads + threadIdx.x);
         if (g + 1 < n_rows) st_cs_v2(out + g, x0[u], x1[u]);
         else if (g < n_rows) st_cs(out + g, x0[u]);
+    }
+}
+
+/* The same with 256-bit stores (sm_100: STG.E.ENL2.256): one thread = FOUR consecutive rows = one full
+ * 32-byte sector, a warp's store instruction writes 1 KB.  Needs a 32-byte aligned output. */
+#ifndef DNAGPU_EXTRACT_QUADS
+#define DNAGPU_EXTRACT_QUADS 2
+#endif
+constexpr int kQuadsPerThread = DNAGPU_EXTRACT_QUADS;
+
+__device__ __forceinline__ void st_v4(uint64_t *p, uint64_t a, uint64_t b, uint64_t c, uint64_t d)
+{
+    asm volatile("st.global.cs.v4.u64 [%0], {%1, %2, %3, %4};" ::"l"(p), "l"(a), "l"(b), "l"(c), "l"(d) : "memory");
+}
+
+template <int L>
+__global__ void __launch_bounds__(kThreads) k_extract4(SeqView sv, uint64_t mask, uint64_t *__restrict__ out)
+{
+    const uint64_t n_rows = sv.n_rows;
+    const uint64_t tile = (uint64_t)blockIdx.x * (kThreads * kQuadsPerThread);
+    uint64_t x[kQuadsPerThread][4];
+#pragma unroll
+    for (int u = 0; u < kQuadsPerThread; ++u) {
+        const uint64_t g = 4 * (tile + (uint64_t)u * kThreads + threadIdx.x);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) x[u][j] = 0;
+        if (g < n_rows) {
+            if (L == kSingle) { /* g is a multiple of 4: the four rows start in the same packed word */
+                unsigned s;
+                const uint64_t *w = locate_row<L>(sv, g, s);
+                const uint64_t w0 = ld_nc(w), w1 = ld_nc(w + 1);
+#pragma unroll
+                for (int j = 0; j < 4; ++j) x[u][j] = window(w0, w1, s + 2 * j) & mask;
+            } else {
+#pragma unroll
+                for (int j = 0; j < 4; ++j)
+                    if (g + j < n_rows) {
+                        unsigned s;
+                        const uint64_t *w = locate_row<L>(sv, g + j, s);
+                        x[u][j] = window(ld_nc(w), ld_nc(w + 1), s) & mask;
+                    }
+            }
+        }
+    }
+#pragma unroll
+    for (int u = 0; u < kQuadsPerThread; ++u) {
+        const uint64_t g = 4 * (tile + (uint64_t)u * kThreads + threadIdx.x);
+        if (g + 3 < n_rows) {
+            st_v4(out + g, x[u][0], x[u][1], x[u][2], x[u][3]);
+        } else {
+#pragma unroll
+            for (int j = 0; j < 4; ++j)
+                if (g + j < n_rows) st_cs(out + g + j, x[u][j]);
+        }
     }
 }
 
