@@ -25,9 +25,15 @@
  *       (README.md:107-135, test.sql:95-119,140-154), i.e. PostgreSQL's
  *       HashAggregate driven by kmer_hash (dna.c:722-735) and kmer_eq
  *       (dna.c:655-668,686-696; opclass dna--1.0.sql:204-212).
- *   dnagpu_partition / dnagpu_owner_of
- *       no reference counterpart (the reference is single-process); this is
- *       the owner-routing step of the multi-GPU GROUP BY.
+ *   dnagpu_filter_keys
+ *       the same two operators as a seq scan over a stored kmer column
+ *       (SELECT ... WHERE kmer_sequence ^@ / @> / =, test.sql:186-262).
+ *   dnagpu_encode_dna / dnagpu_seq_from_text / dnagpu_decode_dna
+ *       dna_in -> dna_make: validate_dna_sequence (dna.c:159-171) + encode_dna
+ *       (dna.c:114-128); dna_out -> decode_dna (dna.c:135-152).
+ *   dnagpu_partition / dnagpu_owner_of, dnagpu_shuffle_*, dnagpu_peer_*
+ *       no reference counterpart (the reference is single-process); these are
+ *       the owner-routing / exchange steps of the multi-GPU GROUP BY.
  *
  * Errors: every call returns an int status (0 = ok).  Argument errors carry
  * the reference's own ereport() texts (see dnagpu_strerror), so glue can do
@@ -103,13 +109,13 @@ typedef struct dnagpu_stats {
 enum {
     DNAGPU_COUNT_AUTO = 0,
     DNAGPU_COUNT_DENSE = 1,     /* direct-indexed 4^k counters (k <= 16)        */
-    DNAGPU_COUNT_HASH = 2,      /* HBM open-addressing table, CAS + RED         */
-    DNAGPU_COUNT_PARTITION = 3  /* radix-partition to L2-sized buckets, then hash */
+    DNAGPU_COUNT_HASH = 2,      /* HBM open-addressing table, CAS + add         */
+    DNAGPU_COUNT_PARTITION = 3  /* two-level radix partition, then one shared-memory table per bucket */
 };
 
 typedef struct dnagpu_count_opts {
     int32_t method;        /* DNAGPU_COUNT_*                                    */
-    int32_t warp_aggregate;/* 1: merge equal keys inside a warp before atomics  */
+    int32_t warp_aggregate;/* reserved, must be 0 (MATCH.ANY measured too slow)  */
     double load_factor;    /* hash table target load, 0 = default (0.5)         */
     uint64_t expected_keys;/* 0 = derive from input (n_kmers, 4^k)              */
 } dnagpu_count_opts;
