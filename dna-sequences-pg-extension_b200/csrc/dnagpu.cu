@@ -1472,7 +1472,8 @@ static int l1_regions_begin(dnagpu_ctx *ctx, Scratch &sc, uint64_t n_rows, int b
 {
     r->b1 = b1;
     r->P1 = 1u << b1;
-    r->cap = (n_rows >> b1) + (n_rows >> b1) / 8 + 65536; /* hashing is even; the slack is for k-mers with ~1e5-1e6 copies */
+    const uint64_t mean = n_rows >> b1; /* hashing is even; the slack is for k-mers with many copies */
+    r->cap = mean + mean / 8 + std::min<uint64_t>(65536, std::max<uint64_t>(1024, mean / 2));
     TRY(sc.get((void **)&r->keys, ((uint64_t)r->P1 * r->cap + 2) * 8));
     TRY(sc.get((void **)&r->beg, (uint64_t)r->P1 * 8));
     TRY(sc.get((void **)&r->end, (uint64_t)r->P1 * 8));

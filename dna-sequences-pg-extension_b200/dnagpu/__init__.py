@@ -328,28 +328,38 @@ class Context:
         return int(n.value)
 
     def filter(self, seq, k, prefix=None, pattern=None):
+        """Rows of generate_kmers that pass the WHERE clause, in sequence order (torch int64 CUDA tensor).
+        One pass into a buffer sized for 1/8 of the rows; a second, exactly sized pass only if that was too small."""
         import torch
         w, _keep = _where(prefix, pattern)
         wp = C.byref(w) if w is not None else None
         n = C.c_uint64()
-        self._ok(self.lib.dnagpu_filter(self.handle, seq.handle, k, wp, None, 0, C.byref(n)))
-        out = torch.empty(max(int(n.value), 2), dtype=torch.int64, device=f"cuda:{self.device}")
-        if n.value:
-            self._ok(self.lib.dnagpu_filter(self.handle, seq.handle, k, wp, out.data_ptr(), out.numel(), C.byref(n)))
-        return out[:n.value]
+        guess = seq.kmer_count(k) if w is None else max(1024, seq.kmer_count(k) // 8)
+        for _ in range(2):
+            out = torch.empty(max(int(guess), 2), dtype=torch.int64, device=f"cuda:{self.device}")
+            rc = self.lib.dnagpu_filter(self.handle, seq.handle, k, wp, out.data_ptr(), out.numel(), C.byref(n))
+            if rc != 21:  # DNAGPU_ECAPACITY: n holds the need
+                self._ok(rc)
+                return out[:n.value]
+            guess = n.value
+        self._ok(rc)
 
     def filter_keys(self, keys, k, prefix=None, pattern=None):
-        """The same predicates over a materialised kmer column (torch int64 CUDA tensor)."""
+        """The same predicates over a materialised kmer column (torch int64 CUDA tensor), rows in column order."""
         import torch
         w, _keep = _where(prefix, pattern)
         wp = C.byref(w) if w is not None else None
         n = C.c_uint64()
-        self._ok(self.lib.dnagpu_filter_keys(self.handle, keys.data_ptr(), keys.numel(), k, wp, None, 0, C.byref(n)))
-        out = torch.empty(max(int(n.value), 2), dtype=torch.int64, device=f"cuda:{self.device}")
-        if n.value:
-            self._ok(self.lib.dnagpu_filter_keys(self.handle, keys.data_ptr(), keys.numel(), k, wp,
-                                                 out.data_ptr(), out.numel(), C.byref(n)))
-        return out[:n.value]
+        guess = keys.numel() if w is None else max(1024, keys.numel() // 8)
+        for _ in range(2):
+            out = torch.empty(max(int(guess), 2), dtype=torch.int64, device=f"cuda:{self.device}")
+            rc = self.lib.dnagpu_filter_keys(self.handle, keys.data_ptr(), keys.numel(), k, wp, out.data_ptr(),
+                                             out.numel(), C.byref(n))
+            if rc != 21:
+                self._ok(rc)
+                return out[:n.value]
+            guess = n.value
+        self._ok(rc)
 
     # ---- GROUP BY kmer ------------------------------------------------------------------
     @staticmethod
