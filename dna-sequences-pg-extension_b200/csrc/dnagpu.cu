@@ -267,6 +267,7 @@ extern "C" int dnagpu_create(dnagpu_ctx **out, int device)
             const int psmem32 = 32 * kScatThreads * (int)sizeof(uint64_t) + (int)sizeof(ScatterSmem);
 #define PSMEM32_ATTR(kern) cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, psmem32)
             PSMEM32_ATTR((k_part_scatter_keys<false, 32>));
+            PSMEM32_ATTR((k_part_scatter_keys<true, 32>));
             PSMEM32_ATTR((k_part_scatter_seq<kSingle, false, 32>));
             PSMEM32_ATTR((k_part_scatter_seq<kSingle, true, 32>));
             PSMEM32_ATTR((k_part_scatter_seq<kFixed, false, 32>));
@@ -1620,6 +1621,19 @@ static int count_kmers_pipelined(dnagpu_ctx *ctx, const uint64_t *words, uint64_
     return DNAGPU_OK;
 }
 
+/* One predicate scan, matches appended in no particular order. */
+static int collect_rows(dnagpu_ctx *ctx, const CountInput &in, int k, uint64_t *d_out, uint64_t cap, uint64_t *n_match)
+{
+    const unsigned tiles = grid_for(in.v.n_items, kThreads);
+    const int smem = kThreads * 32 * (int)sizeof(uint64_t);
+    TRY(zero_counters(ctx));
+    DISPATCH_LAYOUT(in.seq->layout, TRY(launch(ctx, "filter_collect", [&] {
+        k_filter_collect<LY><<<(tiles + kFilterTiles - 1) / kFilterTiles, kThreads, smem, ctx->stream>>>(
+            in.v, in.p, kmer_mask(k), cap, ctx->d_ctr + C_CURSOR, d_out);
+    })));
+    return read_u64(ctx, (const uint64_t *)(ctx->d_ctr + C_CURSOR), n_match);
+}
+
 static int count_any(dnagpu_ctx *ctx, CountInput &in, int k, const dnagpu_count_opts *opts,
                      dnagpu_stats *stats, dnagpu_table **table)
 {
@@ -1644,15 +1658,8 @@ static int count_any(dnagpu_ctx *ctx, CountInput &in, int k, const dnagpu_count_
         uint64_t n_match = 0, cap0 = std::min<uint64_t>(in.n, std::max<uint64_t>(1ull << 20, in.n / 8));
         uint64_t *keys;
         TRY(keep.get((void **)&keys, (cap0 + 2) * 8));
-        const unsigned tiles = grid_for(in.v.n_items, kThreads);
-        const int smem = kThreads * 32 * (int)sizeof(uint64_t);
         for (int attempt = 0; attempt < 2; ++attempt) {
-            TRY(zero_counters(ctx));
-            DISPATCH_LAYOUT(in.seq->layout, TRY(launch(ctx, "filter_collect", [&] {
-                k_filter_collect<LY><<<(tiles + kFilterTiles - 1) / kFilterTiles, kThreads, smem, ctx->stream>>>(
-                    in.v, in.p, kmer_mask(k), cap0, ctx->d_ctr + C_CURSOR, keys);
-            })));
-            TRY(read_u64(ctx, (const uint64_t *)(ctx->d_ctr + C_CURSOR), &n_match));
+            TRY(collect_rows(ctx, in, k, keys, cap0, &n_match));
             if (n_match <= cap0) break;
             keep.release(keys);
             dfree(ctx, keys);
@@ -1703,6 +1710,26 @@ static int count_any(dnagpu_ctx *ctx, CountInput &in, int k, const dnagpu_count_
         *table = nullptr;
     }
     return rc;
+}
+
+extern "C" int dnagpu_collect(dnagpu_ctx *ctx, const dnagpu_seq *seq, int k, const dnagpu_where *filter,
+                              uint64_t *d_out, uint64_t cap, uint64_t *n_out)
+{
+    if (!ctx || !seq || !n_out || (cap && !d_out)) return fail(ctx, DNAGPU_EARG, "dnagpu_collect: NULL argument");
+    TRY(check_k(ctx, k));
+    TRY(check_filter_literals(ctx, filter));
+    CU(ctx, cudaSetDevice(ctx->device));
+    *n_out = 0;
+    CountInput in;
+    in.seq = seq;
+    TRY(make_view(ctx, seq, k, &in.v));
+    in.n = in.v.n_rows;
+    TRY(build_pred(ctx, filter, k, in.n, &in.p, &in.filtered));
+    if (in.n == 0) return DNAGPU_OK;
+    TRY(collect_rows(ctx, in, k, d_out, cap, n_out));
+    if (*n_out > cap)
+        return fail(ctx, DNAGPU_ECAPACITY, "collect needs room for %llu rows", (unsigned long long)*n_out);
+    return DNAGPU_OK;
 }
 
 extern "C" int dnagpu_count(dnagpu_ctx *ctx, const dnagpu_seq *seq, int k,
@@ -2089,6 +2116,75 @@ extern "C" int dnagpu_shuffle_scatter_to(dnagpu_ctx *ctx, const dnagpu_seq *seq,
     })));
     TRY(fetch_counters(ctx)); /* synchronises: every store of this rank has been issued and retired */
     if (rows_kept) *rows_kept = ctx->h_ctr[C_TOTAL];
+    if (side_rows) *side_rows = ctx->h_ctr[C_SIDE];
+    return DNAGPU_OK;
+}
+
+/* the same two steps from a key list on the device */
+static int shuffle_root(dnagpu_ctx *ctx, Scratch &sc, uint64_t n, uint64_t tile, uint64_t **root_off, uint64_t **tiles)
+{
+    TRY(sc.get((void **)root_off, 2 * 8));
+    ctx->h_ctr[0] = 0;
+    ctx->h_ctr[1] = n;
+    CU(ctx, cudaMemcpyAsync(*root_off, ctx->h_ctr, 16, cudaMemcpyHostToDevice, ctx->stream));
+    CU(ctx, cudaStreamSynchronize(ctx->stream)); /* h_ctr is pinned staging shared with the counters */
+    return part_tiles(ctx, sc, *root_off, *root_off + 1, 1, tile, tiles);
+}
+
+extern "C" int dnagpu_shuffle_hist_keys(dnagpu_ctx *ctx, const uint64_t *d_keys, uint64_t n,
+                                        const dnagpu_shuffle_plan *plan, uint64_t *digit_counts)
+{
+    if (!ctx || !plan || !digit_counts || (n && !d_keys))
+        return fail(ctx, DNAGPU_EARG, "dnagpu_shuffle_hist_keys: NULL argument");
+    CU(ctx, cudaSetDevice(ctx->device));
+    for (uint32_t d = 0; d < plan->n_digits; ++d) digit_counts[d] = 0;
+    if (n == 0) return DNAGPU_OK;
+    Scratch sc(ctx);
+    const uint32_t P1 = plan->n_digits;
+    unsigned long long *hist1;
+    uint64_t *root_off, *tiles;
+    TRY(sc.get((void **)&hist1, (uint64_t)P1 * 8));
+    CU(ctx, cudaMemsetAsync(hist1, 0, (uint64_t)P1 * 8, ctx->stream));
+    TRY(shuffle_root(ctx, sc, n, kSuperTile, &root_off, &tiles));
+    TRY(launch(ctx, "part_hist", [&] {
+        k_part_hist_keys<<<grid_for(n, kSuperTile), kThreads, 0, ctx->stream>>>(d_keys, root_off, root_off + 1, tiles, 1, 1,
+                                                                              64 - plan->bits1, P1, hist1);
+    }));
+    CU(ctx, cudaMemcpyAsync(digit_counts, hist1, (uint64_t)P1 * 8, cudaMemcpyDeviceToHost, ctx->stream));
+    CU(ctx, cudaStreamSynchronize(ctx->stream));
+    return DNAGPU_OK;
+}
+
+extern "C" int dnagpu_shuffle_scatter_keys_to(dnagpu_ctx *ctx, const uint64_t *d_keys, uint64_t n,
+                                              const dnagpu_shuffle_plan *plan, const uint64_t *digit_dest,
+                                              uint64_t *side_rows)
+{
+    if (!ctx || !plan || !digit_dest || (n && !d_keys))
+        return fail(ctx, DNAGPU_EARG, "dnagpu_shuffle_scatter_keys_to: NULL argument");
+    CU(ctx, cudaSetDevice(ctx->device));
+    if (side_rows) *side_rows = 0;
+    if (n == 0) return DNAGPU_OK;
+    Scratch sc(ctx);
+    const uint32_t P1 = plan->n_digits;
+    std::vector<uint64_t> idx(P1); /* addresses / 8 as indices from a NULL base, as in dnagpu_shuffle_scatter_to */
+    for (uint32_t d = 0; d < P1; ++d) {
+        if (digit_dest[d] & 7) return fail(ctx, DNAGPU_EARG, "destination of digit %u is not 8-byte aligned", d);
+        idx[d] = digit_dest[d] >> 3;
+    }
+    uint64_t *d_idx, *root_off, *tiles;
+    unsigned long long *cur1;
+    TRY(sc.get((void **)&d_idx, ((uint64_t)P1 + 1) * 8));
+    TRY(sc.get((void **)&cur1, (uint64_t)P1 * 8));
+    CU(ctx, cudaMemcpyAsync(d_idx, idx.data(), (uint64_t)P1 * 8, cudaMemcpyHostToDevice, ctx->stream));
+    CU(ctx, cudaMemsetAsync(cur1, 0, (uint64_t)P1 * 8, ctx->stream));
+    TRY(shuffle_root(ctx, sc, n, 2 * kTileKeys, &root_off, &tiles)); /* synchronises: idx is a host temporary */
+    TRY(zero_counters(ctx));
+    const int psmem32 = 32 * kScatThreads * (int)sizeof(uint64_t) + (int)sizeof(ScatterSmem);
+    TRY(launch(ctx, "part_scatter_peer", [&] {
+        k_part_scatter_keys<true, 32><<<grid_for(n, 2 * kTileKeys), kScatThreads, psmem32, ctx->stream>>>(
+            d_keys, root_off, root_off + 1, tiles, 1, 1, 64 - plan->bits1, P1, d_idx, cur1, (uint64_t *)nullptr, ctx->d_ctr);
+    }));
+    TRY(fetch_counters(ctx)); /* synchronises: every store of this rank has been issued and retired */
     if (side_rows) *side_rows = ctx->h_ctr[C_SIDE];
     return DNAGPU_OK;
 }

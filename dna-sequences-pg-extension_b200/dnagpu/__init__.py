@@ -344,6 +344,22 @@ class Context:
             guess = n.value
         self._ok(rc)
 
+    def collect(self, seq, k, prefix=None, pattern=None):
+        """The rows that pass the WHERE clause in no particular order (one predicate scan): torch int64 CUDA tensor."""
+        import torch
+        w, _keep = _where(prefix, pattern)
+        wp = C.byref(w) if w is not None else None
+        n = C.c_uint64()
+        guess = seq.kmer_count(k) if w is None else max(1024, seq.kmer_count(k) // 8)
+        for _ in range(2):
+            out = torch.empty(max(int(guess), 2), dtype=torch.int64, device=f"cuda:{self.device}")
+            rc = self.lib.dnagpu_collect(self.handle, seq.handle, k, wp, out.data_ptr(), out.numel(), C.byref(n))
+            if rc != 21:  # DNAGPU_ECAPACITY: n holds the need
+                self._ok(rc)
+                return out[:n.value]
+            guess = n.value
+        self._ok(rc)
+
     def filter_keys(self, keys, k, prefix=None, pattern=None):
         """The same predicates over a materialised kmer column (torch int64 CUDA tensor), rows in column order."""
         import torch
@@ -503,6 +519,19 @@ class Context:
                                                     C.byref(plan), digit_dest.ctypes.data_as(_lib.u64p),
                                                     C.byref(kept), C.byref(side)))
         return int(kept.value), int(side.value)
+
+    def shuffle_hist_keys(self, keys, plan):
+        counts = np.zeros(plan.n_digits, dtype=np.uint64)
+        self._ok(self.lib.dnagpu_shuffle_hist_keys(self.handle, keys.data_ptr(), keys.numel(), C.byref(plan),
+                                                   counts.ctypes.data_as(_lib.u64p)))
+        return counts
+
+    def shuffle_scatter_keys_to(self, keys, plan, digit_dest):
+        digit_dest = np.ascontiguousarray(digit_dest, dtype=np.uint64)
+        side = C.c_uint64()
+        self._ok(self.lib.dnagpu_shuffle_scatter_keys_to(self.handle, keys.data_ptr(), keys.numel(), C.byref(plan),
+                                                         digit_dest.ctypes.data_as(_lib.u64p), C.byref(side)))
+        return int(side.value)
 
     def shuffle_count_addr(self, addr, piece_counts, n_groups, plan, k):
         """dnagpu_shuffle_count on a raw device address (a peer-allocated receive buffer)."""

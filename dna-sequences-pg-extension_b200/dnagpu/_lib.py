@@ -67,6 +67,7 @@ SIGNATURES = {
     "dnagpu_extract": (C.c_int, [vp, vp, C.c_int, vp, u64, u64p]),
     "dnagpu_filter_kmers": (C.c_int, [vp, vp, u64, C.c_int, C.POINTER(Where), vp, u64, u64p]),
     "dnagpu_filter": (C.c_int, [vp, vp, C.c_int, C.POINTER(Where), vp, u64, u64p]),
+    "dnagpu_collect": (C.c_int, [vp, vp, C.c_int, C.POINTER(Where), vp, u64, u64p]),
     "dnagpu_filter_keys": (C.c_int, [vp, vp, u64, C.c_int, C.POINTER(Where), vp, u64, u64p]),
     "dnagpu_count_kmers": (C.c_int, [vp, vp, u64, C.c_int, C.POINTER(Where), C.POINTER(Stats), C.POINTER(vp)]),
     "dnagpu_count_reads": (C.c_int, [vp, vp, u64, C.c_uint32, C.c_uint32, C.c_int, C.POINTER(Where),
@@ -95,6 +96,8 @@ SIGNATURES = {
     "dnagpu_shuffle_hist": (C.c_int, [vp, vp, C.c_int, C.POINTER(Where), C.POINTER(ShufflePlan), u64p]),
     "dnagpu_shuffle_scatter_to": (C.c_int, [vp, vp, C.c_int, C.POINTER(Where), C.POINTER(ShufflePlan), u64p, u64p,
                                             u64p]),
+    "dnagpu_shuffle_hist_keys": (C.c_int, [vp, vp, u64, C.POINTER(ShufflePlan), u64p]),
+    "dnagpu_shuffle_scatter_keys_to": (C.c_int, [vp, vp, u64, C.POINTER(ShufflePlan), u64p, u64p]),
     "dnagpu_profile_enable": (C.c_int, [vp, C.c_int]),
     "dnagpu_profile_reset": (C.c_int, [vp]),
     "dnagpu_profile_query": (C.c_int, [vp, C.c_char_p, C.POINTER(C.c_double), u64p]),

@@ -235,8 +235,15 @@ def count_sharded_peer(ctx, seq, k, n_rows_total, world, rank, px, prefix=None, 
     import torch
     import torch.distributed as dist
     dev = torch.device("cuda", ctx.device)
+    # a WHERE clause is evaluated once into a key list (one predicate scan); hist and scatter then read the list,
+    # and the partition plan is sized by the rows that passed on all ranks, not by the rows scanned
+    listed = ctx.collect(seq, k, prefix=prefix, pattern=pattern) if (prefix is not None or pattern is not None) else None
+    if listed is not None:
+        passed = torch.tensor([listed.numel()], dtype=torch.int64, device=dev)
+        dist.all_reduce(passed, group=group)
+        n_rows_total = max(int(passed.item()), 1)
     plan = ctx.shuffle_plan(n_rows_total, world)
-    mine = ctx.shuffle_hist(seq, k, plan, prefix=prefix, pattern=pattern)
+    mine = ctx.shuffle_hist_keys(listed, plan) if listed is not None else ctx.shuffle_hist(seq, k, plan)
     counts = torch.empty(world * plan.n_digits, dtype=torch.int64, device=dev)
     dist.all_gather_into_tensor(counts, torch.from_numpy(mine.astype(np.int64)).to(dev), group=group)
     counts = counts.cpu().numpy().astype(np.uint64).reshape(world, plan.n_digits)
@@ -250,7 +257,10 @@ def count_sharded_peer(ctx, seq, k, n_rows_total, world, rank, px, prefix=None, 
         if int(block.sum()) > px.capacity:
             raise RuntimeError(f"rank {o} would receive {int(block.sum())} keys, above the peer buffer of {px.capacity}")
         dest[a:b] = np.uint64(px.base[o]) + np.uint64(8) * (np.uint64(before_me) + within)
-    kept, side = ctx.shuffle_scatter_to(seq, k, plan, dest, prefix=prefix, pattern=pattern)
+    if listed is not None:
+        kept, side = int(listed.numel()), ctx.shuffle_scatter_keys_to(listed, plan, dest)
+    else:
+        kept, side = ctx.shuffle_scatter_to(seq, k, plan, dest)
     dist.barrier(group=group)                                   # every rank's stores have landed
     lo, hi = ranges[rank]
     st = ctx.shuffle_count_addr(px.local, counts[:, lo:hi].reshape(-1), hi - lo, plan, k)

@@ -6,3 +6,9 @@ CREATE OR REPLACE FUNCTION kmer_stats(dna, integer, OUT total bigint, OUT "disti
     RETURNS record
     AS 'MODULE_PATHNAME', 'kmer_stats'
     LANGUAGE C IMMUTABLE STRICT PARALLEL SAFE;
+
+-- SELECT kmer, count(*) FROM generate_kmers(seq, k) GROUP BY kmer  (README.md:107-116) in one call
+CREATE OR REPLACE FUNCTION count_kmers(dna, integer, OUT kmer kmer, OUT count bigint)
+    RETURNS SETOF record
+    AS 'MODULE_PATHNAME', 'count_kmers'
+    LANGUAGE C IMMUTABLE STRICT PARALLEL SAFE;

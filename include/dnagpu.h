@@ -217,6 +217,11 @@ int dnagpu_filter_kmers(dnagpu_ctx *ctx, const uint64_t *words, uint64_t n_bases
 int dnagpu_filter(dnagpu_ctx *ctx, const dnagpu_seq *seq, int k,
                   const dnagpu_where *filter, uint64_t *d_out, uint64_t cap,
                   uint64_t *n_out);
+/* The rows that pass the WHERE clause in NO particular order -- what a GROUP BY or an exchange
+ * between GPUs needs; one predicate scan instead of the two of the ordered form.  Writes at most
+ * cap rows; with more matches than cap returns DNAGPU_ECAPACITY and *n_out = the number needed. */
+int dnagpu_collect(dnagpu_ctx *ctx, const dnagpu_seq *seq, int k, const dnagpu_where *filter,
+                   uint64_t *d_out, uint64_t cap, uint64_t *n_out);
 /* The same predicates over a materialised kmer column (k the same for all
  * rows): keeps input order.  d_out may alias nothing and may be NULL. */
 int dnagpu_filter_keys(dnagpu_ctx *ctx, const uint64_t *d_keys, uint64_t n, int k,
@@ -316,6 +321,14 @@ int dnagpu_shuffle_hist(dnagpu_ctx *ctx, const dnagpu_seq *seq, int k, const dna
 int dnagpu_shuffle_scatter_to(dnagpu_ctx *ctx, const dnagpu_seq *seq, int k, const dnagpu_where *filter,
                               const dnagpu_shuffle_plan *plan, const uint64_t *digit_dest,
                               uint64_t *rows_kept, uint64_t *side_rows);
+/* The same two steps over a key list already on the device (e.g. what dnagpu_collect kept of
+ * a selective WHERE clause): keys per digit, then the stores.  side_rows = the 'G' x 32 rows
+ * (k = 32) of the list, which are not stored. */
+int dnagpu_shuffle_hist_keys(dnagpu_ctx *ctx, const uint64_t *d_keys, uint64_t n,
+                             const dnagpu_shuffle_plan *plan, uint64_t *digit_counts);
+int dnagpu_shuffle_scatter_keys_to(dnagpu_ctx *ctx, const uint64_t *d_keys, uint64_t n,
+                                   const dnagpu_shuffle_plan *plan, const uint64_t *digit_dest,
+                                   uint64_t *side_rows);
 
 /* ---- per-kernel device timing (CUDA events on the ctx stream) --------------- */
 int dnagpu_profile_enable(dnagpu_ctx *ctx, int on);

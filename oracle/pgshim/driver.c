@@ -510,3 +510,80 @@ int dnaref_count(const uint64_t *words, uint64_t n_seqs, uint64_t bases_per_seq,
     free(tids);
     return rc;
 }
+
+#ifdef DNAREF_WITH_GLUE
+/*
+ * The GPU glue's pushdown functions (dna-sequences-pg-extension_b200/pg/dna_gpu.c), linked into
+ * this build together with dna.c.  The driver plays the executor: it supplies the expected row
+ * type, runs the SRF loop and unpacks the composite Datums.
+ */
+extern Datum kmer_stats(PG_FUNCTION_ARGS);
+extern Datum count_kmers(PG_FUNCTION_ARGS);
+
+static Datum call_row(Datum (*fn)(PG_FUNCTION_ARGS), FmgrInfo *fl, ReturnSetInfo *rsi, TupleDesc desc, Datum a0,
+                      Datum a1)
+{
+    FunctionCallInfoBaseData fc;
+    memset(&fc, 0, sizeof fc);
+    fc.flinfo = fl;
+    fc.resultinfo = rsi;
+    fc.nargs = 2;
+    fc.args[0].value = a0;
+    fc.args[1].value = a1;
+    fc.shim_result_desc = desc;
+    return fn(&fc);
+}
+
+/* SELECT * FROM kmer_stats(dna, k) */
+int dnaref_kmer_stats(const uint64_t *words, uint64_t n_bases, int k, int64_t stats[3], char *err, size_t errcap)
+{
+    GUARDED(err, errcap, {
+        RefDna *d = dna_from_words(words, n_bases);
+        TupleDescData desc = {3};
+        HeapTuple t = (HeapTuple)DatumGetPointer(call_row(kmer_stats, &fl_, NULL, &desc, PointerGetDatum(d), Int32GetDatum(k)));
+        int i;
+        for (i = 0; i < 3; i++) stats[i] = DatumGetInt64(t->values[i]);
+        heap_freetuple(t);
+        pfree(d);
+    });
+    return 0;
+}
+
+/* SELECT * FROM count_kmers(dna, k): rows in the order the function returns them */
+int dnaref_count_kmers(const uint64_t *words, uint64_t n_bases, int k, uint64_t *kmers, int64_t *counts,
+                       uint64_t cap, uint64_t *n_out, char *err, size_t errcap)
+{
+    GUARDED(err, errcap, {
+        RefDna *d = dna_from_words(words, n_bases);
+        TupleDescData desc = {2};
+        ReturnSetInfo rsi;
+        uint64_t n = 0;
+        int bad_len = 0;
+        for (;;) {
+            Datum r;
+            rsi.isDone = ExprSingleResult;
+            r = call_row(count_kmers, &fl_, &rsi, &desc, PointerGetDatum(d), Int32GetDatum(k));
+            if (rsi.isDone == ExprEndResult) break;
+            {
+                HeapTuple t = (HeapTuple)DatumGetPointer(r);
+                RefKmer *km = (RefKmer *)DatumGetPointer(t->values[0]);
+                if (km->length != k || t->natts != 2 || t->nulls[0] || t->nulls[1]) bad_len = 1;
+                if (n < cap) {
+                    kmers[n] = km->bit_sequence;
+                    counts[n] = DatumGetInt64(t->values[1]);
+                }
+                n++;
+                pfree(km);
+                heap_freetuple(t);
+            }
+        }
+        *n_out = n;
+        pfree(d);
+        if (bad_len) {
+            snprintf(shim_error_text, sizeof shim_error_text, "driver: malformed count_kmers row");
+            longjmp(jb_, 1);
+        }
+    });
+    return 0;
+}
+#endif /* DNAREF_WITH_GLUE */

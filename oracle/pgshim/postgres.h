@@ -5,7 +5,8 @@
  *
  * What is emulated: palloc/pfree (malloc), ereport(ERROR) (longjmp to the driver), varlena
  * headers, the fmgr V1 calling convention, the ValuePerCall SRF protocol of funcapi.h,
- * pqformat buffers, hash_any (Bob Jenkins' lookup3 as PostgreSQL uses it) and the struct
+ * composite results (get_call_result_type / heap_form_tuple, for the GPU glue's pushdown
+ * functions: dna.c itself returns none), pqformat buffers, hash_any (Bob Jenkins' lookup3 as PostgreSQL uses it) and the struct
  * layouts of access/spgist.h that dna.c's index support functions mention (never called).
  * Every other server header dna.c includes is an empty file that includes this one.
  */
@@ -95,6 +96,8 @@ char *text_to_cstring(const text *t);
 #define DatumGetInt32(x) ((int32)(x))
 #define UInt32GetDatum(x) ((Datum)(uintptr_t)(uint32)(x))
 #define DatumGetUInt32(x) ((uint32)(x))
+#define Int64GetDatum(x) ((Datum)(int64)(x)) /* 64-bit build: pass-by-value */
+#define DatumGetInt64(x) ((int64)(x))
 #define BoolGetDatum(x) ((Datum)((x) ? 1 : 0))
 #define DatumGetBool(x) ((bool)((x) != 0))
 
@@ -115,6 +118,7 @@ typedef struct FunctionCallInfoBaseData {
     bool isnull;
     short nargs;
     NullableDatum args[8];
+    void *shim_result_desc; /* shim only: the row type the caller expects (the catalog lookup of the server) */
 } FunctionCallInfoBaseData;
 typedef FunctionCallInfoBaseData *FunctionCallInfo;
 #define PG_FUNCTION_ARGS FunctionCallInfo fcinfo
@@ -177,6 +181,24 @@ FuncCallContext *shim_init_MultiFuncCall(FunctionCallInfo fcinfo);
         rsi->isDone = ExprEndResult;                              \
         PG_RETURN_NULL();                                         \
     } while (0)
+
+/* ---- funcapi.h / access/htup_details.h: composite results ---- */
+typedef struct TupleDescData {
+    int natts;
+} TupleDescData;
+typedef TupleDescData *TupleDesc;
+typedef enum { TYPEFUNC_SCALAR, TYPEFUNC_COMPOSITE, TYPEFUNC_COMPOSITE_DOMAIN, TYPEFUNC_RECORD, TYPEFUNC_OTHER } TypeFuncClass;
+TypeFuncClass get_call_result_type(FunctionCallInfo fcinfo, Oid *resultTypeId, TupleDesc *resultTupleDesc);
+TupleDesc BlessTupleDesc(TupleDesc tupdesc);
+typedef struct HeapTupleData { /* the shim keeps the column values as they are */
+    int natts;
+    Datum *values;
+    bool *nulls;
+} HeapTupleData;
+typedef HeapTupleData *HeapTuple;
+HeapTuple heap_form_tuple(TupleDesc tupdesc, const Datum *values, const bool *isnull);
+void heap_freetuple(HeapTuple t);
+#define HeapTupleGetDatum(t) PointerGetDatum(t)
 
 /* ---- libpq/pqformat.h ---- */
 typedef struct StringInfoData {

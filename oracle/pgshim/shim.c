@@ -81,6 +81,32 @@ FuncCallContext *shim_init_MultiFuncCall(FunctionCallInfo fcinfo)
     return f;
 }
 
+/* ---- composite results ---- */
+TypeFuncClass get_call_result_type(FunctionCallInfo fcinfo, Oid *resultTypeId, TupleDesc *resultTupleDesc)
+{
+    if (resultTypeId) *resultTypeId = InvalidOid;
+    if (!fcinfo->shim_result_desc) return TYPEFUNC_SCALAR;
+    if (resultTupleDesc) *resultTupleDesc = (TupleDesc)fcinfo->shim_result_desc;
+    return TYPEFUNC_COMPOSITE;
+}
+TupleDesc BlessTupleDesc(TupleDesc tupdesc) { return tupdesc; }
+HeapTuple heap_form_tuple(TupleDesc tupdesc, const Datum *values, const bool *isnull)
+{
+    HeapTuple t = (HeapTuple)palloc(sizeof(HeapTupleData));
+    t->natts = tupdesc->natts;
+    t->values = (Datum *)palloc(sizeof(Datum) * (size_t)t->natts);
+    t->nulls = (bool *)palloc(sizeof(bool) * (size_t)t->natts);
+    memcpy(t->values, values, sizeof(Datum) * (size_t)t->natts);
+    memcpy(t->nulls, isnull, sizeof(bool) * (size_t)t->natts);
+    return t;
+}
+void heap_freetuple(HeapTuple t)
+{
+    pfree(t->values);
+    pfree(t->nulls);
+    pfree(t);
+}
+
 /* ---- pqformat (network byte order, like the server) ---- */
 static void sb_need(StringInfo b, int n)
 {

@@ -3,6 +3,8 @@ the PostgreSQL API shim in oracle/pgshim/ and driven like the executor drives it
 
 TEST INFRASTRUCTURE ONLY.  The library can be built only where /root/reference exists
 (`make -C oracle ref`); the built .so travels to the GPU box with the repo snapshot.
+`make -C oracle glue` builds the same module with generate_kmers swapped for the GPU glue
+(pg/dna_gpu.c -> libdnagpu): the drop-in itself, driven through the same fmgr / SRF protocol.
 """
 import ctypes as C
 import os
@@ -12,118 +14,23 @@ import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 SO = os.path.join(_HERE, "_ref", "libdnaref.so")
+# the same module with generate_kmers swapped for the GPU glue (pg/dna_gpu.c) + the glue's pushdown functions
+GLUE_SO = os.path.join(_HERE, "_ref", "libdnaglue.so")
 REFERENCE_SRC = "/root/reference/dna.c"
 u64, vp = C.c_uint64, C.c_void_p
-_lib = None
+_default = None
 
 
 def available():
     return os.path.exists(SO) or os.path.exists(REFERENCE_SRC)
 
 
-def lib():
-    global _lib
-    if _lib is not None:
-        return _lib
-    if not os.path.exists(SO):
-        if not os.path.exists(REFERENCE_SRC):
-            raise FileNotFoundError("oracle/_ref/libdnaref.so is not built and /root/reference is absent")
-        subprocess.run(["make", "-C", _HERE, "ref"], check=True, stdout=subprocess.DEVNULL)
-    L = C.CDLL(SO)
-    err = [C.c_char_p, C.c_size_t]
-    sig = {
-        "dnaref_dna_in": (C.c_int, [C.c_char_p, vp, u64, C.POINTER(u64)] + err),
-        "dnaref_dna_out": (C.c_int, [vp, u64, C.c_char_p, C.c_size_t] + err),
-        "dnaref_kmer_in": (C.c_int, [C.c_char_p, C.POINTER(u64), C.POINTER(C.c_int32)] + err),
-        "dnaref_kmer_out": (C.c_int, [u64, C.c_int32, C.c_char_p, C.c_size_t] + err),
-        "dnaref_qkmer_in": (C.c_int, [C.c_char_p] + err),
-        "dnaref_starts_with": (C.c_int, [u64, C.c_int32, u64, C.c_int32, C.POINTER(C.c_int)] + err),
-        "dnaref_contains": (C.c_int, [C.c_char_p, u64, C.c_int32, C.POINTER(C.c_int)] + err),
-        "dnaref_kmer_hash": (C.c_uint32, [u64]),
-        "dnaref_kmer_eq": (C.c_int, [u64, C.c_int32, u64, C.c_int32]),
-        "dnaref_generate_kmers": (C.c_int, [vp, u64, C.c_int, u64, C.c_int32, C.c_char_p, vp, u64, C.POINTER(u64)] + err),
-        "dnaref_count": (C.c_int, [vp, u64, u64, u64, C.c_int, u64, C.c_int32, C.c_char_p, C.c_int, vp, vp, vp, vp,
-                                   u64, C.POINTER(u64)] + err),
-    }
-    for name, (res, args) in sig.items():
-        fn = getattr(L, name)
-        fn.restype, fn.argtypes = res, args
-    _lib = L
-    return L
+def glue_available():
+    return os.path.exists(GLUE_SO) or os.path.exists(REFERENCE_SRC)
 
 
 class PgError(ValueError):
-    """An ereport(ERROR) raised inside the reference's code."""
-
-
-def _run(fn, *args):
-    buf = C.create_string_buffer(512)
-    rc = fn(*args, buf, 512)
-    if rc != 0:
-        raise PgError(buf.value.decode())
-
-
-def dna_in(text):
-    words = np.zeros(len(text) // 32 + 2, dtype=np.uint64)
-    n = u64()
-    _run(lib().dnaref_dna_in, text.encode("ascii", "replace"), words.ctypes.data, words.size, C.byref(n))
-    return words[:(n.value + 31) // 32].copy(), n.value
-
-
-def dna_out(words, n):
-    words = np.ascontiguousarray(words, dtype=np.uint64)
-    out = C.create_string_buffer(n + 1)
-    _run(lib().dnaref_dna_out, words.ctypes.data, n, out, n + 1)
-    return out.value.decode()
-
-
-def kmer_in(text):
-    bits, length = u64(), C.c_int32()
-    _run(lib().dnaref_kmer_in, text.encode("ascii", "replace"), C.byref(bits), C.byref(length))
-    return bits.value, length.value
-
-
-def kmer_out(bits, length):
-    out = C.create_string_buffer(40)
-    _run(lib().dnaref_kmer_out, int(bits), length, out, 40)
-    return out.value.decode()
-
-
-def qkmer_in(text):
-    _run(lib().dnaref_qkmer_in, text.encode("ascii", "replace"))
-    return text
-
-
-def starts_with(kbits, klen, pbits, plen):
-    r = C.c_int()
-    _run(lib().dnaref_starts_with, int(kbits), klen, int(pbits), plen, C.byref(r))
-    return bool(r.value)
-
-
-def contains(pattern, kbits, klen):
-    r = C.c_int()
-    _run(lib().dnaref_contains, pattern.encode("ascii", "replace"), int(kbits), klen, C.byref(r))
-    return bool(r.value)
-
-
-def kmer_hash(bits):
-    return int(lib().dnaref_kmer_hash(int(bits)))
-
-
-def kmer_eq(a, alen, b, blen):
-    return bool(lib().dnaref_kmer_eq(int(a), alen, int(b), blen))
-
-
-def generate_kmers(words, n_bases, k, prefix=None, pattern=None):
-    """SELECT * FROM generate_kmers(dna, k) AS g(kmer) [WHERE kmer ^@ prefix AND pattern @> kmer]."""
-    words = np.ascontiguousarray(words, dtype=np.uint64)
-    cap = max(0, n_bases - k + 1) if 1 <= k <= 32 else 0
-    out = np.empty(cap + 1, dtype=np.uint64)
-    n = u64()
-    pb, pl = (0, 0) if prefix is None else prefix
-    _run(lib().dnaref_generate_kmers, words.ctypes.data, n_bases, k, pb, pl,
-         None if pattern is None else pattern.encode("ascii", "replace"), out.ctypes.data, out.size, C.byref(n))
-    return out[:n.value].copy()
+    """An ereport(ERROR) raised inside the reference's (or the glue's) code."""
 
 
 class CountResult:
@@ -133,18 +40,162 @@ class CountResult:
         self.digest, self.kmers, self.counts = digest, kmers, counts
 
 
-def count(words, n_seqs, bases_per_seq, stride, k, prefix=None, pattern=None, threads=1, want_rows=True):
-    words = np.ascontiguousarray(words, dtype=np.uint64)
-    stats = np.zeros(3, dtype=np.uint64)
-    digest = np.zeros(4, dtype=np.uint64)
-    pb, pl = (0, 0) if prefix is None else prefix
-    cap = n_seqs * max(0, bases_per_seq - k + 1) if want_rows else 0
-    kk = np.empty(cap + 1, dtype=np.uint64)
-    cc = np.empty(cap + 1, dtype=np.uint64)
-    n = u64()
-    _run(lib().dnaref_count, words.ctypes.data, n_seqs, bases_per_seq, stride, k, pb, pl,
-         None if pattern is None else pattern.encode("ascii", "replace"), threads, stats.ctypes.data,
-         digest.ctypes.data, kk.ctypes.data if want_rows else None, cc.ctypes.data if want_rows else None, cap,
-         C.byref(n))
-    st = [int(x) for x in stats]
-    return CountResult(st, digest, kk[:n.value].copy() if want_rows else None, cc[:n.value].copy() if want_rows else None)
+def _run(fn, *args):
+    buf = C.create_string_buffer(512)
+    rc = fn(*args, buf, 512)
+    if rc != 0:
+        raise PgError(buf.value.decode())
+
+
+class Module:
+    """One built module (the reference, or the reference + GPU glue) behind the executor-like driver."""
+
+    def __init__(self, so, target):
+        if not os.path.exists(so):
+            if not os.path.exists(REFERENCE_SRC):
+                raise FileNotFoundError(f"{so} is not built and /root/reference is absent")
+            subprocess.run(["make", "-C", _HERE, target], check=True, stdout=subprocess.DEVNULL)
+        L = C.CDLL(so)
+        err = [C.c_char_p, C.c_size_t]
+        sig = {
+            "dnaref_dna_in": (C.c_int, [C.c_char_p, vp, u64, C.POINTER(u64)] + err),
+            "dnaref_dna_out": (C.c_int, [vp, u64, C.c_char_p, C.c_size_t] + err),
+            "dnaref_kmer_in": (C.c_int, [C.c_char_p, C.POINTER(u64), C.POINTER(C.c_int32)] + err),
+            "dnaref_kmer_out": (C.c_int, [u64, C.c_int32, C.c_char_p, C.c_size_t] + err),
+            "dnaref_qkmer_in": (C.c_int, [C.c_char_p] + err),
+            "dnaref_starts_with": (C.c_int, [u64, C.c_int32, u64, C.c_int32, C.POINTER(C.c_int)] + err),
+            "dnaref_contains": (C.c_int, [C.c_char_p, u64, C.c_int32, C.POINTER(C.c_int)] + err),
+            "dnaref_kmer_hash": (C.c_uint32, [u64]),
+            "dnaref_kmer_eq": (C.c_int, [u64, C.c_int32, u64, C.c_int32]),
+            "dnaref_generate_kmers": (C.c_int, [vp, u64, C.c_int, u64, C.c_int32, C.c_char_p, vp, u64,
+                                                C.POINTER(u64)] + err),
+            "dnaref_count": (C.c_int, [vp, u64, u64, u64, C.c_int, u64, C.c_int32, C.c_char_p, C.c_int, vp, vp, vp, vp,
+                                       u64, C.POINTER(u64)] + err),
+        }
+        if hasattr(L, "dnaref_kmer_stats"):   # only the glue build has the pushdown functions
+            sig["dnaref_kmer_stats"] = (C.c_int, [vp, u64, C.c_int, vp] + err)
+            sig["dnaref_count_kmers"] = (C.c_int, [vp, u64, C.c_int, vp, vp, u64, C.POINTER(u64)] + err)
+        for name, (res, args) in sig.items():
+            fn = getattr(L, name)
+            fn.restype, fn.argtypes = res, args
+        self.L = L
+
+    def dna_in(self, text):
+        words = np.zeros(len(text) // 32 + 2, dtype=np.uint64)
+        n = u64()
+        _run(self.L.dnaref_dna_in, text.encode("ascii", "replace"), words.ctypes.data, words.size, C.byref(n))
+        return words[:(n.value + 31) // 32].copy(), n.value
+
+    def dna_out(self, words, n):
+        words = np.ascontiguousarray(words, dtype=np.uint64)
+        out = C.create_string_buffer(n + 1)
+        _run(self.L.dnaref_dna_out, words.ctypes.data, n, out, n + 1)
+        return out.value.decode()
+
+    def kmer_in(self, text):
+        bits, length = u64(), C.c_int32()
+        _run(self.L.dnaref_kmer_in, text.encode("ascii", "replace"), C.byref(bits), C.byref(length))
+        return bits.value, length.value
+
+    def kmer_out(self, bits, length):
+        out = C.create_string_buffer(40)
+        _run(self.L.dnaref_kmer_out, int(bits), length, out, 40)
+        return out.value.decode()
+
+    def qkmer_in(self, text):
+        _run(self.L.dnaref_qkmer_in, text.encode("ascii", "replace"))
+        return text
+
+    def starts_with(self, kbits, klen, pbits, plen):
+        r = C.c_int()
+        _run(self.L.dnaref_starts_with, int(kbits), klen, int(pbits), plen, C.byref(r))
+        return bool(r.value)
+
+    def contains(self, pattern, kbits, klen):
+        r = C.c_int()
+        _run(self.L.dnaref_contains, pattern.encode("ascii", "replace"), int(kbits), klen, C.byref(r))
+        return bool(r.value)
+
+    def kmer_hash(self, bits):
+        return int(self.L.dnaref_kmer_hash(int(bits)))
+
+    def kmer_eq(self, a, alen, b, blen):
+        return bool(self.L.dnaref_kmer_eq(int(a), alen, int(b), blen))
+
+    def generate_kmers(self, words, n_bases, k, prefix=None, pattern=None):
+        """SELECT * FROM generate_kmers(dna, k) AS g(kmer) [WHERE kmer ^@ prefix AND pattern @> kmer]."""
+        words = np.ascontiguousarray(words, dtype=np.uint64)
+        cap = max(0, n_bases - k + 1) if 1 <= k <= 32 else 0
+        out = np.empty(cap + 1, dtype=np.uint64)
+        n = u64()
+        pb, pl = (0, 0) if prefix is None else prefix
+        _run(self.L.dnaref_generate_kmers, words.ctypes.data, n_bases, k, pb, pl,
+             None if pattern is None else pattern.encode("ascii", "replace"), out.ctypes.data, out.size, C.byref(n))
+        return out[:n.value].copy()
+
+    def count(self, words, n_seqs, bases_per_seq, stride, k, prefix=None, pattern=None, threads=1, want_rows=True):
+        words = np.ascontiguousarray(words, dtype=np.uint64)
+        stats = np.zeros(3, dtype=np.uint64)
+        digest = np.zeros(4, dtype=np.uint64)
+        pb, pl = (0, 0) if prefix is None else prefix
+        cap = n_seqs * max(0, bases_per_seq - k + 1) if want_rows else 0
+        kk = np.empty(cap + 1, dtype=np.uint64)
+        cc = np.empty(cap + 1, dtype=np.uint64)
+        n = u64()
+        _run(self.L.dnaref_count, words.ctypes.data, n_seqs, bases_per_seq, stride, k, pb, pl,
+             None if pattern is None else pattern.encode("ascii", "replace"), threads, stats.ctypes.data,
+             digest.ctypes.data, kk.ctypes.data if want_rows else None, cc.ctypes.data if want_rows else None, cap,
+             C.byref(n))
+        st = [int(x) for x in stats]
+        return CountResult(st, digest, kk[:n.value].copy() if want_rows else None,
+                           cc[:n.value].copy() if want_rows else None)
+
+    # ---- the glue's pushdown functions (libdnaglue.so only) ----
+    def kmer_stats(self, words, n_bases, k):
+        """SELECT * FROM kmer_stats(dna, k) -> (total, distinct, uniq)."""
+        words = np.ascontiguousarray(words, dtype=np.uint64)
+        st = np.zeros(3, dtype=np.int64)
+        _run(self.L.dnaref_kmer_stats, words.ctypes.data, n_bases, k, st.ctypes.data)
+        return tuple(int(x) for x in st)
+
+    def count_kmers(self, words, n_bases, k):
+        """SELECT * FROM count_kmers(dna, k) -> (kmers, counts) sorted by kmer, plus the Kmer.length check."""
+        words = np.ascontiguousarray(words, dtype=np.uint64)
+        cap = max(0, n_bases - k + 1) if 1 <= k <= 32 else 0
+        kk = np.empty(cap + 1, dtype=np.uint64)
+        cc = np.empty(cap + 1, dtype=np.int64)
+        n = u64()
+        _run(self.L.dnaref_count_kmers, words.ctypes.data, n_bases, k, kk.ctypes.data, cc.ctypes.data, kk.size,
+             C.byref(n))
+        order = np.argsort(kk[:n.value], kind="stable")
+        return kk[:n.value][order], cc[:n.value][order]
+
+
+def reference():
+    """The reference's own module (libdnaref.so)."""
+    global _default
+    if _default is None:
+        _default = Module(SO, "ref")
+    return _default
+
+
+def glue():
+    """The reference's module with generate_kmers swapped for the GPU glue (libdnaglue.so; needs a GPU to call)."""
+    return Module(GLUE_SO, "glue")
+
+
+def lib():
+    return reference().L
+
+
+def _forward(name):
+    def f(*a, **kw):
+        return getattr(reference(), name)(*a, **kw)
+    f.__name__ = name
+    f.__doc__ = getattr(Module, name).__doc__
+    return f
+
+
+for _n in ("dna_in", "dna_out", "kmer_in", "kmer_out", "qkmer_in", "starts_with", "contains", "kmer_hash", "kmer_eq",
+           "generate_kmers", "count"):
+    globals()[_n] = _forward(_n)

@@ -435,6 +435,72 @@ def test_fused_owner_routing_composes_to_the_single_gpu_answer(gpu, k, prefix):
         assert np.array_equal(kk[order], oracle.kmers) and np.array_equal(cc[order], oracle.counts), (G, k)
 
 
+@pytest.mark.parametrize("k,prefix,pattern", [(31, None, None), (32, None, None), (21, "AC", None),
+                                              (12, None, "NNNNNNNNNNNN"), (31, "G", "S" + "N" * 30)])
+def test_scatter_to_destinations_composes_to_the_single_gpu_answer(gpu, k, prefix, pattern):
+    """dnagpu_shuffle_hist / _scatter_to (and, with a WHERE clause, dnagpu_collect + the _keys forms): the
+    exchange that stores straight into the owners' buffers, G ranks emulated on one device with local buffers
+    standing in for the peer-mapped ones (the layout arithmetic of distributed.count_sharded_peer)."""
+    import torch
+    from dnagpu.distributed import owner_digits, shard_of
+    n = 2_500_000
+    words = R.synth_seq(32, n)
+    oracle = R.count_query(words, 1, n, words.size, k, prefix=R.kmer_make(prefix) if prefix else None,
+                           pattern=pattern, faithful=False, threads=4)
+    where = dict(prefix=prefix, pattern=pattern)
+    for G in (1, 2, 5):
+        plan = gpu.shuffle_plan(n - k + 1, G)
+        seqs = [gpu.synth_range(n, 32, 8, *shard_of(n, k, G, r), k) for r in range(G)]
+        listed = [gpu.collect(s, k, **where) if (prefix or pattern) else None for s in seqs]
+        counts = np.stack([gpu.shuffle_hist_keys(l, plan) if l is not None else gpu.shuffle_hist(s, k, plan)
+                           for s, l in zip(seqs, listed)])
+        if prefix or pattern:                                   # the two histogram forms agree
+            assert np.array_equal(counts, np.stack([gpu.shuffle_hist(s, k, plan, **where) for s in seqs]))
+        ranges = [owner_digits(plan, r) for r in range(G)]
+        recv = [torch.full((int(counts[:, a:b].sum()) + 2,), -7, dtype=torch.int64, device="cuda") for a, b in ranges]
+        kept_all = side_all = 0
+        for r in range(G):
+            dest = np.zeros(plan.n_digits, dtype=np.uint64)
+            for o, (a, b) in enumerate(ranges):
+                block = counts[:, a:b]
+                within = np.concatenate([[0], np.cumsum(block[r])[:-1]]).astype(np.uint64) if b > a else np.zeros(0, np.uint64)
+                dest[a:b] = np.uint64(recv[o].data_ptr()) + np.uint64(8) * (np.uint64(int(block[:r].sum())) + within)
+            if listed[r] is not None:
+                kept, side = int(listed[r].numel()), gpu.shuffle_scatter_keys_to(listed[r], plan, dest)
+            else:
+                kept, side = gpu.shuffle_scatter_to(seqs[r], k, plan, dest)
+            kept_all += kept
+            side_all += side
+        assert kept_all == oracle.total
+        distinct = unique = 0
+        for o, (a, b) in enumerate(ranges):
+            assert int((recv[o][:-2] == -7).sum()) == 0 or k == 32   # every slot of the layout was written
+            st = gpu.shuffle_count_addr(recv[o].data_ptr(), counts[:, a:b].reshape(-1), b - a, plan, k)
+            distinct += st.distinct
+            unique += st.unique
+        assert (distinct + (side_all > 0), unique + (side_all == 1)) == (oracle.distinct, oracle.unique), (G, k)
+        for s in seqs:
+            s.free()
+
+
+def test_collect_keeps_the_rows_of_filter_in_any_order(gpu):
+    """dnagpu_collect == dnagpu_filter as a multiset; a short buffer reports the need."""
+    import torch
+    n, k = 1_000_003, 9
+    seq = gpu.synth(n, 41)
+    for where in (dict(prefix="ACG"), dict(pattern="NNWNNSNNN"), dict(prefix="T", pattern="NNNNNNNNN"), dict()):
+        a = gpu.filter(seq, k, **where).cpu().numpy()
+        b = gpu.collect(seq, k, **where).cpu().numpy()
+        assert np.array_equal(np.sort(a), np.sort(b))
+    out = torch.empty(16, dtype=torch.int64, device="cuda")
+    import ctypes
+    need = ctypes.c_uint64()
+    w, _keep = dnagpu._where("A", None)
+    rc = gpu.lib.dnagpu_collect(gpu.handle, seq.handle, k, ctypes.byref(w), out.data_ptr(), 16, ctypes.byref(need))
+    assert rc == 21 and need.value == gpu.filter_count(seq, k, prefix="A")
+    seq.free()
+
+
 def test_shards_with_overlap_cover_the_sequence_once(gpu):
     """Base-range shards with a (k-1)-base overlap (synth_range + start limit) reproduce the
     k-mers of the whole sequence exactly once."""

@@ -7,9 +7,27 @@ from conftest import PKG, ROOT
 
 
 def test_pg_glue_compiles_against_the_fmgr_api():
-    subprocess.run(["gcc", "-std=gnu11", "-Wall", "-Werror", "-fsyntax-only", "-DDNAGPU_GLUE_SHIM_SYNTAX_CHECK",
+    subprocess.run(["gcc", "-std=gnu11", "-Wall", "-Wextra", "-Werror", "-fsyntax-only",
                     "-I", os.path.join(ROOT, "oracle", "pgshim"), os.path.join(PKG, "pg", "dna_gpu.c")],
                    check=True)
+
+
+def test_reference_module_links_with_the_glue_in_place_of_generate_kmers():
+    """dna.c (generate_kmers renamed away, as pg/Makefile does) + pg/dna_gpu.c + libdnagpu link into one module
+    that exports the SQL-visible symbols; the scalar functions of the reference still answer through it.
+    (Calling the GPU entry points is tests/test_gpu_pg_glue.py.)"""
+    import pytest
+    from oracle import ref_real
+    if not ref_real.glue_available():
+        pytest.skip("oracle/_ref/libdnaglue.so not built and /root/reference absent")
+    glue = ref_real.glue()
+    out = subprocess.run(["nm", "-D", "--defined-only", ref_real.GLUE_SO], capture_output=True, text=True,
+                         check=True).stdout
+    for sym in ("generate_kmers", "generate_kmers_cpu", "kmer_stats", "count_kmers", "starts_with", "contains",
+                "kmer_hash", "kmer_eq", "dna_in", "kmer_in", "qkmer_in"):
+        assert f" T {sym}\n" in out, sym
+    assert glue.kmer_in("ACGT") == (0x78, 4)
+    assert glue.kmer_out(0xE4, 4) == "ATCG"
 
 
 def test_host_mirror_and_c_harness_build():
