@@ -21,6 +21,7 @@
 
 #include "kernels.cuh"
 #include "partition.cuh"
+#include "index.cuh"
 
 using namespace dnagpu;
 
@@ -67,6 +68,13 @@ struct dnagpu_table {
     int k = 0;
     uint64_t rows = 0;
     uint64_t *d_kmers = nullptr, *d_counts = nullptr;
+};
+
+struct dnagpu_index {
+    dnagpu_ctx *ctx = nullptr;
+    int k = 0;
+    uint64_t rows = 0;
+    uint64_t *d_skeys = nullptr, *d_rows = nullptr; /* sort keys ascending; the row each came from */
 };
 
 static thread_local char g_err[512] = "";
@@ -2187,6 +2195,209 @@ extern "C" int dnagpu_shuffle_scatter_keys_to(dnagpu_ctx *ctx, const uint64_t *d
     TRY(fetch_counters(ctx)); /* synchronises: every store of this rank has been issued and retired */
     if (side_rows) *side_rows = ctx->h_ctr[C_SIDE];
     return DNAGPU_OK;
+}
+
+/* ---- sorted k-mer index (the SP-GiST replacement) ------------------------------------------------ */
+/* Stable LSD radix sort of n (key, value) pairs over key bits [0, bits).  a* hold the input, b* are
+ * scratch of the same size; *in_a tells where the result is.  vals may be NULL (keys only). */
+static int radix_sort(dnagpu_ctx *ctx, Scratch &sc, uint64_t *ak, uint64_t *av, uint64_t *bk, uint64_t *bv, uint64_t n,
+                      int bits, bool *in_a)
+{
+    *in_a = true;
+    if (n < 2 || bits <= 0) return DNAGPU_OK;
+    const uint64_t chunks = (n + kSortChunk - 1) / kSortChunk;
+    const unsigned grid = (unsigned)std::min<uint64_t>(chunks, (uint64_t)ctx->sm_count * 4);
+    const uint64_t per_cta = (chunks + grid - 1) / grid * kSortChunk;
+    uint64_t *cnt, *off;
+    TRY(sc.get((void **)&cnt, 256ull * grid * 8));
+    TRY(sc.get((void **)&off, (256ull * grid + 1) * 8));
+    for (int shift = 0; shift < bits; shift += 8) {
+        const uint64_t *src_k = *in_a ? ak : bk, *src_v = *in_a ? av : bv;
+        uint64_t *dst_k = *in_a ? bk : ak, *dst_v = *in_a ? bv : av;
+        TRY(launch(ctx, "sort_hist", [&] { k_sort_hist<<<grid, kSortThreads, 0, ctx->stream>>>(src_k, n, per_cta, shift, cnt); }));
+        TRY(scan_any(ctx, sc, cnt, 256ull * grid, off));
+        TRY(launch(ctx, "sort_scatter", [&] {
+            if (av)
+                k_sort_scatter<true><<<grid, kSortThreads, 0, ctx->stream>>>(src_k, src_v, n, per_cta, shift, off, dst_k, dst_v);
+            else
+                k_sort_scatter<false><<<grid, kSortThreads, 0, ctx->stream>>>(src_k, nullptr, n, per_cta, shift, off, dst_k, nullptr);
+        }));
+        *in_a = !*in_a;
+    }
+    return DNAGPU_OK;
+}
+
+extern "C" int dnagpu_index_build(dnagpu_ctx *ctx, const uint64_t *d_keys, uint64_t n, int k, dnagpu_index **index)
+{
+    if (!ctx || !index || (n && !d_keys)) return fail(ctx, DNAGPU_EARG, "dnagpu_index_build: NULL argument");
+    *index = nullptr;
+    TRY(check_k(ctx, k));
+    CU(ctx, cudaSetDevice(ctx->device));
+    dnagpu_index *ix = new (std::nothrow) dnagpu_index;
+    if (!ix) return fail(ctx, DNAGPU_ENOMEM, "out of host memory");
+    ix->ctx = ctx;
+    ix->k = k;
+    ix->rows = n;
+    int rc = DNAGPU_OK;
+    uint64_t *tk = nullptr, *tv = nullptr;
+    {
+        Scratch sc(ctx);
+        rc = dalloc(ctx, (void **)&ix->d_skeys, (n + 2) * 8);
+        if (rc == DNAGPU_OK) rc = dalloc(ctx, (void **)&ix->d_rows, (n + 2) * 8);
+        if (rc == DNAGPU_OK && n) rc = dalloc(ctx, (void **)&tk, (n + 2) * 8);
+        if (rc == DNAGPU_OK && n) rc = dalloc(ctx, (void **)&tv, (n + 2) * 8);
+        if (rc == DNAGPU_OK && n) {
+            const unsigned grid = (unsigned)std::min<uint64_t>(grid_for(n, kThreads), (uint64_t)ctx->sm_count * 16);
+            rc = launch(ctx, "index_keys", [&] { k_index_keys<<<grid, kThreads, 0, ctx->stream>>>(d_keys, n, k, ix->d_skeys, ix->d_rows); });
+            bool in_a = true;
+            if (rc == DNAGPU_OK) rc = radix_sort(ctx, sc, ix->d_skeys, ix->d_rows, tk, tv, n, 2 * k, &in_a);
+            if (rc == DNAGPU_OK && !in_a) {
+                std::swap(ix->d_skeys, tk);
+                std::swap(ix->d_rows, tv);
+            }
+        }
+        if (rc == DNAGPU_OK && cudaStreamSynchronize(ctx->stream) != cudaSuccess)
+            rc = fail(ctx, DNAGPU_ECUDA, "index build: %s", cudaGetErrorString(cudaGetLastError()));
+    }
+    dfree(ctx, tk);
+    dfree(ctx, tv);
+    if (rc != DNAGPU_OK) {
+        dnagpu_index_free(ix);
+        return rc;
+    }
+    *index = ix;
+    return DNAGPU_OK;
+}
+
+extern "C" void dnagpu_index_free(dnagpu_index *ix)
+{
+    if (!ix) return;
+    if (ix->ctx) {
+        cudaSetDevice(ix->ctx->device);
+        dfree(ix->ctx, ix->d_skeys);
+        dfree(ix->ctx, ix->d_rows);
+    }
+    delete ix;
+}
+
+extern "C" uint64_t dnagpu_index_rows(const dnagpu_index *ix) { return ix ? ix->rows : 0; }
+extern "C" int dnagpu_index_k(const dnagpu_index *ix) { return ix ? ix->k : 0; }
+
+extern "C" int dnagpu_index_device(const dnagpu_index *ix, const uint64_t **d_sort_keys, const uint64_t **d_rows)
+{
+    if (!ix) return fail(nullptr, DNAGPU_EARG, "index is NULL");
+    if (d_sort_keys) *d_sort_keys = ix->d_skeys;
+    if (d_rows) *d_rows = ix->d_rows;
+    return DNAGPU_OK;
+}
+
+/* positions [beg, end) of the sorted column whose sort key lies in [lo, hi] */
+static int index_bounds(dnagpu_ctx *ctx, const dnagpu_index *ix, uint64_t lo, uint64_t hi, uint64_t *beg, uint64_t *end)
+{
+    uint64_t *d_out = (uint64_t *)(ctx->d_ctr + C_COUNT); /* two spare counters */
+    TRY(launch(ctx, "index_bounds", [&] { k_index_bounds<<<1, 32, 0, ctx->stream>>>(ix->d_skeys, ix->rows, lo, hi, d_out); }));
+    CU(ctx, cudaMemcpyAsync(ctx->h_ctr, d_out, 16, cudaMemcpyDeviceToHost, ctx->stream));
+    CU(ctx, cudaStreamSynchronize(ctx->stream));
+    *beg = ctx->h_ctr[0];
+    *end = ctx->h_ctr[1];
+    return DNAGPU_OK;
+}
+
+/* hand out `n` row numbers (device, unordered unless `ordered`) in ascending order, like a bitmap heap scan */
+static int index_emit(dnagpu_ctx *ctx, const dnagpu_index *ix, uint64_t *d_found, uint64_t n, bool ordered,
+                      uint64_t *d_rows, uint64_t cap, uint64_t *n_out)
+{
+    *n_out = n;
+    if (!d_rows || n == 0) return DNAGPU_OK;
+    if (cap < n) return fail(ctx, DNAGPU_ECAPACITY, "index search needs room for %llu rows", (unsigned long long)n);
+    if (ordered || n == 1) {
+        CU(ctx, cudaMemcpyAsync(d_rows, d_found, n * 8, cudaMemcpyDeviceToDevice, ctx->stream));
+    } else {
+        Scratch sc(ctx);
+        uint64_t *a, *b;
+        TRY(sc.get((void **)&a, (n + 2) * 8));
+        TRY(sc.get((void **)&b, (n + 2) * 8));
+        CU(ctx, cudaMemcpyAsync(a, d_found, n * 8, cudaMemcpyDeviceToDevice, ctx->stream));
+        bool in_a = true;
+        TRY(radix_sort(ctx, sc, a, nullptr, b, nullptr, n, ceil_log2(std::max<uint64_t>(ix->rows, 2)), &in_a));
+        CU(ctx, cudaMemcpyAsync(d_rows, in_a ? a : b, n * 8, cudaMemcpyDeviceToDevice, ctx->stream));
+    }
+    CU(ctx, cudaStreamSynchronize(ctx->stream));
+    return DNAGPU_OK;
+}
+
+extern "C" int dnagpu_index_equal(dnagpu_ctx *ctx, const dnagpu_index *ix, uint64_t kmer_bits, int kmer_len,
+                                  uint64_t *d_rows, uint64_t cap, uint64_t *n_out)
+{
+    if (!ctx || !ix || !n_out) return fail(ctx, DNAGPU_EARG, "dnagpu_index_equal: NULL argument");
+    CU(ctx, cudaSetDevice(ctx->device));
+    *n_out = 0;
+    /* kmer_eq compares the lengths first (dna.c:655-668): a k-mer of another length equals no row */
+    if (ix->rows == 0 || kmer_len != ix->k || (kmer_bits & ~kmer_mask(ix->k))) return DNAGPU_OK;
+    const uint64_t s = sort_key_of(kmer_bits, ix->k);
+    uint64_t beg, end;
+    TRY(index_bounds(ctx, ix, s, s, &beg, &end));
+    /* rows of one key are in input order: the sort is stable */
+    return index_emit(ctx, ix, ix->d_rows + beg, end - beg, true, d_rows, cap, n_out);
+}
+
+extern "C" int dnagpu_index_search(dnagpu_ctx *ctx, const dnagpu_index *ix, const dnagpu_where *where, uint64_t *d_rows,
+                                   uint64_t cap, uint64_t *n_out)
+{
+    if (!ctx || !ix || !n_out) return fail(ctx, DNAGPU_EARG, "dnagpu_index_search: NULL argument");
+    CU(ctx, cudaSetDevice(ctx->device));
+    *n_out = 0;
+    TRY(check_filter_literals(ctx, where));
+    const int k = ix->k;
+    Pred p;
+    bool active = false;
+    TRY(build_pred(ctx, where, k, ix->rows, &p, &active)); /* the reference's length errors, raised when a row exists */
+    if (ix->rows == 0) return DNAGPU_OK;
+    /* the leading positions that allow exactly one base select one range of the sorted column */
+    uint64_t lead = 0;
+    int n_lead = 0;
+    bool rest = false; /* constraints after the leading run */
+    if (active) {
+        const uint64_t plane[4] = {p.ma, p.mt, p.mc, p.mg};
+        bool leading = true;
+        for (int j = 0; j < k; ++j) {
+            int set = 0;
+            for (int b = 0; b < 4; ++b) set |= (int)((plane[b] >> (2 * j)) & 1) << b;
+            if (set == 0) return DNAGPU_OK; /* a position nothing can match (e.g. 'U', dna.c:1064-1086) */
+            const bool one = (set & (set - 1)) == 0;
+            if (leading && one) {
+                const int base = set == 1 ? 0 : set == 2 ? 1 : set == 4 ? 2 : 3;
+                lead = (lead << 2) | (uint64_t)base;
+                ++n_lead;
+            } else {
+                leading = false;
+                if (set != 15) rest = true;
+            }
+        }
+    }
+    const int free_bits = 2 * (k - n_lead);
+    const uint64_t lo = free_bits >= 64 ? 0 : lead << free_bits;
+    const uint64_t hi = free_bits >= 64 ? ~0ull : lo | (free_bits ? ((1ull << free_bits) - 1) : 0);
+    uint64_t beg = 0, end = ix->rows;
+    if (n_lead) TRY(index_bounds(ctx, ix, lo, hi, &beg, &end));
+    if (end == beg) return DNAGPU_OK;
+    if (!rest) return index_emit(ctx, ix, ix->d_rows + beg, end - beg, n_lead == k, d_rows, cap, n_out);
+    /* remaining positions: evaluate the predicate on the range only */
+    Scratch sc(ctx);
+    uint64_t found_cap = d_rows ? std::min<uint64_t>(end - beg, std::max<uint64_t>(cap, 1)) : 0, *found = nullptr, n_found = 0;
+    TRY(sc.get((void **)&found, (found_cap + 2) * 8));
+    TRY(zero_counters(ctx));
+    const unsigned grid = (unsigned)std::min<uint64_t>(grid_for(end - beg, kThreads), (uint64_t)ctx->sm_count * 16);
+    TRY(launch(ctx, "index_match", [&] {
+        k_index_match<<<grid, kThreads, 0, ctx->stream>>>(ix->d_skeys, ix->d_rows, beg, end, k, p, found_cap,
+                                                        ctx->d_ctr + C_CURSOR, found);
+    }));
+    TRY(read_u64(ctx, (const uint64_t *)(ctx->d_ctr + C_CURSOR), &n_found));
+    if (d_rows && n_found > found_cap) {
+        *n_out = n_found;
+        return fail(ctx, DNAGPU_ECAPACITY, "index search needs room for %llu rows", (unsigned long long)n_found);
+    }
+    return index_emit(ctx, ix, found, n_found, false, d_rows, cap, n_out);
 }
 
 /* ---- profiling --------------------------------------------------------------------------------- */

@@ -146,6 +146,74 @@ class Table:
             pass
 
 
+class Index:
+    """Sorted k-mer index over a stored kmer column (dnagpu_index_*): the SP-GiST replacement."""
+
+    def __init__(self, ctx, handle):
+        self.ctx, self.handle = ctx, handle
+
+    @property
+    def rows(self):
+        return int(self.ctx.lib.dnagpu_index_rows(self.handle))
+
+    @property
+    def k(self):
+        return int(self.ctx.lib.dnagpu_index_k(self.handle))
+
+    def _rows_of(self, call):
+        """Run a search: count first, then fetch into an exactly sized torch int64 CUDA tensor."""
+        import torch
+        n = C.c_uint64()
+        self.ctx._ok(call(None, 0, C.byref(n)))
+        out = torch.empty(max(int(n.value), 1), dtype=torch.int64, device=f"cuda:{self.ctx.device}")
+        if n.value:
+            self.ctx._ok(call(out.data_ptr(), out.numel(), C.byref(n)))
+        return out[:n.value]
+
+    def equal(self, kmer):
+        """WHERE kmer_sequence = kmer -> row numbers, ascending."""
+        kmer = Kmer(kmer)
+        return self._rows_of(lambda p, cap, n: self.ctx.lib.dnagpu_index_equal(self.ctx.handle, self.handle, kmer.bits,
+                                                                               kmer.length, p, cap, n))
+
+    def search(self, prefix=None, pattern=None):
+        """WHERE kmer_sequence ^@ prefix AND pattern @> kmer_sequence -> row numbers, ascending."""
+        w, _keep = _where(prefix, pattern)
+        wp = C.byref(w) if w is not None else None
+        return self._rows_of(lambda p, cap, n: self.ctx.lib.dnagpu_index_search(self.ctx.handle, self.handle, wp, p, cap, n))
+
+    def sorted_column(self):
+        """(sort keys ascending, row of each entry) as torch int64 CUDA tensors viewing the index's memory."""
+        import torch
+        a, b = C.c_void_p(), C.c_void_p()
+        self.ctx._ok(self.ctx.lib.dnagpu_index_device(self.handle, C.byref(a), C.byref(b)))
+        n = self.rows
+        if n == 0:
+            e = torch.empty(0, dtype=torch.int64, device=f"cuda:{self.ctx.device}")
+            return e, e.clone()
+        return _device_view(a.value, n, self.ctx.device), _device_view(b.value, n, self.ctx.device)
+
+    def free(self):
+        if self.handle:
+            self.ctx.lib.dnagpu_index_free(self.handle)
+            self.handle = None
+
+    def __del__(self):
+        try:
+            self.free()
+        except Exception:  # noqa: BLE001 - interpreter shutdown
+            pass
+
+
+def _device_view(addr, n, device):
+    """A torch int64 tensor over n u64 at a raw device address (no ownership)."""
+    import torch
+
+    class _Iface:
+        __cuda_array_interface__ = {"shape": (int(n),), "typestr": "<i8", "data": (int(addr), False), "version": 3}
+    return torch.as_tensor(_Iface(), device=f"cuda:{device}")
+
+
 class Context:
     """One GPU, one stream (dnagpu_ctx).  `torch_stream=True` issues the library's
     work on torch's current stream so torch tensors can be passed in and out."""
@@ -376,6 +444,12 @@ class Context:
                 return out[:n.value]
             guess = n.value
         self._ok(rc)
+
+    def index_build(self, keys, k):
+        """CREATE INDEX ... ON column(kmer): keys = torch int64 CUDA tensor of Kmer.bit_sequence, all of length k."""
+        h = C.c_void_p()
+        self._ok(self.lib.dnagpu_index_build(self.handle, keys.data_ptr(), keys.numel(), k, C.byref(h)))
+        return Index(self, h)
 
     # ---- GROUP BY kmer ------------------------------------------------------------------
     @staticmethod

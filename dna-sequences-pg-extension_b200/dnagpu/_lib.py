@@ -98,6 +98,13 @@ SIGNATURES = {
                                             u64p]),
     "dnagpu_shuffle_hist_keys": (C.c_int, [vp, vp, u64, C.POINTER(ShufflePlan), u64p]),
     "dnagpu_shuffle_scatter_keys_to": (C.c_int, [vp, vp, u64, C.POINTER(ShufflePlan), u64p, u64p]),
+    "dnagpu_index_build": (C.c_int, [vp, vp, u64, C.c_int, C.POINTER(vp)]),
+    "dnagpu_index_rows": (u64, [vp]),
+    "dnagpu_index_k": (C.c_int, [vp]),
+    "dnagpu_index_device": (C.c_int, [vp, C.POINTER(vp), C.POINTER(vp)]),
+    "dnagpu_index_equal": (C.c_int, [vp, vp, u64, C.c_int, vp, u64, u64p]),
+    "dnagpu_index_search": (C.c_int, [vp, vp, C.POINTER(Where), vp, u64, u64p]),
+    "dnagpu_index_free": (None, [vp]),
     "dnagpu_profile_enable": (C.c_int, [vp, C.c_int]),
     "dnagpu_profile_reset": (C.c_int, [vp]),
     "dnagpu_profile_query": (C.c_int, [vp, C.c_char_p, C.POINTER(C.c_double), u64p]),

@@ -330,6 +330,30 @@ int dnagpu_shuffle_scatter_keys_to(dnagpu_ctx *ctx, const uint64_t *d_keys, uint
                                    const dnagpu_shuffle_plan *plan, const uint64_t *digit_dest,
                                    uint64_t *side_rows);
 
+/* ---- index over a stored kmer column -------------------------------------------
+ * Replaces the reference's SP-GiST operator class (spgist_kmer_ops: config / choose /
+ * picksplit / inner_consistent / leaf_consistent, dna.c:1137-1737, dna--1.0.sql:278-330)
+ * for the queries it serves (test.sql:186-262):  kmer = x,  kmer ^@ prefix,  qkmer @> kmer.
+ * The index is the column sorted by base string (base 0 most significant) with the row
+ * number of every entry; a prefix is one contiguous range.  Searches return 0-based row
+ * numbers of the indexed column in ascending order (the order of a bitmap heap scan) and,
+ * unlike the reference's trie (1021 of 1025 rows, test.sql:186-214), exactly the rows a
+ * sequential scan returns.  d_rows may be NULL: then only the number of rows is computed;
+ * too small a buffer gives DNAGPU_ECAPACITY with *n_out = the number needed. */
+typedef struct dnagpu_index dnagpu_index;
+int dnagpu_index_build(dnagpu_ctx *ctx, const uint64_t *d_keys, uint64_t n, int k, dnagpu_index **index);
+uint64_t dnagpu_index_rows(const dnagpu_index *index);
+int dnagpu_index_k(const dnagpu_index *index);
+/* the sorted column (sort keys: the 2-bit groups of Kmer.bit_sequence in reverse order) and the rows */
+int dnagpu_index_device(const dnagpu_index *index, const uint64_t **d_sort_keys, const uint64_t **d_rows);
+/* WHERE kmer = x: kmer_eq compares the lengths too (dna.c:655-668) */
+int dnagpu_index_equal(dnagpu_ctx *ctx, const dnagpu_index *index, uint64_t kmer_bits, int kmer_len,
+                       uint64_t *d_rows, uint64_t cap, uint64_t *n_out);
+/* WHERE kmer ^@ prefix AND qkmer @> kmer (either may be absent); same errors as dnagpu_filter_keys */
+int dnagpu_index_search(dnagpu_ctx *ctx, const dnagpu_index *index, const dnagpu_where *where,
+                        uint64_t *d_rows, uint64_t cap, uint64_t *n_out);
+void dnagpu_index_free(dnagpu_index *index);
+
 /* ---- per-kernel device timing (CUDA events on the ctx stream) --------------- */
 int dnagpu_profile_enable(dnagpu_ctx *ctx, int on);
 int dnagpu_profile_reset(dnagpu_ctx *ctx);
