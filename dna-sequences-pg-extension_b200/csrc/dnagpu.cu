@@ -37,6 +37,7 @@ struct dnagpu_ctx {
     cudaStream_t stream = nullptr;
     bool own_stream = true;
     unsigned long long *d_ctr = nullptr; /* C_COUNT + kMaxParts*2 u64 device counters */
+    int bins_ctas_per_sm = 4;            /* resident CTAs of k_count_buckets_bins (occupancy query) */
     unsigned long long *h_ctr = nullptr; /* pinned mirror */
     cudaStream_t copy_stream = nullptr; /* H2D of the host-buffer calls, overlapped with level 1 */
     bool profiling = false;
@@ -286,6 +287,12 @@ extern "C" int dnagpu_create(dnagpu_ctx **out, int device)
         }
         PSMEM_ATTR(k_part_scatter_keys<true>);
 #undef PSMEM_ATTR
+        {
+            int per_sm = 0;
+            if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_count_buckets_bins, kThreads, 0) == cudaSuccess &&
+                per_sm > 0)
+                ctx->bins_ctas_per_sm = per_sm;
+        }
         const int bsmem = kBucketSlots * 12;
         cudaFuncSetAttribute(k_count_buckets<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, bsmem);
         cudaFuncSetAttribute(k_count_buckets<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, bsmem);
@@ -1417,10 +1424,27 @@ static int part_finish(dnagpu_ctx *ctx, Scratch &sc, const uint64_t *keys, uint6
     }));
     const int bsmem = kBucketSlots * 12;
     const unsigned cgrid = (unsigned)std::min<uint64_t>(n_buckets, (uint64_t)ctx->sm_count * (16384 / kBucketSlots));
-    TRY(launch(ctx, "count_buckets", [&] {
-        k_count_buckets<false><<<cgrid, kThreads, bsmem, ctx->stream>>>(bucket_keys, bucket_off, bucket_end, n_buckets,
-                                                                       spill, spill_cap, ctx->d_ctr, nullptr, nullptr);
-    }));
+    /* the aggregates: bin / place / compare for every bucket that fits, the table kernel for the rest */
+    static const bool use_bins = !getenv("DNAGPU_NO_BINS");
+    if (use_bins) {
+        uint32_t *passed;
+        TRY(sc.get((void **)&passed, n_buckets * 4 + 16));
+        const unsigned bgrid = (unsigned)std::min<uint64_t>(n_buckets, (uint64_t)ctx->sm_count * ctx->bins_ctas_per_sm);
+        TRY(launch(ctx, "count_buckets", [&] {
+            k_count_buckets_bins<<<bgrid, kThreads, 0, ctx->stream>>>(bucket_keys, bucket_off, bucket_end, n_buckets,
+                                                                     ctx->d_ctr, passed, ctx->d_ctr + C_PASSED);
+        }));
+        TRY(launch(ctx, "count_buckets_passed", [&] {
+            k_count_buckets<false><<<cgrid, kThreads, bsmem, ctx->stream>>>(bucket_keys, bucket_off, bucket_end, n_buckets,
+                                                                           spill, spill_cap, ctx->d_ctr, nullptr, nullptr,
+                                                                           passed, ctx->d_ctr + C_PASSED);
+        }));
+    } else {
+        TRY(launch(ctx, "count_buckets", [&] {
+            k_count_buckets<false><<<cgrid, kThreads, bsmem, ctx->stream>>>(bucket_keys, bucket_off, bucket_end, n_buckets,
+                                                                           spill, spill_cap, ctx->d_ctr, nullptr, nullptr);
+        }));
+    }
     TRY(fetch_counters(ctx));
 #ifdef DNAGPU_PHASE_TIMING
     fprintf(stderr, "count_buckets phases (cycles/bucket, thread 0): init %.0f | sync %.0f | insert %.0f | prefetch+sync %.0f | buckets %llu\n",

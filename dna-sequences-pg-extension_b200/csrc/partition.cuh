@@ -457,8 +457,12 @@ __global__ void __launch_bounds__(kThreads) k_count_buckets(const uint64_t *__re
                                                             uint64_t spill_cap,
                                                             unsigned long long *__restrict__ ctr,
                                                             uint64_t *__restrict__ out_kmers,
-                                                            uint64_t *__restrict__ out_counts)
+                                                            uint64_t *__restrict__ out_counts,
+                                                            const uint32_t *__restrict__ list = nullptr,
+                                                            const unsigned long long *__restrict__ list_n = nullptr)
 {
+    /* with a list: only the buckets list[0 .. *list_n) (the ones k_count_buckets_bins passed on) */
+    if (list) n_buckets = *list_n;
     extern __shared__ __align__(16) unsigned char smem_raw[];
     unsigned long long *tk = reinterpret_cast<unsigned long long *>(smem_raw);                /* keys   */
     uint32_t *tc = reinterpret_cast<uint32_t *>(smem_raw + sizeof(uint64_t) * kBucketSlots); /* extras */
@@ -469,8 +473,9 @@ __global__ void __launch_bounds__(kThreads) k_count_buckets(const uint64_t *__re
     uint64_t beg = 0, end = 0;
     uint64_t pre[kPre];
     if (b < n_buckets) {
-        beg = bucket_off[b];
-        end = bucket_end[b];
+        const uint64_t id = list ? list[b] : b;
+        beg = bucket_off[id];
+        end = bucket_end[id];
 #pragma unroll
         for (int u = 0; u < kPre; ++u) {
             uint64_t i = beg + (uint64_t)u * kThreads + threadIdx.x;
@@ -488,8 +493,9 @@ __global__ void __launch_bounds__(kThreads) k_count_buckets(const uint64_t *__re
         const uint64_t nb = b + gridDim.x;
         uint64_t nbeg = 0, nend = 0;
         if (nb < n_buckets) {
-            nbeg = bucket_off[nb];
-            nend = bucket_end[nb];
+            const uint64_t id = list ? list[nb] : nb;
+            nbeg = bucket_off[id];
+            nend = bucket_end[id];
         }
         { /* 48 KB of 16-byte stores */
             ulonglong2 *k2 = reinterpret_cast<ulonglong2 *>(tk);
@@ -615,6 +621,187 @@ __global__ void __launch_bounds__(kThreads) k_count_buckets(const uint64_t *__re
     }
     ty.total = 0; /* totals were taken by the scatter pass */
     tally_flush(ty, ctr);
+}
+
+/* ---- bucket count without a hash table: bin, place, compare -------------------------------------
+ * The aggregates (distinct, unique) of a bucket need no table.  The bucket's keys are spread over
+ * kBins sub-bins by an independent hash with a RETURNING shared-memory add (11.6 lane-ops/clk/SM
+ * against 3.1 for the 64-bit CAS of the table, profiles/r01e_microbench); the value returned is the
+ * key's rank r inside its bin.  Each warp scans the counts of its own bins with shuffles, the keys
+ * are placed bin by bin into a staging area, and a key of rank r > 0 (one in six with 4096 bins) is
+ * compared with the r keys placed before it in its bin:
+ *     e = earlier keys equal to mine;  distinct += (e == 0);  second += (e == 1);
+ *     unique = distinct - second  (a key is unique iff it has no second occurrence).
+ * No probe chains, no 48 KB table to clear, three barriers per bucket.
+ * A bucket this cannot hold -- more than kBinCap keys, a warp's region overflowing, or a bin with
+ * more than kBinHeavy keys (a k-mer with many copies) -- is appended to `list` and counted by the
+ * table kernel afterwards (k_count_buckets with the list). */
+constexpr int kBins = 2048;
+constexpr int kBinPer = 12;                      /* keys per thread held in registers            */
+constexpr int kBinCap = kBinPer * kThreads;      /* 3072 keys staged per bucket                  */
+constexpr int kBinWarpCap = kBinCap / (kThreads / 32); /* staging slots of the bins of one warp  */
+constexpr int kBinHeavy = 15;                    /* rank fits 4 bits, position 12 bits           */
+static_assert(kBins == 8 * kThreads && kBinCap <= 4096, "packing of k_count_buckets_bins");
+
+__device__ __forceinline__ uint32_t bin_of(uint64_t x)
+{
+    return (((uint32_t)x ^ (uint32_t)(x >> 32)) * 0x9E3779B1u) >> 21;
+}
+
+/* phases A and C for a bucket of at most ROWS x kThreads keys: straight-line code, the lanes past the end of
+ * the bucket work on their dummy entries */
+template <int ROWS>
+__device__ __forceinline__ void bins_rank(const uint64_t (&x)[kBinPer], uint32_t (&f)[kBinPer / 2], uint32_t n,
+                                          uint32_t tid, uint32_t lane, uint32_t *cnt)
+{
+#pragma unroll
+    for (int u = 0; u < ROWS; ++u) {
+        const uint32_t bin = u * kThreads + tid < n ? bin_of(x[u]) : kBins + lane;
+        const uint32_t v = bin | (atomicAdd(&cnt[bin], 1u) << 12);
+        f[u >> 1] = (u & 1) ? __byte_perm(f[u >> 1], v, 0x5410) : v;
+    }
+}
+
+template <int ROWS>
+__device__ __forceinline__ void bins_place(const uint64_t (&x)[kBinPer], const uint32_t (&f)[kBinPer / 2],
+                                           const uint16_t *st, uint64_t *stage, uint8_t *rank_at)
+{
+#pragma unroll
+    for (int u = 0; u < ROWS; ++u) {
+        const uint32_t v = (u & 1) ? (f[u >> 1] >> 16) : (f[u >> 1] & 0xffffu);
+        const uint32_t bin = v & 0xfffu;
+        const uint32_t pos = st[bin] + (bin < kBins ? v >> 12 : 0u);
+        stage[pos] = x[u];
+        rank_at[pos] = (uint8_t)(v >> 12);
+    }
+}
+
+#define BINS_DISPATCH(n, CALL)                                   \
+    do {                                                         \
+        if ((n) <= 4 * kThreads) { constexpr int ROWS = 4; CALL; } \
+        else if ((n) <= 6 * kThreads) { constexpr int ROWS = 6; CALL; } \
+        else if ((n) <= 8 * kThreads) { constexpr int ROWS = 8; CALL; } \
+        else { constexpr int ROWS = kBinPer; CALL; }               \
+    } while (0)
+
+__global__ void __launch_bounds__(kThreads, 4) k_count_buckets_bins(const uint64_t *__restrict__ keys,
+                                                                    const uint64_t *__restrict__ bucket_off,
+                                                                    const uint64_t *__restrict__ bucket_end,
+                                                                    uint64_t n_buckets,
+                                                                    unsigned long long *__restrict__ ctr,
+                                                                    uint32_t *__restrict__ list,
+                                                                    unsigned long long *__restrict__ list_n)
+{
+    /* every array ends in 32 dummy entries, one per lane: the lanes past the end of a bucket's last row
+     * work on those instead of branching around the atomics and the stores */
+    __shared__ __align__(16) uint64_t stage[kBinCap + 32];
+    __shared__ __align__(16) uint32_t cnt[kBins + 32];
+    __shared__ __align__(16) uint16_t st[kBins + 32];       /* start of the bin in `stage` */
+    __shared__ __align__(16) uint8_t rank_at[kBinCap + 32]; /* rank of the key at a stage position inside its bin */
+    const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    uint32_t repeats = 0, second = 0; /* keys with >= 1 / exactly 1 equal key before them in their bin */
+    unsigned long long placed = 0;    /* thread 0: keys of the buckets counted here */
+    for (int i = tid; i < kBins + 32; i += kThreads) cnt[i] = 0;
+    if (tid < 32) st[kBins + tid] = (uint16_t)(kBinCap + tid);
+    uint64_t b = blockIdx.x;
+    uint32_t n = 0;
+    uint64_t x[kBinPer];
+#pragma unroll
+    for (int u = 0; u < kBinPer; ++u) x[u] = 0;
+    if (b < n_buckets) {
+        const uint64_t beg = bucket_off[b];
+        n = (uint32_t)min(bucket_end[b] - beg, (uint64_t)kBinCap + 1);
+        if (n <= kBinCap) {
+            const uint64_t *src = keys + beg + tid;
+#pragma unroll
+            for (int u = 0; u < kBinPer; ++u)
+                if (u * kThreads + tid < n) x[u] = ld_nc(src + u * kThreads);
+        }
+    }
+    __syncthreads();
+    while (b < n_buckets) {
+        const uint64_t nb = b + gridDim.x;
+        uint64_t nbeg = 0;
+        uint32_t nn = 0;
+        if (nb < n_buckets) {
+            nbeg = bucket_off[nb];
+            nn = (uint32_t)min(bucket_end[nb] - nbeg, (uint64_t)kBinCap + 1);
+        }
+        bool pass_on = n > kBinCap; /* uniform */
+        uint32_t wtotal = 0;        /* keys in the bins of this warp */
+        if (!pass_on) {
+            uint32_t f[kBinPer / 2]; /* two 16-bit fields per register: rank (4 bits, on top) and bin (12 bits) */
+            /* A: rank of every key inside its bin */
+            BINS_DISPATCH(n, bins_rank<ROWS>(x, f, n, tid, lane, cnt));
+            __syncthreads();
+            /* B: the owner of 8 consecutive bins reads their counts and clears them; warp scan -> starts */
+            const uint4 c0 = *reinterpret_cast<const uint4 *>(&cnt[8 * tid]);
+            const uint4 c1 = *reinterpret_cast<const uint4 *>(&cnt[8 * tid + 4]);
+            *reinterpret_cast<uint4 *>(&cnt[8 * tid]) = make_uint4(0, 0, 0, 0);
+            *reinterpret_cast<uint4 *>(&cnt[8 * tid + 4]) = make_uint4(0, 0, 0, 0);
+            const uint32_t s1 = c0.x, s2 = s1 + c0.y, s3 = s2 + c0.z, s4 = s3 + c0.w, s5 = s4 + c1.x, s6 = s5 + c1.y,
+                           s7 = s6 + c1.z, mine = s7 + c1.w;
+            const uint32_t worst = max(max(max(c0.x, c0.y), max(c0.z, c0.w)), max(max(c1.x, c1.y), max(c1.z, c1.w)));
+            uint32_t inc = mine;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const uint32_t y = __shfl_up_sync(0xffffffffu, inc, o);
+                if (lane >= o) inc += y;
+            }
+            wtotal = __shfl_sync(0xffffffffu, inc, 31);
+            const bool bad = wtotal > (uint32_t)kBinWarpCap || worst > (uint32_t)kBinHeavy;
+            const uint32_t p = warp * kBinWarpCap + inc - mine;
+            /* (harmless when bad: the bucket is passed on and st is not read) */
+            *reinterpret_cast<uint4 *>(&st[8 * tid]) =
+                make_uint4(p | ((p + s1) << 16), (p + s2) | ((p + s3) << 16), (p + s4) | ((p + s5) << 16),
+                           (p + s6) | ((p + s7) << 16));
+            pass_on = __syncthreads_or(bad);
+            if (!pass_on) {
+                /* C: place, and leave the rank beside the key */
+                BINS_DISPATCH(n, bins_place<ROWS>(x, f, st, stage, rank_at));
+                if (tid == 0) placed += n;
+            }
+        }
+        /* the next bucket's keys fly during the compare phase */
+        if (nn <= kBinCap) {
+            const uint64_t *src = keys + nbeg + tid;
+#pragma unroll
+            for (int u = 0; u < kBinPer; ++u)
+                if (u * kThreads + tid < nn) x[u] = ld_nc(src + u * kThreads);
+        }
+        if (n <= kBinCap) { /* uniform: the barriers above were taken */
+            __syncthreads();
+            if (!pass_on) {
+                /* D: a key of rank r against the r keys placed before it in its bin.  A warp walks the
+                 * region of its own bins: ranks > 0 are one in four, their loops one or two steps. */
+                const uint32_t base = warp * kBinWarpCap;
+                for (uint32_t q = base + lane; q < base + wtotal; q += 32) {
+                    const uint32_t r = rank_at[q];
+                    if (r) {
+                        const uint64_t key = stage[q];
+                        uint32_t e = 0;
+                        for (uint32_t j = 1; j <= r; ++j) e += stage[q - j] == key;
+                        repeats += e >= 1;
+                        second += e == 1;
+                    }
+                }
+            }
+        }
+        if (pass_on && tid == 0) list[atomicAdd(list_n, 1ull)] = (uint32_t)b;
+        b = nb;
+        n = nn;
+    }
+    /* distinct = keys - repeats; unique = distinct - second (a key is unique iff it has no second occurrence) */
+    repeats = warp_sum32(repeats);
+    second = warp_sum32(second);
+    if (lane == 0 && (repeats | second)) {
+        atomicAdd(&ctr[C_DISTINCT], (unsigned long long)(-(long long)repeats));
+        atomicAdd(&ctr[C_UNIQUE], (unsigned long long)(-(long long)repeats - (long long)second));
+    }
+    if (tid == 0 && placed) {
+        atomicAdd(&ctr[C_DISTINCT], placed);
+        atomicAdd(&ctr[C_UNIQUE], placed);
+    }
 }
 
 /* ---- multi-CTA exclusive scan (bucket offsets: up to 4 M entries) ------------------------------ */

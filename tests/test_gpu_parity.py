@@ -255,6 +255,29 @@ def test_count_partition_skewed_input_spills_correctly(gpu):
     seq.free()
 
 
+def test_count_partition_every_multiplicity_around_the_bin_limits(gpu):
+    """The bin / place / compare bucket count holds up to 16 copies of a key in a bin and passes buckets with more
+    (or with more keys than its staging area) on to the table kernel: multiplicities on both sides of the limits,
+    mixed into ordinary keys, must give the exact aggregates and rows."""
+    import torch
+    rng = np.random.default_rng(21)
+    k = 31
+    parts = [rng.integers(0, 2**62, size=2_600_000, dtype=np.uint64)]
+    for copies, n_keys in ((2, 200_000), (3, 50_000), (7, 20_000), (15, 5_000), (16, 5_000), (17, 5_000), (18, 2_000),
+                           (40, 2_000), (300, 300), (2000, 40), (3072, 3), (3073, 3), (5000, 5)):
+        parts.append(np.repeat(rng.integers(0, 2**62, size=n_keys, dtype=np.uint64), copies))
+    keys = np.concatenate(parts)
+    rng.shuffle(keys)
+    dev = torch.from_numpy(keys.view(np.int64)).cuda()
+    uk, uc = np.unique(keys, return_counts=True)
+    st, table = gpu.count_keys(dev, k, table=True, method=dnagpu.COUNT_PARTITION)
+    assert (st.total, st.distinct, st.unique) == (keys.size, uk.size, int((uc == 1).sum()))
+    kk, cc = table.sorted()
+    assert np.array_equal(kk, uk) and np.array_equal(cc, uc.astype(np.uint64))
+    st, _ = gpu.count_keys(dev, k, method=dnagpu.COUNT_PARTITION)      # aggregates only
+    assert (st.total, st.distinct, st.unique) == (keys.size, uk.size, int((uc == 1).sum()))
+
+
 def test_host_buffer_call_pipelined_upload_and_overflow_fallback(gpu):
     """dnagpu_count_kmers on host words: chunked upload overlapped with the optimistic level 1 (no histogram
     pass, fixed-capacity regions).  Heavily repeated input overflows a region and must fall back to the exact
