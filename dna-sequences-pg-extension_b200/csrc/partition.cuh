@@ -669,8 +669,7 @@ __device__ __forceinline__ void bins_place(const uint64_t (&x)[kBinPer], const u
 #pragma unroll
     for (int u = 0; u < ROWS; ++u) {
         const uint32_t v = (u & 1) ? (f[u >> 1] >> 16) : (f[u >> 1] & 0xffffu);
-        const uint32_t bin = v & 0xfffu;
-        const uint32_t pos = st[bin] + (bin < kBins ? v >> 12 : 0u);
+        const uint32_t pos = st[v & 0xfffu] + (v >> 12);
         stage[pos] = x[u];
         rank_at[pos] = (uint8_t)(v >> 12);
     }
@@ -692,12 +691,13 @@ __global__ void __launch_bounds__(kThreads, 4) k_count_buckets_bins(const uint64
                                                                     uint32_t *__restrict__ list,
                                                                     unsigned long long *__restrict__ list_n)
 {
-    /* every array ends in 32 dummy entries, one per lane: the lanes past the end of a bucket's last row
-     * work on those instead of branching around the atomics and the stores */
-    __shared__ __align__(16) uint64_t stage[kBinCap + 32];
+    /* every array ends in dummy entries, one per lane (+ 15 for a dummy's meaningless 4-bit rank): the lanes
+     * past the end of a bucket's last row work on those instead of branching around the atomics and the stores */
+    __shared__ __align__(16) uint64_t stage_raw[4 + kBinCap + 48]; /* 4 in front: the compare phase looks back */
+    uint64_t *const stage = stage_raw + 4;
     __shared__ __align__(16) uint32_t cnt[kBins + 32];
     __shared__ __align__(16) uint16_t st[kBins + 32];       /* start of the bin in `stage` */
-    __shared__ __align__(16) uint8_t rank_at[kBinCap + 32]; /* rank of the key at a stage position inside its bin */
+    __shared__ __align__(16) uint8_t rank_at[kBinCap + 48]; /* rank of the key at a stage position inside its bin */
     const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     uint32_t repeats = 0, second = 0; /* keys with >= 1 / exactly 1 equal key before them in their bin */
     unsigned long long placed = 0;    /* thread 0: keys of the buckets counted here */
@@ -776,14 +776,15 @@ __global__ void __launch_bounds__(kThreads, 4) k_count_buckets_bins(const uint64
                  * region of its own bins: ranks > 0 are one in four, their loops one or two steps. */
                 const uint32_t base = warp * kBinWarpCap;
                 for (uint32_t q = base + lane; q < base + wtotal; q += 32) {
+                    /* three look-backs without a branch (rank > 3 is rare): neighbouring lanes read
+                     * neighbouring slots, and a slot before the bin is simply not counted */
                     const uint32_t r = rank_at[q];
-                    if (r) {
-                        const uint64_t key = stage[q];
-                        uint32_t e = 0;
-                        for (uint32_t j = 1; j <= r; ++j) e += stage[q - j] == key;
-                        repeats += e >= 1;
-                        second += e == 1;
-                    }
+                    const uint64_t key = stage[q], k1 = stage[q - 1], k2 = stage[q - 2], k3 = stage[q - 3];
+                    uint32_t e = (uint32_t)((r >= 1) & (k1 == key)) + (uint32_t)((r >= 2) & (k2 == key)) +
+                                 (uint32_t)((r >= 3) & (k3 == key));
+                    for (uint32_t j = 4; j <= r; ++j) e += stage[q - j] == key;
+                    repeats += e >= 1;
+                    second += e == 1;
                 }
             }
         }
