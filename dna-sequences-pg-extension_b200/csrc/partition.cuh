@@ -663,6 +663,14 @@ __device__ __forceinline__ void bins_rank(const uint64_t (&x)[kBinPer], uint32_t
 }
 
 template <int ROWS>
+__device__ __forceinline__ void bins_load(uint64_t (&x)[kBinPer], const uint64_t *__restrict__ src, uint32_t n, uint32_t tid)
+{
+#pragma unroll
+    for (int u = 0; u < ROWS; ++u)
+        if (u * kThreads + tid < n) x[u] = ld_nc(src + u * kThreads);
+}
+
+template <int ROWS>
 __device__ __forceinline__ void bins_place(const uint64_t (&x)[kBinPer], const uint32_t (&f)[kBinPer / 2],
                                            const uint16_t *st, uint64_t *stage, uint8_t *rank_at)
 {
@@ -711,12 +719,7 @@ __global__ void __launch_bounds__(kThreads, 4) k_count_buckets_bins(const uint64
     if (b < n_buckets) {
         const uint64_t beg = bucket_off[b];
         n = (uint32_t)min(bucket_end[b] - beg, (uint64_t)kBinCap + 1);
-        if (n <= kBinCap) {
-            const uint64_t *src = keys + beg + tid;
-#pragma unroll
-            for (int u = 0; u < kBinPer; ++u)
-                if (u * kThreads + tid < n) x[u] = ld_nc(src + u * kThreads);
-        }
+        if (n <= kBinCap) BINS_DISPATCH(n, bins_load<ROWS>(x, keys + beg + tid, n, tid));
     }
     __syncthreads();
     while (b < n_buckets) {
@@ -763,12 +766,7 @@ __global__ void __launch_bounds__(kThreads, 4) k_count_buckets_bins(const uint64
             }
         }
         /* the next bucket's keys fly during the compare phase */
-        if (nn <= kBinCap) {
-            const uint64_t *src = keys + nbeg + tid;
-#pragma unroll
-            for (int u = 0; u < kBinPer; ++u)
-                if (u * kThreads + tid < nn) x[u] = ld_nc(src + u * kThreads);
-        }
+        if (nn <= kBinCap) BINS_DISPATCH(nn, bins_load<ROWS>(x, keys + nbeg + tid, nn, tid));
         if (n <= kBinCap) { /* uniform: the barriers above were taken */
             __syncthreads();
             if (!pass_on) {
