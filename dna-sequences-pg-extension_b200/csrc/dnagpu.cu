@@ -11,6 +11,7 @@
 #include <cuda_runtime.h>
 
 #include <algorithm>
+#include <cmath>
 #include <cstdarg>
 #include <cstdio>
 #include <cstdlib>
@@ -1371,49 +1372,75 @@ static int part_level1(dnagpu_ctx *ctx, Scratch &sc, const CountInput &in, int k
 
 /* Level 2 (inside every parent; parents with equal parent % n_groups merge into the same children)
  * and the shared-memory count of every bucket.  Leaves distinct / unique in the device counters. */
-static int part_finish(dnagpu_ctx *ctx, Scratch &sc, const uint64_t *keys, uint64_t n, const uint64_t *parent_off,
-                       const uint64_t *parent_end, uint64_t n_parents, uint64_t n_groups, int b1, int b2, int k,
-                       dnagpu_stats *stats, uint64_t total_rows, dnagpu_table **table)
+static int part_finish_impl(dnagpu_ctx *ctx, Scratch &sc, const uint64_t *keys, uint64_t n, const uint64_t *parent_off,
+                            const uint64_t *parent_end, uint64_t n_parents, uint64_t n_groups, int b1, int b2, int k,
+                            dnagpu_stats *stats, uint64_t total_rows, dnagpu_table **table, bool optimistic2,
+                            bool *regions_full)
 {
     const int psmem = kTileKeys * (int)sizeof(uint64_t) + (int)sizeof(ScatterSmem);
     const uint64_t *bucket_keys = keys, *bucket_off = parent_off, *bucket_end = parent_end;
     uint64_t n_buckets = n_parents;
+    *regions_full = false;
     if (b2 > 0) {
         const uint32_t P2 = 1u << b2;
         const int shift2 = 64 - b1 - b2;
         n_buckets = n_groups * P2;
-        unsigned long long *hist2, *cur2;
-        uint64_t *off2, *tiles_hist, *tiles_scat, *bufB;
-        TRY(sc.get((void **)&hist2, n_buckets * 8));
+        unsigned long long *hist2 = nullptr, *cur2;
+        uint64_t *off2, *end2 = nullptr, *tiles_hist = nullptr, *tiles_scat, *bufB;
+        /* Optimistic level 2 (like level 1): hashing spreads a parent's keys evenly over its children, so every
+         * bucket gets a fixed region of mean + 7 sigma and the histogram pass is skipped; a run that finds its
+         * region full flags C_L2OVF and part_finish redoes level 2 with the exact histogram + scan. */
+        const uint64_t mean2 = (n + n_buckets - 1) / n_buckets;
+        const uint64_t cap2 = mean2 + 7 * (uint64_t)std::ceil(std::sqrt((double)mean2)) + 64;
         TRY(sc.get((void **)&cur2, n_buckets * 8));
         TRY(sc.get((void **)&off2, (n_buckets + 1) * 8));
-        TRY(sc.get((void **)&bufB, (n + 2) * 8));
-        CU(ctx, cudaMemsetAsync(hist2, 0, n_buckets * 8, ctx->stream));
         CU(ctx, cudaMemsetAsync(cur2, 0, n_buckets * 8, ctx->stream));
-        TRY(part_tiles(ctx, sc, parent_off, parent_end, n_parents, kSuperTile, &tiles_hist));
+        if (optimistic2) {
+            TRY(sc.get((void **)&end2, n_buckets * 8));
+            TRY(sc.get((void **)&bufB, (n_buckets * cap2 + 2) * 8));
+            TRY(launch(ctx, "part_tiles", [&] {
+                k_region_begs<<<grid_for(n_buckets, kThreads), kThreads, 0, ctx->stream>>>(cap2, n_buckets, off2);
+            }));
+        } else {
+            TRY(sc.get((void **)&hist2, n_buckets * 8));
+            TRY(sc.get((void **)&bufB, (n + 2) * 8));
+            CU(ctx, cudaMemsetAsync(hist2, 0, n_buckets * 8, ctx->stream));
+            TRY(part_tiles(ctx, sc, parent_off, parent_end, n_parents, kSuperTile, &tiles_hist));
+        }
         /* measured on the headline workload: at a fan-out of 2048 a (tile, digit) run of an 8192-key tile
          * is only 4 keys; 16384-key tiles (one CTA per SM) win 13 % there, are even at 1024 and lose 10 % at 256 */
         const bool per32 = scatter_tile32(P2);
         TRY(part_tiles(ctx, sc, parent_off, parent_end, n_parents, per32 ? 2 * kTileKeys : kTileKeys, &tiles_scat));
-        TRY(launch(ctx, "part_hist2", [&] {
-            k_part_hist_keys<<<grid_for(n, kSuperTile) + (unsigned)n_parents, kThreads, 0, ctx->stream>>>(
-                keys, parent_off, parent_end, tiles_hist, n_parents, n_groups, shift2, P2, hist2);
-        }));
-        TRY(scan_any(ctx, sc, (const uint64_t *)hist2, n_buckets, off2));
+        if (!optimistic2) {
+            TRY(launch(ctx, "part_hist2", [&] {
+                k_part_hist_keys<<<grid_for(n, kSuperTile) + (unsigned)n_parents, kThreads, 0, ctx->stream>>>(
+                    keys, parent_off, parent_end, tiles_hist, n_parents, n_groups, shift2, P2, hist2);
+            }));
+            TRY(scan_any(ctx, sc, (const uint64_t *)hist2, n_buckets, off2));
+        }
+        const uint64_t cap = optimistic2 ? cap2 : 0;
         TRY(launch(ctx, "part_scatter2", [&] {
             if (per32) {
                 const int psmem32 = 32 * kScatThreads * (int)sizeof(uint64_t) + (int)sizeof(ScatterSmem);
                 k_part_scatter_keys<false, 32><<<grid_for(n, 2 * kTileKeys) + (unsigned)n_parents, kScatThreads, psmem32,
                                                  ctx->stream>>>(keys, parent_off, parent_end, tiles_scat, n_parents, n_groups,
-                                                                shift2, P2, off2, cur2, bufB, ctx->d_ctr);
+                                                                shift2, P2, off2, cur2, bufB, ctx->d_ctr, cap);
             } else {
                 k_part_scatter_keys<false><<<grid_for(n, kTileKeys) + (unsigned)n_parents, kScatThreads, psmem, ctx->stream>>>(
-                    keys, parent_off, parent_end, tiles_scat, n_parents, n_groups, shift2, P2, off2, cur2, bufB, ctx->d_ctr);
+                    keys, parent_off, parent_end, tiles_scat, n_parents, n_groups, shift2, P2, off2, cur2, bufB, ctx->d_ctr,
+                    cap);
             }
         }));
         bucket_keys = bufB;
         bucket_off = off2;
         bucket_end = off2 + 1;
+        if (optimistic2) {
+            TRY(launch(ctx, "part_tiles", [&] {
+                k_region_ends<<<grid_for(n_buckets, kThreads), kThreads, 0, ctx->stream>>>(cur2, off2, cap2, (uint32_t)n_buckets,
+                                                                                         end2);
+            }));
+            bucket_end = end2;
+        }
     }
     const uint64_t spill_cap = std::max<uint64_t>(1ull << 16, n / 64);
     Slot *spill;
@@ -1446,6 +1473,10 @@ static int part_finish(dnagpu_ctx *ctx, Scratch &sc, const uint64_t *keys, uint6
         }));
     }
     TRY(fetch_counters(ctx));
+    if (ctx->h_ctr[C_L2OVF]) { /* some keys were dropped: the caller redoes level 2 exactly */
+        *regions_full = true;
+        return DNAGPU_OK;
+    }
 #ifdef DNAGPU_PHASE_TIMING
     fprintf(stderr, "count_buckets phases (cycles/bucket, thread 0): init %.0f | sync %.0f | insert %.0f | prefetch+sync %.0f | buckets %llu\n",
             (double)ctx->h_ctr[110] / ctx->h_ctr[114], (double)ctx->h_ctr[111] / ctx->h_ctr[114],
@@ -1487,6 +1518,29 @@ static int part_finish(dnagpu_ctx *ctx, Scratch &sc, const uint64_t *keys, uint6
         CU(ctx, cudaStreamSynchronize(ctx->stream));
     }
     return DNAGPU_OK;
+}
+
+static int part_finish(dnagpu_ctx *ctx, Scratch &sc, const uint64_t *keys, uint64_t n, const uint64_t *parent_off,
+                       const uint64_t *parent_end, uint64_t n_parents, uint64_t n_groups, int b1, int b2, int k,
+                       dnagpu_stats *stats, uint64_t total_rows, dnagpu_table **table)
+{
+    /* optimistic level 2 where no parents merge (one GPU) and the buckets are full-sized */
+    static const bool allow = !getenv("DNAGPU_EXACT_L2");
+    const bool optimistic2 = allow && b2 > 0 && n_groups == n_parents && (n >> (b1 + b2)) >= 512;
+    bool full = false;
+    TRY(part_finish_impl(ctx, sc, keys, n, parent_off, parent_end, n_parents, n_groups, b1, b2, k, stats, total_rows, table,
+                         optimistic2, &full));
+    if (!full) return DNAGPU_OK;
+    /* the counters of the scatter passes before (rows kept, 'G' x 32 rows, level-1 flag) stay; the count starts over */
+    CU(ctx, cudaMemsetAsync(ctx->d_ctr + C_DISTINCT, 0, 2 * 8, ctx->stream));
+    CU(ctx, cudaMemsetAsync(ctx->d_ctr + C_OVERFLOW, 0, 2 * 8, ctx->stream));
+    CU(ctx, cudaMemsetAsync(ctx->d_ctr + C_L2OVF, 0, 2 * 8, ctx->stream));
+    if (table && *table) {
+        dnagpu_table_free(*table);
+        *table = nullptr;
+    }
+    return part_finish_impl(ctx, sc, keys, n, parent_off, parent_end, n_parents, n_groups, b1, b2, k, stats, total_rows, table,
+                            false, &full);
 }
 
 /* Optimistic level 1 (unfiltered packed input): no histogram pass.  Hashing spreads the keys evenly, so

@@ -52,7 +52,7 @@ struct Pred {
 };
 
 /* Device counters of one GROUP BY (u64 each). */
-enum { C_TOTAL = 0, C_DISTINCT, C_UNIQUE, C_SIDE, C_OVERFLOW, C_CURSOR, C_L1OVF, C_PASSED, C_COUNT };
+enum { C_TOTAL = 0, C_DISTINCT, C_UNIQUE, C_SIDE, C_OVERFLOW, C_CURSOR, C_L1OVF, C_L2OVF, C_PASSED, C_COUNT };
 
 __host__ __device__ __forceinline__ uint64_t mix64(uint64_t x)
 { /* murmur3 fmix64 */

@@ -75,6 +75,13 @@ __device__ __forceinline__ void tile_range(const uint64_t *parent_beg, const uin
     end = min(beg + tile_keys, parent_end[parent]);
 }
 
+/* optimistic layouts: region d starts at d * cap */
+__global__ void __launch_bounds__(kThreads) k_region_begs(uint64_t cap, uint64_t n, uint64_t *__restrict__ beg)
+{
+    const uint64_t d = (uint64_t)blockIdx.x * kThreads + threadIdx.x;
+    if (d < n) beg[d] = d * cap;
+}
+
 /* optimistic level 1: end[d] = beg[d] + keys actually stored in region d */
 __global__ void __launch_bounds__(kThreads) k_region_ends(const unsigned long long *__restrict__ cur,
                                                           const uint64_t *__restrict__ beg, uint64_t cap,
@@ -167,7 +174,8 @@ __device__ __forceinline__ uint32_t scatter_plan(ScatterSmem &s, uint32_t fan,
                                                  const uint64_t *__restrict__ child_off,
                                                  unsigned long long *__restrict__ child_cur,
                                                  long long (&gd)[kPlanPer], uint64_t cap = 0,
-                                                 unsigned long long *__restrict__ ctr = nullptr)
+                                                 unsigned long long *__restrict__ ctr = nullptr,
+                                                 int full_flag = C_L1OVF)
 {
     uint32_t v[kPlanPer], sum = 0;
     const uint32_t base = threadIdx.x * kPlanPer;
@@ -202,7 +210,7 @@ __device__ __forceinline__ uint32_t scatter_plan(ScatterSmem &s, uint32_t fan,
                 const unsigned long long at = atomicAdd(&child_cur[base + i], (unsigned long long)v[i]);
                 if (cap && at + v[i] > cap) { /* optimistic layout: the region is full -> caller re-runs exactly */
                     gd[i] = kNoDest;
-                    atomicExch(&ctr[C_L1OVF], 1ull);
+                    atomicExch(&ctr[full_flag], 1ull);
                 } else {
                     gd[i] = (long long)(child_off[base + i] + at) - (long long)ex;
                 }
@@ -354,7 +362,8 @@ __global__ void __launch_bounds__(kScatThreads, (PER == 16 ? 2 : 1)) k_part_scat
                                                                        const uint64_t *__restrict__ child_off,
                                                                        unsigned long long *__restrict__ child_cur,
                                                                        uint64_t *__restrict__ out,
-                                                                       unsigned long long *__restrict__ ctr)
+                                                                       unsigned long long *__restrict__ ctr,
+                                                                       uint64_t cap = 0)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     uint64_t *stage = reinterpret_cast<uint64_t *>(smem_raw);
@@ -386,7 +395,8 @@ __global__ void __launch_bounds__(kScatThreads, (PER == 16 ? 2 : 1)) k_part_scat
     }
     __syncthreads();
     long long gd[kPlanPer];
-    const uint32_t total = scatter_plan(s, fan, child_off + (parent % n_groups) * fan, child_cur + (parent % n_groups) * fan, gd);
+    const uint32_t total = scatter_plan(s, fan, child_off + (parent % n_groups) * fan, child_cur + (parent % n_groups) * fan, gd,
+                                        cap, ctr, C_L2OVF);
 #pragma unroll
     for (int u = 0; u < PER; ++u) {
         const uint32_t r = (u & 1) ? (rk[u >> 1] >> 16) : (rk[u >> 1] & 0xffffu);

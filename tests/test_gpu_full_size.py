@@ -54,6 +54,7 @@ def test_1gbp_k31_two_methods_and_shards_agree(gpu):
         lo, hi = owner_digits(plan, o)
         pieces = np.concatenate([c[lo:hi] for _, c, _ in sends])
         recv = torch.cat([b_[int(off[lo]):int(off[hi])] for b_, _, off in sends])
+        torch.cuda.synchronize()                   # torch's stream is not the library's
         st, _ = gpu.shuffle_count(recv, pieces, hi - lo, plan, k)
         distinct += st.distinct
         unique += st.unique

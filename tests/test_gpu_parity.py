@@ -440,6 +440,7 @@ def test_fused_owner_routing_composes_to_the_single_gpu_answer(gpu, k, prefix):
                 pieces.extend(int(c) for c in counts[lo:hi])
                 chunks.append(buf[int(offs[lo]):int(offs[hi])])
             recv = torch.cat(chunks) if chunks else torch.empty(0, dtype=torch.int64, device="cuda")
+            torch.cuda.synchronize()               # torch's stream is not the library's
             st, table = gpu.shuffle_count(recv, np.array(pieces, dtype=np.uint64), hi - lo, plan, k, table=True)
             assert st.total == sum(pieces)
             tot[0] += st.distinct
@@ -481,6 +482,7 @@ def test_scatter_to_destinations_composes_to_the_single_gpu_answer(gpu, k, prefi
             assert np.array_equal(counts, np.stack([gpu.shuffle_hist(s, k, plan, **where) for s in seqs]))
         ranges = [owner_digits(plan, r) for r in range(G)]
         recv = [torch.full((int(counts[:, a:b].sum()) + 2,), -7, dtype=torch.int64, device="cuda") for a, b in ranges]
+        torch.cuda.synchronize()                   # torch's stream is not the library's
         kept_all = side_all = 0
         for r in range(G):
             dest = np.zeros(plan.n_digits, dtype=np.uint64)
