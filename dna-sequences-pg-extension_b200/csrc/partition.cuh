@@ -170,19 +170,20 @@ struct ScatterSmem {
 constexpr int kPlanPer = kMaxFan / kScatThreads; /* 4 digits per thread */
 constexpr long long kNoDest = (long long)0x8000000000000000ull; /* a run that found its region full */
 
+struct ScatterClaim { /* what scatter_plan leaves in registers for scatter_publish */
+    unsigned long long at[kPlanPer]; /* value returned by the claim of digit base + i: NOT looked at before the publish */
+    uint32_t n[kPlanPer], ex[kPlanPer];
+};
+
 __device__ __forceinline__ uint32_t scatter_plan(ScatterSmem &s, uint32_t fan,
-                                                 const uint64_t *__restrict__ child_off,
-                                                 unsigned long long *__restrict__ child_cur,
-                                                 long long (&gd)[kPlanPer], uint64_t cap = 0,
-                                                 unsigned long long *__restrict__ ctr = nullptr,
-                                                 int full_flag = C_L1OVF)
+                                                 unsigned long long *__restrict__ child_cur, ScatterClaim &cl)
 {
-    uint32_t v[kPlanPer], sum = 0;
+    uint32_t sum = 0;
     const uint32_t base = threadIdx.x * kPlanPer;
 #pragma unroll
     for (int i = 0; i < kPlanPer; ++i) {
-        v[i] = base + i < fan ? s.cur[base + i] : 0;
-        sum += v[i];
+        cl.n[i] = base + i < fan ? s.cur[base + i] : 0;
+        sum += cl.n[i];
     }
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
     uint32_t inc = sum;
@@ -203,32 +204,37 @@ __device__ __forceinline__ uint32_t scatter_plan(ScatterSmem &s, uint32_t fan,
     uint32_t ex = woff + inc - sum;
 #pragma unroll
     for (int i = 0; i < kPlanPer; ++i) {
-        gd[i] = 0;
+        cl.at[i] = 0;
+        cl.ex[i] = ex;
         if (base + i < fan) {
             s.cur[base + i] = ex;
-            if (v[i]) {
-                const unsigned long long at = atomicAdd(&child_cur[base + i], (unsigned long long)v[i]);
-                if (cap && at + v[i] > cap) { /* optimistic layout: the region is full -> caller re-runs exactly */
-                    gd[i] = kNoDest;
-                    atomicExch(&ctr[full_flag], 1ull);
-                } else {
-                    gd[i] = (long long)(child_off[base + i] + at) - (long long)ex;
-                }
-            }
+            if (cl.n[i]) cl.at[i] = atomicAdd(&child_cur[base + i], (unsigned long long)cl.n[i]);
         }
-        ex += v[i];
+        ex += cl.n[i];
     }
     if (threadIdx.x == 0) s.cur[fan] = 0;
     __syncthreads();
     return total;
 }
 
-__device__ __forceinline__ void scatter_publish(ScatterSmem &s, uint32_t fan, const long long (&gd)[kPlanPer])
+/* After the placing phase: where every digit's run goes.  With cap != 0 (optimistic layout) a run that
+ * finds its region full gets no destination and raises `full_flag`: the caller re-runs exactly. */
+__device__ __forceinline__ void scatter_publish(ScatterSmem &s, uint32_t fan, const uint64_t *__restrict__ child_off,
+                                                const ScatterClaim &cl, uint64_t cap = 0,
+                                                unsigned long long *__restrict__ ctr = nullptr, int full_flag = C_L1OVF)
 {
     const uint32_t base = threadIdx.x * kPlanPer;
 #pragma unroll
-    for (int i = 0; i < kPlanPer; ++i)
-        if (base + i < fan) s.gdelta[base + i] = gd[i];
+    for (int i = 0; i < kPlanPer; ++i) {
+        if (base + i < fan && cl.n[i]) {
+            if (cap && cl.at[i] + cl.n[i] > cap) {
+                s.gdelta[base + i] = kNoDest;
+                atomicExch(&ctr[full_flag], 1ull);
+            } else {
+                s.gdelta[base + i] = (long long)(child_off[base + i] + cl.at[i]) - (long long)cl.ex[i];
+            }
+        }
+    }
 }
 
 /* stage -> global: consecutive threads copy consecutive stage entries, i.e. whole runs.  The digit of
@@ -315,8 +321,8 @@ __global__ void __launch_bounds__(kScatThreads, (PER == 16 ? 2 : 1)) k_part_scat
     PHASE_MARK(1);
     __syncthreads();
     PHASE_MARK(2);
-    long long gd[kPlanPer];
-    const uint32_t total = scatter_plan(s, fan, child_off, child_cur, gd, cap, ctr);
+    ScatterClaim cl;
+    const uint32_t total = scatter_plan(s, fan, child_cur, cl);
     PHASE_MARK(3);
     {
         uint64_t cur = a0, nxt = a1;
@@ -331,7 +337,7 @@ __global__ void __launch_bounds__(kScatThreads, (PER == 16 ? 2 : 1)) k_part_scat
             nxt >>= 2;
         }
     }
-    scatter_publish(s, fan, gd);
+    scatter_publish(s, fan, child_off, cl, cap, ctr);
     __syncthreads();
     PHASE_MARK(4);
     scatter_flush<PER>(s, stage, total, shift, fm, out);
@@ -394,9 +400,8 @@ __global__ void __launch_bounds__(kScatThreads, (PER == 16 ? 2 : 1)) k_part_scat
         rk[u >> 1] = (u & 1) ? __byte_perm(rk[u >> 1], r, 0x5410) : r;
     }
     __syncthreads();
-    long long gd[kPlanPer];
-    const uint32_t total = scatter_plan(s, fan, child_off + (parent % n_groups) * fan, child_cur + (parent % n_groups) * fan, gd,
-                                        cap, ctr, C_L2OVF);
+    ScatterClaim cl;
+    const uint32_t total = scatter_plan(s, fan, child_cur + (parent % n_groups) * fan, cl);
 #pragma unroll
     for (int u = 0; u < PER; ++u) {
         const uint32_t r = (u & 1) ? (rk[u >> 1] >> 16) : (rk[u >> 1] & 0xffffu);
@@ -404,7 +409,7 @@ __global__ void __launch_bounds__(kScatThreads, (PER == 16 ? 2 : 1)) k_part_scat
         const uint32_t pos = (s.cur[d] + r) & (TILE - 1);
         if (d != fan) stage[pos] = x[u];
     }
-    scatter_publish(s, fan, gd);
+    scatter_publish(s, fan, child_off + (parent % n_groups) * fan, cl, cap, ctr, C_L2OVF);
     __syncthreads();
     scatter_flush<PER>(s, stage, total, shift, fm, out);
     if (COUNT_SIDE) {
