@@ -387,11 +387,14 @@ def run_b200(args):
         # rows = k-mers one launch handles on this rank; base reads are 0.25 B/base
         rows_r = stats[0] / world          # keys that reach the partition / count stages (after WHERE)
         base_b = 8.0 * n_words_local       # the packed words one launch reads (0.25 B/base)
+        listed = "filter_collect" in kernels and kernels["filter_collect"]["launches"] > 0
         ALG = {
             "count_hash": base_b + 16.0 * rows_r, "count_hash_keys": 8.0 * rows_r + 16.0 * rows_r,
             "count_dense": base_b + 4.0 * rows_r, "count_dense_smem": base_b,
-            "part_hist": base_b if world == 1 else 8.0 * rows_r,
-            "part_scatter": (base_b if world == 1 else 8.0 * rows_r) + 8.0 * rows_r,
+            "part_hist": base_b if world == 1 and not listed else 8.0 * rows_r,
+            "part_scatter": (base_b if world == 1 and not listed else 8.0 * rows_r) + 8.0 * rows_r,
+            # a WHERE clause is evaluated once into a key list: packed words in, matching rows out
+            "filter_collect": base_b + 8.0 * rows_r,
             "part_hist2": 8.0 * rows_r, "part_scatter2": 16.0 * rows_r, "count_buckets": 8.0 * rows_r,
             "partition_count": base_b, "partition_write": base_b + 8.0 * rows_r,
         }
