@@ -1220,10 +1220,14 @@ static int count_hash(dnagpu_ctx *ctx, const CountInput &in, int k, const dnagpu
 }
 
 /* scatter tile: 16384 keys (one CTA per SM) when the fan-out makes 8192-key runs too short */
-static inline bool scatter_tile32(uint32_t fan)
+static inline bool scatter_tile32(uint32_t fan, int level = 0)
 {
     if (const char *e = getenv("DNAGPU_SCATTER_TILE")) return atoi(e) == 16384;
-    return fan >= 2048;
+    if (level == 1)
+        if (const char *e = getenv("DNAGPU_SCATTER_TILE_L1")) return atoi(e) == 16384;
+    if (level == 2)
+        if (const char *e = getenv("DNAGPU_SCATTER_TILE_L2")) return atoi(e) == 16384;
+    return fan >= 1024; /* measured on the headline workload: 16384-key tiles win 13 % at 2048 and 1 % at 1024 */
 }
 
 /* exclusive scan of n u64 (out has n + 1 entries); multi-CTA above 16 K entries */
@@ -1410,7 +1414,7 @@ static int part_finish_impl(dnagpu_ctx *ctx, Scratch &sc, const uint64_t *keys, 
         }
         /* measured on the headline workload: at a fan-out of 2048 a (tile, digit) run of an 8192-key tile
          * is only 4 keys; 16384-key tiles (one CTA per SM) win 13 % there, are even at 1024 and lose 10 % at 256 */
-        const bool per32 = scatter_tile32(P2);
+        const bool per32 = scatter_tile32(P2, 2);
         TRY(part_tiles(ctx, sc, parent_off, parent_end, n_parents, per32 ? 2 * kTileKeys : kTileKeys, &tiles_scat));
         if (!optimistic2) {
             TRY(launch(ctx, "part_hist2", [&] {
@@ -1577,7 +1581,7 @@ static int l1_regions_begin(dnagpu_ctx *ctx, Scratch &sc, uint64_t n_rows, int b
 static int l1_regions_scatter(dnagpu_ctx *ctx, const L1Regions &r, int layout, const SeqView &v, int k)
 {
     const Pred none = {~0ull, ~0ull, ~0ull, ~0ull};
-    if (scatter_tile32(r.P1)) {
+    if (scatter_tile32(r.P1, 1)) {
         const int psmem = 32 * kScatThreads * (int)sizeof(uint64_t) + (int)sizeof(ScatterSmem);
         const unsigned grid = grid_for(v.n_items, kScatThreads);
         DISPATCH_LAYOUT(layout, TRY(launch(ctx, "part_scatter", [&] {
