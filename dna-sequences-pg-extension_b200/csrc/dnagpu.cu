@@ -1227,7 +1227,9 @@ static inline bool scatter_tile32(uint32_t fan, int level = 0)
         if (const char *e = getenv("DNAGPU_SCATTER_TILE_L1")) return atoi(e) == 16384;
     if (level == 2)
         if (const char *e = getenv("DNAGPU_SCATTER_TILE_L2")) return atoi(e) == 16384;
-    return fan >= 1024; /* measured on the headline workload: 16384-key tiles win 13 % at 2048 and 1 % at 1024 */
+    /* measured: from packed input (level 1) 16384-key tiles win at every fan-out (256: 15 %, 1024: 12 %, 2048: 2x);
+     * from a key list they win 13 % at 2048, 1 % at 1024 and lose 10 % at 256 */
+    return level == 1 || fan >= 1024;
 }
 
 /* exclusive scan of n u64 (out has n + 1 entries); multi-CTA above 16 K entries */
@@ -1346,7 +1348,7 @@ static int part_level1(dnagpu_ctx *ctx, Scratch &sc, const CountInput &in, int k
                 in.d_keys, root_off, root_off + 1, root_tiles_scat, 1, 1, shift1, P1, off1, cur1, out, ctx->d_ctr);
         }));
     } else {
-        const bool per32 = scatter_tile32(P1);
+        const bool per32 = scatter_tile32(P1, in.d_keys ? 0 : 1);
         if (per32) {
             const int psmem32 = 32 * kScatThreads * (int)sizeof(uint64_t) + (int)sizeof(ScatterSmem);
             const unsigned grid = grid_for(in.v.n_items, kScatThreads);
