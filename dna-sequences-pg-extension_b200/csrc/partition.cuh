@@ -643,11 +643,14 @@ __global__ void __launch_bounds__(kThreads) k_count_buckets(const uint64_t *__re
  * kBins sub-bins by an independent hash with a RETURNING shared-memory add (11.6 lane-ops/clk/SM
  * against 3.1 for the 64-bit CAS of the table, profiles/r01e_microbench); the value returned is the
  * key's rank r inside its bin.  Each warp scans the counts of its own bins with shuffles, the keys
- * are placed bin by bin into a staging area, and a key of rank r > 0 (one in six with 4096 bins) is
- * compared with the r keys placed before it in its bin:
- *     e = earlier keys equal to mine;  distinct += (e == 0);  second += (e == 1);
- *     unique = distinct - second  (a key is unique iff it has no second occurrence).
- * No probe chains, no 48 KB table to clear, three barriers per bucket.
+ * are placed bin by bin into a staging area with their rank beside them, and every staged key is
+ * compared with the r keys placed before it in its bin (r > 0 for about one key in four; the first
+ * three look-backs are branch-free):
+ *     e = earlier keys equal to mine;  repeats += (e >= 1);  second += (e == 1);
+ *     distinct = keys - repeats;  unique = distinct - second  (unique iff no second occurrence).
+ * No probe chains, no 48 KB table to clear, three barriers per bucket.  The kernel is bound by issue
+ * slots, so it is written as straight-line code: lanes past the end of a bucket work on dummy bins and
+ * slots, and the rank / place / load phases are instantiated per number of key rows (BINS_DISPATCH).
  * A bucket this cannot hold -- more than kBinCap keys, a warp's region overflowing, or a bin with
  * more than kBinHeavy keys (a k-mer with many copies) -- is appended to `list` and counted by the
  * table kernel afterwards (k_count_buckets with the list). */
