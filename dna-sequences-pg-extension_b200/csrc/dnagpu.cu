@@ -1715,16 +1715,54 @@ static int count_kmers_pipelined(dnagpu_ctx *ctx, const uint64_t *words, uint64_
 }
 
 /* One predicate scan, matches appended in no particular order. */
+static int collect_launch(dnagpu_ctx *ctx, int layout, const SeqView &v, const Pred &p, int k, uint64_t *d_out, uint64_t cap)
+{
+    const unsigned tiles = grid_for(v.n_items, kThreads);
+    const int smem = kThreads * 32 * (int)sizeof(uint64_t);
+    DISPATCH_LAYOUT(layout, TRY(launch(ctx, "filter_collect", [&] {
+        k_filter_collect<LY><<<(tiles + kFilterTiles - 1) / kFilterTiles, kThreads, smem, ctx->stream>>>(
+            v, p, kmer_mask(k), cap, ctx->d_ctr + C_CURSOR, d_out);
+    })));
+    return DNAGPU_OK;
+}
+
 static int collect_rows(dnagpu_ctx *ctx, const CountInput &in, int k, uint64_t *d_out, uint64_t cap, uint64_t *n_match)
 {
-    const unsigned tiles = grid_for(in.v.n_items, kThreads);
-    const int smem = kThreads * 32 * (int)sizeof(uint64_t);
     TRY(zero_counters(ctx));
-    DISPATCH_LAYOUT(in.seq->layout, TRY(launch(ctx, "filter_collect", [&] {
-        k_filter_collect<LY><<<(tiles + kFilterTiles - 1) / kFilterTiles, kThreads, smem, ctx->stream>>>(
-            in.v, in.p, kmer_mask(k), cap, ctx->d_ctr + C_CURSOR, d_out);
-    })));
+    TRY(collect_launch(ctx, in.seq->layout, in.v, in.p, k, d_out, cap));
     return read_u64(ctx, (const uint64_t *)(ctx->d_ctr + C_CURSOR), n_match);
+}
+
+static int count_dense_any(dnagpu_ctx *ctx, const CountInput &in, int k, dnagpu_stats *stats, dnagpu_table **table);
+static int count_partition(dnagpu_ctx *ctx, const CountInput &in, int k, dnagpu_stats *stats, dnagpu_table **table);
+
+/* GROUP BY over a key list on the device (what a WHERE clause kept) */
+static int count_listed(dnagpu_ctx *ctx, const uint64_t *keys, uint64_t n_match, int k, const dnagpu_count_opts *opts,
+                        dnagpu_stats *stats, dnagpu_table **table)
+{
+    CountInput listed;
+    listed.d_keys = keys;
+    listed.n = n_match;
+    dnagpu_count_opts o2 = opts ? *opts : dnagpu_count_opts{0, 0, 0.0, 0};
+    const int method = pick_method(&o2, k, n_match);
+    int rc;
+    if (method == DNAGPU_COUNT_DENSE)
+        rc = count_dense_any(ctx, listed, k, stats, table);
+    else if (method == DNAGPU_COUNT_PARTITION)
+        rc = count_partition(ctx, listed, k, stats, table);
+    else
+        rc = count_hash(ctx, listed, k, opts, n_match, stats, table);
+    if (rc != DNAGPU_OK && table && *table) {
+        dnagpu_table_free(*table);
+        *table = nullptr;
+    }
+    return rc;
+}
+
+static int count_dense_any(dnagpu_ctx *ctx, const CountInput &in, int k, dnagpu_stats *stats, dnagpu_table **table)
+{
+    return in.n < 0xffffffffull ? count_dense_t<uint32_t>(ctx, in, k, stats, table)
+                                : count_dense_t<unsigned long long>(ctx, in, k, stats, table);
 }
 
 static int count_any(dnagpu_ctx *ctx, CountInput &in, int k, const dnagpu_count_opts *opts,
@@ -1744,7 +1782,6 @@ static int count_any(dnagpu_ctx *ctx, CountInput &in, int k, const dnagpu_count_
      * scans: count per tile, then write) and count that list, instead of dragging the whole
      * input through the partition / hash machinery only to drop most of it. */
     Scratch keep(ctx);
-    CountInput listed;
     if (in.filtered && in.seq && method != DNAGPU_COUNT_DENSE) {
         /* one predicate scan: matches are appended (unordered -- GROUP BY does not care) to a buffer sized
          * for a selectivity of 1/8; only a less selective clause needs the second, exactly sized scan */
@@ -1763,24 +1800,7 @@ static int count_any(dnagpu_ctx *ctx, CountInput &in, int k, const dnagpu_count_
             if (table) TRY(table_new(ctx, k, 0, table));
             return DNAGPU_OK;
         }
-        if (n_match <= in.n / 2 || method == DNAGPU_COUNT_PARTITION) {
-            listed.d_keys = keys;
-            listed.n = n_match;
-            dnagpu_count_opts o2 = opts ? *opts : dnagpu_count_opts{0, 0, 0.0, 0};
-            method = pick_method(&o2, k, n_match);
-            if (method == DNAGPU_COUNT_DENSE)
-                rc = n_match < 0xffffffffull ? count_dense_t<uint32_t>(ctx, listed, k, stats, table)
-                                             : count_dense_t<unsigned long long>(ctx, listed, k, stats, table);
-            else if (method == DNAGPU_COUNT_PARTITION)
-                rc = count_partition(ctx, listed, k, stats, table);
-            else
-                rc = count_hash(ctx, listed, k, opts, n_match, stats, table);
-            if (rc != DNAGPU_OK && table && *table) {
-                dnagpu_table_free(*table);
-                *table = nullptr;
-            }
-            return rc;
-        }
+        if (n_match <= in.n / 2 || method == DNAGPU_COUNT_PARTITION) return count_listed(ctx, keys, n_match, k, opts, stats, table);
         if (method == DNAGPU_COUNT_HASH) { /* not selective: fused insert into a table sized by n_match */
             rc = count_hash(ctx, in, k, opts, n_match, stats, table);
             if (rc != DNAGPU_OK && table && *table) {
@@ -1875,6 +1895,78 @@ extern "C" int dnagpu_count_kmers(dnagpu_ctx *ctx, const uint64_t *words, uint64
     return rc;
 }
 
+/* Host reads + a WHERE clause: the upload goes in chunks on the copy stream while the predicate scan of the
+ * previous chunk appends its matches to the key list; the list is counted at the end.  If the list overflows
+ * its guess (a clause that keeps more than 1/8 of the rows) the query is redone on the resident words. */
+static int count_reads_pipelined(dnagpu_ctx *ctx, const uint64_t *words, uint64_t n_reads, uint32_t bases_per_read,
+                                 uint32_t stride_words, int k, const dnagpu_where *filter, dnagpu_stats *stats,
+                                 dnagpu_table **table, bool *done)
+{
+    *done = false;
+    const uint64_t rows_per_read = rows_of(bases_per_read, k), n = n_reads * rows_per_read;
+    if (!words || n < (1ull << 24) || stride_words < words_of(bases_per_read) ||
+        pick_method(nullptr, k, n) == DNAGPU_COUNT_DENSE || getenv("DNAGPU_NO_READS_PIPELINE"))
+        return DNAGPU_OK;
+    CU(ctx, cudaSetDevice(ctx->device));
+    Pred p;
+    bool active = false;
+    TRY(build_pred(ctx, filter, k, n, &p, &active));
+    if (!active) return DNAGPU_OK;
+    if (!ctx->copy_stream) CU(ctx, cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking));
+    Scratch sc(ctx);
+    const uint64_t n_words = n_reads * stride_words, alloc_words = (n_words + 3) & ~1ull;
+    const uint64_t cap = std::max<uint64_t>(1ull << 20, n / 8);
+    uint64_t *d_words, *keys;
+    TRY(sc.get((void **)&d_words, alloc_words * 8));
+    TRY(sc.get((void **)&keys, (cap + 2) * 8));
+    CU(ctx, cudaMemsetAsync(d_words + n_words, 0, (alloc_words - n_words) * 8, ctx->stream));
+    TRY(zero_counters(ctx));
+    CU(ctx, cudaStreamSynchronize(ctx->stream)); /* d_words exists before the copy stream writes it */
+    const int n_chunks = 8;
+    const uint64_t chunk_reads = (n_reads + n_chunks - 1) / n_chunks;
+    std::vector<cudaEvent_t> ev;
+    int rc = DNAGPU_OK;
+    for (uint64_t r0 = 0; r0 < n_reads && rc == DNAGPU_OK; r0 += chunk_reads) {
+        const uint64_t r1 = std::min(n_reads, r0 + chunk_reads);
+        cudaEvent_t e;
+        CU(ctx, cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+        ev.push_back(e);
+        CU(ctx, cudaMemcpyAsync(d_words + r0 * stride_words, words + r0 * stride_words, (r1 - r0) * stride_words * 8,
+                                cudaMemcpyHostToDevice, ctx->copy_stream));
+        CU(ctx, cudaEventRecord(e, ctx->copy_stream));
+        CU(ctx, cudaStreamWaitEvent(ctx->stream, e, 0));
+        SeqView v;
+        memset(&v, 0, sizeof v);
+        v.words = d_words + r0 * stride_words;
+        v.n_seqs = r1 - r0;
+        v.stride = stride_words;
+        v.rows_per_seq = rows_per_read;
+        v.items_per_seq = (rows_per_read + 31) / 32;
+        v.n_rows = v.rows_per_seq * v.n_seqs;
+        v.n_items = v.items_per_seq * v.n_seqs;
+        if (v.n_rows) rc = collect_launch(ctx, kFixed, v, p, k, keys, cap);
+    }
+    uint64_t n_match = 0;
+    if (rc == DNAGPU_OK) rc = read_u64(ctx, (const uint64_t *)(ctx->d_ctr + C_CURSOR), &n_match);
+    cudaStreamSynchronize(ctx->copy_stream);
+    for (cudaEvent_t e : ev) cudaEventDestroy(e);
+    TRY(rc);
+    if (n_match > cap) { /* not selective after all: the ordinary path, on the words that are resident now */
+        dnagpu_seq *seq = nullptr;
+        TRY(dnagpu_seq_wrap_reads(ctx, d_words, n_reads, bases_per_read, stride_words, alloc_words, &seq));
+        rc = dnagpu_count(ctx, seq, k, filter, nullptr, stats, table);
+        dnagpu_seq_free(seq);
+        TRY(rc);
+    } else if (n_match == 0) {
+        stats->total = stats->distinct = stats->unique = 0;
+        if (table) TRY(table_new(ctx, k, 0, table));
+    } else {
+        TRY(count_listed(ctx, keys, n_match, k, nullptr, stats, table));
+    }
+    *done = true;
+    return DNAGPU_OK;
+}
+
 extern "C" int dnagpu_count_reads(dnagpu_ctx *ctx, const uint64_t *words, uint64_t n_reads,
                                   uint32_t bases_per_read, uint32_t stride_words, int k,
                                   const dnagpu_where *filter, dnagpu_stats *stats,
@@ -1883,6 +1975,12 @@ extern "C" int dnagpu_count_reads(dnagpu_ctx *ctx, const uint64_t *words, uint64
     if (!ctx) return fail(ctx, DNAGPU_EARG, "dnagpu_count_reads: NULL ctx");
     TRY(check_k(ctx, k));
     TRY(check_filter_literals(ctx, filter));
+    if (stats && filter) {
+        if (table) *table = nullptr;
+        bool done = false;
+        TRY(count_reads_pipelined(ctx, words, n_reads, bases_per_read, stride_words, k, filter, stats, table, &done));
+        if (done) return DNAGPU_OK;
+    }
     dnagpu_seq *seq = nullptr;
     TRY(dnagpu_seq_upload_reads(ctx, words, n_reads, bases_per_read, stride_words, &seq));
     int rc = dnagpu_count(ctx, seq, k, filter, nullptr, stats, table);

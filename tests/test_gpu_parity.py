@@ -348,6 +348,24 @@ def test_count_reads_never_span_rows(gpu):
     assert (st.total, st.distinct, st.unique) == oracle.stats
 
 
+def test_count_reads_host_call_with_where_clause_pipelined(gpu):
+    """dnagpu_count_reads on host words with a WHERE clause: chunked upload overlapped with the predicate scan
+    (needs >= 2^24 rows).  A selective clause is counted from the collected list; one that keeps more than 1/8
+    of the rows overflows the list and must fall back to the ordinary path with identical results."""
+    n_reads, bpr, stride, k = 150_000, 150, 5, 31
+    reads = R.synth_reads(8, n_reads, bpr, stride)
+    for prefix, pattern in (("AC", "NNNNNNNNNNNNWSNNNNNNNNNNNNNNNRY"), ("AC", None), ("A", None),
+                            (None, "NNNNNNNNNNNNNNNNNNNNNNNNNNNNNNU")):
+        pk = R.kmer_make(prefix) if prefix else None
+        oracle = R.count_query(reads, n_reads, bpr, stride, k, prefix=pk, pattern=pattern, faithful=False, threads=8)
+        st, table = gpu.count_reads(reads, n_reads, bpr, stride, k, prefix=prefix, pattern=pattern, table=True)
+        assert (st.total, st.distinct, st.unique) == oracle.stats, (prefix, pattern)
+        kk, cc = table.sorted()
+        assert np.array_equal(kk, oracle.kmers) and np.array_equal(cc, oracle.counts), (prefix, pattern)
+    with pytest.raises(DnaError, match="Prefix length cannot exceed kmer length"):
+        gpu.count_reads(reads, n_reads, bpr, stride, 3, prefix="ACGT")
+
+
 def test_count_ragged_table_of_sequences(gpu):
     """SELECT ... FROM dna_sequences d, generate_kmers(d.sequence, k) GROUP BY kmer (test.sql:140-150)."""
     rng = np.random.default_rng(8)
