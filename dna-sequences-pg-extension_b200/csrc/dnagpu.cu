@@ -294,6 +294,8 @@ extern "C" int dnagpu_create(dnagpu_ctx **out, int device)
                 per_sm > 0)
                 ctx->bins_ctas_per_sm = per_sm;
         }
+        cudaFuncSetAttribute(k_sort_scatter<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(SortSmem));
+        cudaFuncSetAttribute(k_sort_scatter<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(SortSmem));
         const int bsmem = kBucketSlots * 12;
         cudaFuncSetAttribute(k_count_buckets<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, bsmem);
         cudaFuncSetAttribute(k_count_buckets<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, bsmem);
@@ -2401,9 +2403,11 @@ static int radix_sort(dnagpu_ctx *ctx, Scratch &sc, uint64_t *ak, uint64_t *av, 
         TRY(scan_any(ctx, sc, cnt, 256ull * grid, off));
         TRY(launch(ctx, "sort_scatter", [&] {
             if (av)
-                k_sort_scatter<true><<<grid, kSortThreads, 0, ctx->stream>>>(src_k, src_v, n, per_cta, shift, off, dst_k, dst_v);
+                k_sort_scatter<true><<<grid, kSortThreads, sizeof(SortSmem), ctx->stream>>>(src_k, src_v, n, per_cta, shift, off,
+                                                                                          dst_k, dst_v);
             else
-                k_sort_scatter<false><<<grid, kSortThreads, 0, ctx->stream>>>(src_k, nullptr, n, per_cta, shift, off, dst_k, nullptr);
+                k_sort_scatter<false><<<grid, kSortThreads, sizeof(SortSmem), ctx->stream>>>(src_k, nullptr, n, per_cta, shift,
+                                                                                           off, dst_k, nullptr);
         }));
         *in_a = !*in_a;
     }

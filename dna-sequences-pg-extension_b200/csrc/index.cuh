@@ -66,7 +66,19 @@ __global__ void __launch_bounds__(kSortThreads) k_sort_hist(const uint64_t *__re
 }
 
 /* Stable scatter of one pass.  off = exclusive scan of cnt (digit-major), i.e. where the CTA's first
- * key of every digit goes.  per_cta is a multiple of kSortChunk. */
+ * key of every digit goes.  per_cta is a multiple of kSortChunk.
+ * A chunk of 4096 pairs is ranked (warp ballots, round-major inside a warp, warps in input order), laid out by
+ * digit in shared memory and copied out run by run: consecutive threads store consecutive addresses of a
+ * digit's run instead of one 32-byte sector per lane straight from the registers. */
+struct SortSmem {
+    uint64_t keys[kSortChunk];
+    uint64_t vals[kSortChunk];
+    uint32_t wcnt[kSortWarps][256]; /* keys of digit d seen by warp w, then the warp's start inside the digit */
+    uint64_t dbase[256];            /* where the next key of digit d goes in the output */
+    uint32_t dstart[256 + 1];       /* start of digit d inside the staged chunk */
+    uint32_t wtot[kSortWarps];
+};
+
 template <bool VALS>
 __global__ void __launch_bounds__(kSortThreads) k_sort_scatter(const uint64_t *__restrict__ keys,
                                                                const uint64_t *__restrict__ vals, uint64_t n,
@@ -75,13 +87,13 @@ __global__ void __launch_bounds__(kSortThreads) k_sort_scatter(const uint64_t *_
                                                                uint64_t *__restrict__ keys_out,
                                                                uint64_t *__restrict__ vals_out)
 {
-    __shared__ uint32_t wcnt[kSortWarps][256];
-    __shared__ uint64_t dbase[256];
-    const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    extern __shared__ __align__(16) unsigned char sort_smem_raw[];
+    SortSmem &s = *reinterpret_cast<SortSmem *>(sort_smem_raw);
+    const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const uint32_t lt = (1u << lane) - 1u;
-    dbase[threadIdx.x] = off[(uint64_t)threadIdx.x * gridDim.x + blockIdx.x];
+    s.dbase[tid] = off[(uint64_t)tid * gridDim.x + blockIdx.x];
 #pragma unroll
-    for (int w = 0; w < kSortWarps; ++w) wcnt[w][threadIdx.x] = 0;
+    for (int w = 0; w < kSortWarps; ++w) s.wcnt[w][tid] = 0;
     __syncthreads();
     const uint64_t beg = (uint64_t)blockIdx.x * per_cta, end = beg + per_cta < n ? beg + per_cta : n;
     for (uint64_t chunk = beg; chunk < end; chunk += kSortChunk) {
@@ -102,33 +114,59 @@ __global__ void __launch_bounds__(kSortThreads) k_sort_scatter(const uint64_t *_
                 peers &= ((d >> b) & 1u) ? vote : ~vote;
             }
             uint32_t base = 0;
-            if (ok) base = wcnt[warp][d];
+            if (ok) base = s.wcnt[warp][d];
             __syncwarp();
-            if (ok && (peers & lt) == 0) wcnt[warp][d] = base + __popc(peers); /* the lowest peer updates */
+            if (ok && (peers & lt) == 0) s.wcnt[warp][d] = base + __popc(peers); /* the lowest peer updates */
             __syncwarp();
             rk[j] = ok ? base + __popc(peers & lt) : 0xffffffffu;
         }
         __syncthreads();
-        uint32_t run = 0; /* thread d: keys of digit d per warp -> exclusive start of every warp */
+        uint32_t run = 0; /* thread d: keys of digit d per warp -> exclusive start of every warp inside the digit */
 #pragma unroll
         for (int w = 0; w < kSortWarps; ++w) {
-            const uint32_t t = wcnt[w][threadIdx.x];
-            wcnt[w][threadIdx.x] = run;
+            const uint32_t t = s.wcnt[w][tid];
+            s.wcnt[w][tid] = run;
             run += t;
         }
+        /* exclusive scan of the 256 digit totals -> start of every digit inside the staged chunk */
+        uint32_t inc = run;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const uint32_t y = __shfl_up_sync(0xffffffffu, inc, o);
+            if (lane >= o) inc += y;
+        }
+        if (lane == 31) s.wtot[warp] = inc;
+        __syncthreads();
+        uint32_t woff = 0, total = 0;
+#pragma unroll
+        for (int w = 0; w < kSortWarps; ++w) {
+            const uint32_t t = s.wtot[w];
+            if (w < (int)warp) woff += t;
+            total += t;
+        }
+        s.dstart[tid] = woff + inc - run;
+        if (tid == 0) s.dstart[256] = total;
         __syncthreads();
 #pragma unroll
         for (int j = 0; j < kSortItems; ++j) {
             if (rk[j] == 0xffffffffu) continue;
             const uint32_t d = (uint32_t)(x[j] >> shift) & 255u;
-            const uint64_t pos = dbase[d] + wcnt[warp][d] + rk[j];
-            keys_out[pos] = x[j];
-            if (VALS) vals_out[pos] = v[j];
+            const uint32_t pos = s.dstart[d] + s.wcnt[warp][d] + rk[j];
+            s.keys[pos] = x[j];
+            if (VALS) s.vals[pos] = v[j];
         }
         __syncthreads();
-        dbase[threadIdx.x] += run;
+        for (uint32_t i = tid; i < total; i += kSortThreads) {
+            const uint64_t key = s.keys[i];
+            const uint32_t d = (uint32_t)(key >> shift) & 255u;
+            const uint64_t pos = s.dbase[d] + (i - s.dstart[d]);
+            keys_out[pos] = key;
+            if (VALS) vals_out[pos] = s.vals[i];
+        }
+        __syncthreads();
+        s.dbase[tid] += run;
 #pragma unroll
-        for (int w = 0; w < kSortWarps; ++w) wcnt[w][threadIdx.x] = 0;
+        for (int w = 0; w < kSortWarps; ++w) s.wcnt[w][tid] = 0;
         __syncthreads();
     }
 }
