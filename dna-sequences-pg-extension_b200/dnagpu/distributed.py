@@ -234,7 +234,7 @@ def count_sharded_peer(ctx, seq, k, n_rows_total, world, rank, px, prefix=None, 
     run per (tile, digit)) -> barrier -> level 2 + count of the local receive buffer."""
     import torch
     import torch.distributed as dist
-    dev = torch.device("cuda", ctx.device)
+    dev = getattr(ctx, "torch_device", None) or torch.device("cuda", ctx.device)
     # a WHERE clause is evaluated once into a key list (one predicate scan); hist and scatter then read the list,
     # and the partition plan is sized by the rows that passed on all ranks, not by the rows scanned
     listed = ctx.collect(seq, k, prefix=prefix, pattern=pattern) if (prefix is not None or pattern is not None) else None

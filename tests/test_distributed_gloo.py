@@ -82,6 +82,94 @@ class OracleShuffleCtx:
         return st, None
 
 
+class OraclePeerCtx(OracleShuffleCtx):
+    """Test double for the peer exchange (count_sharded_peer + PeerExchange): receive buffers are POSIX shared
+    memory blocks mapped by every rank, addressed like device memory (a made-up base per owner + byte offset),
+    so the layout arithmetic, the barriers and the WHERE path run exactly as on the GPUs."""
+
+    def __init__(self, n_bases, seed, rank):
+        super().__init__(n_bases, seed)
+        self.rank, self.blocks, self.views = rank, [], {}
+
+    # ---- peer memory ----
+    def peer_alloc(self, n_bytes):
+        from multiprocessing import shared_memory
+        shm = shared_memory.SharedMemory(create=True, size=max(int(n_bytes), 16))
+        base = (self.rank + 1) << 44
+        self.blocks.append(shm)
+        self.views[base] = np.ndarray(shm.size // 8, dtype=np.uint64, buffer=shm.buf)
+        self.own = shm
+        return base, (shm.name, base)
+
+    def peer_open(self, handle):
+        from multiprocessing import shared_memory
+        name, base = handle
+        shm = shared_memory.SharedMemory(name=name)
+        self.blocks.append(shm)
+        self.views[base] = np.ndarray(shm.size // 8, dtype=np.uint64, buffer=shm.buf)
+        return base
+
+    def peer_close(self, addr):
+        self.views.pop(addr, None)
+
+    def peer_free(self, addr):
+        self.views.clear()
+        for shm in self.blocks:
+            shm.close()
+        self.own.unlink()
+
+    def _store(self, addr, rows):
+        base = int(addr) >> 44 << 44
+        off = (int(addr) - base) // 8
+        self.views[base][off:off + rows.size] = rows
+
+    # ---- what the kernels do ----
+    def _rows(self, seq, k, prefix=None, pattern=None):
+        from oracle import ref_cpu as R
+        first, starts = seq.shard
+        n_local = min(self.n_bases - first, starts + k - 1)
+        words = R.synth_seq(self.seed, self.n_bases, first_word=first // 32, n_words=(n_local + 31) // 32 + 1)
+        rows = R.generate_kmers(words, n_local, k, window=True)[:starts]
+        if prefix is not None:
+            pb, pl = R.kmer_make(prefix)
+            rows = rows[(rows & np.uint64((1 << (2 * pl)) - 1)) == np.uint64(pb)]
+        if pattern is not None:
+            rows = np.array([x for x in rows if R.contains(pattern, int(x), k)], dtype=np.uint64)
+        return rows
+
+    def _digits(self, rows, plan):
+        return np.array([((int(x) * self.MUL) & (2**64 - 1)) >> (64 - plan.bits1) for x in rows], dtype=np.int64)
+
+    def collect(self, seq, k, prefix=None, pattern=None):
+        return torch.from_numpy(self._rows(seq, k, prefix, pattern).view(np.int64).copy())
+
+    def shuffle_hist(self, seq, k, plan):
+        return self.shuffle_hist_keys(self.collect(seq, k), plan)
+
+    def shuffle_hist_keys(self, keys, plan):
+        rows = keys.numpy().view(np.uint64)
+        rows = rows[rows != np.uint64(2**64 - 1)]
+        return np.bincount(self._digits(rows, plan), minlength=plan.n_digits).astype(np.uint64)
+
+    def shuffle_scatter_to(self, seq, k, plan, digit_dest):
+        keys = self.collect(seq, k)
+        return keys.numel(), self.shuffle_scatter_keys_to(keys, plan, digit_dest)
+
+    def shuffle_scatter_keys_to(self, keys, plan, digit_dest):
+        rows = keys.numpy().view(np.uint64)
+        side = int((rows == np.uint64(2**64 - 1)).sum())
+        rows = rows[rows != np.uint64(2**64 - 1)]
+        digits = self._digits(rows, plan)
+        for d in np.unique(digits):
+            self._store(digit_dest[d], rows[digits == d])
+        return side
+
+    def shuffle_count_addr(self, addr, piece_counts, n_groups, plan, k):
+        n = int(np.sum(piece_counts))
+        keys = torch.from_numpy(self.views[int(addr)][:n].view(np.int64).copy())
+        return self.shuffle_count(keys, piece_counts, n_groups, plan, k)[0]
+
+
 class FakeSeq:
     def __init__(self, shard, k):
         self.shard, self.k = shard, k
@@ -99,6 +187,22 @@ def _worker_fused(rank, world, port, n_bases, k, seed, chunks, out):
     ctx = OracleShuffleCtx(n_bases, seed)
     seq = FakeSeq(shard_of(n_bases, k, world, rank), k)
     res = count_sharded_fused(ctx, seq, k, n_bases - k + 1, world, rank, {}, chunks=chunks)
+    if rank == 0:
+        out.put(res)
+    dist.destroy_process_group()
+
+
+def _worker_peer(rank, world, port, n_bases, k, seed, where, out):
+    for p in (ROOT, PKG):
+        sys.path.insert(0, p)
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from dnagpu.distributed import PeerExchange, count_sharded_peer, shard_of
+    ctx = OraclePeerCtx(n_bases, seed, rank)
+    seq = FakeSeq(shard_of(n_bases, k, world, rank), k)
+    px = PeerExchange(ctx, world, rank, n_bases)
+    res = [count_sharded_peer(ctx, seq, k, n_bases - k + 1, world, rank, px, **where) for _ in range(2)]  # buffers reused
+    px.close()
     if rank == 0:
         out.put(res)
     dist.destroy_process_group()
@@ -153,6 +257,30 @@ def test_two_rank_fused_exchange_equals_single_rank(n_bases, k, chunks):
     words = R.synth_seq(23, n_bases)
     want = R.count_query(words, 1, n_bases, words.size, k, faithful=False)
     assert tuple(got) == want.stats
+
+
+@pytest.mark.parametrize("n_bases,k,world,where", [(30_000, 31, 2, {}), (20_000, 21, 3, {}), (100, 32, 2, {}),
+                                                   (30_000, 9, 2, dict(prefix="AC")),
+                                                   (30_000, 9, 2, dict(prefix="G", pattern="NNNNWNNNS"))])
+def test_peer_exchange_equals_single_rank(n_bases, k, world, where):
+    """count_sharded_peer (bench.py's default N > 1 path): per-digit counts all-gathered, every rank stores its
+    runs at the computed offsets inside the owners' (here: shared-memory) buffers, barrier, count; with a WHERE
+    clause the key list is collected first and the plan is sized by the rows that passed on all ranks."""
+    from oracle import ref_cpu as R
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 29750 + (n_bases + k + world + len(where)) % 100
+    procs = [ctx.Process(target=_worker_peer, args=(r, world, port, n_bases, k, 29, where, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    got = q.get(timeout=180)
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    words = R.synth_seq(29, n_bases)
+    want = R.count_query(words, 1, n_bases, words.size, k, faithful=False, pattern=where.get("pattern"),
+                         prefix=R.kmer_make(where["prefix"]) if "prefix" in where else None)
+    assert [tuple(g) for g in got] == [want.stats, want.stats]
 
 
 def test_owner_digit_ranges_agree_with_the_library():
