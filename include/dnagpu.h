@@ -25,9 +25,15 @@
  *       (README.md:107-135, test.sql:95-119,140-154), i.e. PostgreSQL's
  *       HashAggregate driven by kmer_hash (dna.c:722-735) and kmer_eq
  *       (dna.c:655-668,686-696; opclass dna--1.0.sql:204-212).
+ *   dnagpu_collect
+ *       the same WHERE clauses when the row order does not matter (the input of
+ *       a GROUP BY or of the exchange between GPUs): one predicate scan.
  *   dnagpu_filter_keys
  *       the same two operators as a seq scan over a stored kmer column
  *       (SELECT ... WHERE kmer_sequence ^@ / @> / =, test.sql:186-262).
+ *   dnagpu_index_build / dnagpu_index_equal / dnagpu_index_search
+ *       CREATE INDEX ... USING spgist (kmer_sequence spgist_kmer_ops) and the index
+ *       scans it serves (dna.c:1137-1737, dna--1.0.sql:278-330, test.sql:186-262).
  *   dnagpu_encode_dna / dnagpu_seq_from_text / dnagpu_decode_dna
  *       dna_in -> dna_make: validate_dna_sequence (dna.c:159-171) + encode_dna
  *       (dna.c:114-128); dna_out -> decode_dna (dna.c:135-152).
