@@ -1842,9 +1842,9 @@ extern "C" int dnagpu_collect(dnagpu_ctx *ctx, const dnagpu_seq *seq, int k, con
     TRY(build_pred(ctx, filter, k, in.n, &in.p, &in.filtered));
     if (in.n == 0) return DNAGPU_OK;
     TRY(collect_rows(ctx, in, k, d_out, cap, n_out));
-    if (*n_out > cap)
+    if (d_out && *n_out > cap)
         return fail(ctx, DNAGPU_ECAPACITY, "collect needs room for %llu rows", (unsigned long long)*n_out);
-    return DNAGPU_OK;
+    return DNAGPU_OK; /* d_out == NULL: only the number of rows was asked for */
 }
 
 extern "C" int dnagpu_count(dnagpu_ctx *ctx, const dnagpu_seq *seq, int k,

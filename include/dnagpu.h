@@ -225,7 +225,8 @@ int dnagpu_filter(dnagpu_ctx *ctx, const dnagpu_seq *seq, int k,
                   uint64_t *n_out);
 /* The rows that pass the WHERE clause in NO particular order -- what a GROUP BY or an exchange
  * between GPUs needs; one predicate scan instead of the two of the ordered form.  Writes at most
- * cap rows; with more matches than cap returns DNAGPU_ECAPACITY and *n_out = the number needed. */
+ * cap rows; with more matches than cap returns DNAGPU_ECAPACITY and *n_out = the number needed.
+ * d_out may be NULL (cap 0): then only the number of matching rows is computed. */
 int dnagpu_collect(dnagpu_ctx *ctx, const dnagpu_seq *seq, int k, const dnagpu_where *filter,
                    uint64_t *d_out, uint64_t cap, uint64_t *n_out);
 /* The same predicates over a materialised kmer column (k the same for all
