@@ -226,12 +226,20 @@ class Context:
             raise DnaError(self.lib.dnagpu_last_error(None).decode(), code=rc)
         self.handle = h
         self.device = device
+        self.shares_torch_stream = bool(torch_stream)
         if torch_stream:
             import torch
             with torch.cuda.device(device):
                 s = torch.cuda.current_stream().cuda_stream
             # stream 0 is the legacy default stream: pass it through as "lent"
             _check(self.lib, self.handle, self.lib.dnagpu_set_stream(self.handle, C.c_void_p(s) if s else None))
+
+    def _after_torch(self):
+        """Call before handing a torch tensor to the library: unless the ctx runs on torch's stream, whatever torch
+        queued to produce the tensor (a copy from pageable memory, torch.cat, a fill) must have finished first."""
+        if not self.shares_torch_stream:
+            import torch
+            torch.cuda.current_stream(self.device).synchronize()
 
     def close(self):
         if getattr(self, "handle", None):
@@ -320,11 +328,13 @@ class Context:
 
     def wrap(self, tensor, n_bases):
         """Borrow a torch int64/uint64 CUDA tensor holding packed words (+ >= 1 zero pad word)."""
+        self._after_torch()
         h = C.c_void_p()
         self._ok(self.lib.dnagpu_seq_wrap(self.handle, tensor.data_ptr(), n_bases, tensor.numel(), C.byref(h)))
         return Seq(self, h, keep=tensor)
 
     def wrap_reads(self, tensor, n_reads, bases_per_read, stride_words):
+        self._after_torch()
         h = C.c_void_p()
         self._ok(self.lib.dnagpu_seq_wrap_reads(self.handle, tensor.data_ptr(), n_reads, bases_per_read,
                                                 stride_words, tensor.numel(), C.byref(h)))
@@ -430,6 +440,7 @@ class Context:
 
     def filter_keys(self, keys, k, prefix=None, pattern=None):
         """The same predicates over a materialised kmer column (torch int64 CUDA tensor), rows in column order."""
+        self._after_torch()
         import torch
         w, _keep = _where(prefix, pattern)
         wp = C.byref(w) if w is not None else None
@@ -447,6 +458,7 @@ class Context:
 
     def index_build(self, keys, k):
         """CREATE INDEX ... ON column(kmer): keys = torch int64 CUDA tensor of Kmer.bit_sequence, all of length k."""
+        self._after_torch()
         h = C.c_void_p()
         self._ok(self.lib.dnagpu_index_build(self.handle, keys.data_ptr(), keys.numel(), k, C.byref(h)))
         return Index(self, h)
@@ -472,6 +484,7 @@ class Context:
         return st, (Table(self, th) if table else None)
 
     def count_keys(self, keys, k, table=False, method=COUNT_AUTO, load_factor=0.0, expected_keys=0):
+        self._after_torch()
         o = self._opts(method, load_factor, expected_keys)
         st, th = Stats(), C.c_void_p()
         self._ok(self.lib.dnagpu_count_keys(self.handle, keys.data_ptr(), keys.numel(), k,
@@ -553,6 +566,7 @@ class Context:
         return counts, int(kept.value), int(side.value)
 
     def shuffle_count(self, keys, piece_counts, n_groups, plan, k, table=False):
+        self._after_torch()
         piece_counts = np.ascontiguousarray(piece_counts, dtype=np.uint64)
         st, th = Stats(), C.c_void_p()
         self._ok(self.lib.dnagpu_shuffle_count(self.handle, keys.data_ptr() if keys is not None else None,
@@ -595,12 +609,14 @@ class Context:
         return int(kept.value), int(side.value)
 
     def shuffle_hist_keys(self, keys, plan):
+        self._after_torch()
         counts = np.zeros(plan.n_digits, dtype=np.uint64)
         self._ok(self.lib.dnagpu_shuffle_hist_keys(self.handle, keys.data_ptr(), keys.numel(), C.byref(plan),
                                                    counts.ctypes.data_as(_lib.u64p)))
         return counts
 
     def shuffle_scatter_keys_to(self, keys, plan, digit_dest):
+        self._after_torch()
         digit_dest = np.ascontiguousarray(digit_dest, dtype=np.uint64)
         side = C.c_uint64()
         self._ok(self.lib.dnagpu_shuffle_scatter_keys_to(self.handle, keys.data_ptr(), keys.numel(), C.byref(plan),
