@@ -378,6 +378,20 @@ def run_b200(args):
         ms, e2e_s = t.tolist()
     assert reads or stats[0] == n_rows_total, (stats, n_rows_total)
     assert tuple(stats) == tuple(stats_e2e), (stats, stats_e2e)
+    # parity gate: the CPU oracle's answer for this exact workload (tests/golden/big_expected.json, produced by
+    # tests/golden/make_golden_big.py).  A run whose result differs prints NO line.
+    gold = None
+    if not args.n_bases:
+        try:
+            with open(os.path.join(ROOT, "tests", "golden", "big_expected.json")) as f:
+                gold = json.load(f).get({"c4": "c4", "c2": "c2", "c5": "c5_k31", "c3": "c3"}[args.workload])
+        except Exception:
+            gold = None
+        if gold is not None and tuple(stats) != (gold["total"], gold["distinct"], gold["unique"]):
+            if rank == 0:
+                print(f"bench: result {tuple(stats)} differs from the oracle's "
+                      f"{(gold['total'], gold['distinct'], gold['unique'])}: no line printed", file=sys.stderr)
+            return 1
 
     if rank == 0:
         value = n_rows_total * args.steps / (ms * 1e-3) / 1e9
@@ -448,7 +462,9 @@ def run_b200(args):
                         "fused": "level-1 layout + one NCCL all-to-all",
                         "routed": "dnagpu_partition + NCCL all-to-all + dnagpu_count_keys"}[args.exchange] + ")",
                        "load_factor": args.load_factor or 0.5},
-            "result": {"total": stats[0], "distinct": stats[1], "unique": stats[2]},
+            "result": {"total": stats[0], "distinct": stats[1], "unique": stats[2],
+                       "oracle": "equal to tests/golden/big_expected.json (CPU oracle at the full size)"
+                       if gold is not None else "not compared (size overridden or no golden entry)"},
             "e2e": {"value": e2e_value, "unit": "Gkmer/s", "steps": args.e2e_steps,
                     "ms_per_step": 1e3 * e2e_s / args.e2e_steps,
                     "h2d_bytes_per_step": int(8 * reads["n_reads"] * reads["stride"]) if reads

@@ -18,6 +18,7 @@
 #include <cstring>
 #include <new>
 #include <string>
+#include <unordered_set>
 #include <vector>
 
 #include "kernels.cuh"
@@ -42,7 +43,13 @@ struct dnagpu_ctx {
     unsigned long long *h_ctr = nullptr; /* pinned mirror */
     cudaStream_t copy_stream = nullptr; /* H2D of the host-buffer calls, overlapped with level 1 */
     bool profiling = false;
+    bool force_exact = false; /* DNAGPU_COUNT_FLAG_EXACT of the running query: no optimistic partition regions */
     std::vector<ProfRec> prof;
+    /* live child handles: dnagpu_destroy releases their device memory and orphans them (ctx = NULL), so a
+     * *_free that comes after the destroy only deletes the host struct */
+    std::unordered_set<dnagpu_seq *> seqs;
+    std::unordered_set<dnagpu_table *> tables;
+    std::unordered_set<dnagpu_index *> indexes;
     char err[512] = {0};
 };
 
@@ -60,6 +67,9 @@ struct dnagpu_seq {
     /* ragged */
     std::vector<uint64_t> h_n_bases;
     uint64_t *d_word_off = nullptr, *d_n_bases = nullptr;
+    /* pieces (kPieces): base-range shards, possibly in peer memory */
+    std::vector<const uint64_t *> piece_ptr;
+    std::vector<uint64_t> piece_first, piece_starts;
     int cached_k = 0;
     uint64_t *d_row_off = nullptr, *d_item_off = nullptr;
     uint64_t cached_rows = 0, cached_items = 0;
@@ -80,6 +90,14 @@ struct dnagpu_index {
 };
 
 static thread_local char g_err[512] = "";
+
+/* A/B switches of the kernel experiments (profiles/README.md): compiled in only with -DDNAGPU_TUNING
+ * (tools/try_alt_lib.sh); the product library reads no environment variables. */
+#ifdef DNAGPU_TUNING
+static inline const char *tune_env(const char *name) { return getenv(name); }
+#else
+static inline const char *tune_env(const char *) { return nullptr; }
+#endif
 
 static int fail(dnagpu_ctx *ctx, int code, const char *fmt, ...)
 {
@@ -294,6 +312,8 @@ extern "C" int dnagpu_create(dnagpu_ctx **out, int device)
                 per_sm > 0)
                 ctx->bins_ctas_per_sm = per_sm;
         }
+        cudaFuncSetAttribute(k_part_scatter_owned, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                             2 * kOwnList * (int)sizeof(uint64_t) + (int)sizeof(ScatterSmem));
         cudaFuncSetAttribute(k_sort_scatter<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(SortSmem));
         cudaFuncSetAttribute(k_sort_scatter<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(SortSmem));
         const int bsmem = kBucketSlots * 12;
@@ -305,10 +325,24 @@ extern "C" int dnagpu_create(dnagpu_ctx **out, int device)
     return DNAGPU_OK;
 }
 
+static void seq_release(dnagpu_seq *s);
+static void table_release(dnagpu_table *t);
+static void index_release(dnagpu_index *ix);
+
 extern "C" void dnagpu_destroy(dnagpu_ctx *ctx)
 {
     if (!ctx) return;
     cudaSetDevice(ctx->device);
+    cudaStreamSynchronize(ctx->stream);
+    if (ctx->copy_stream) cudaStreamSynchronize(ctx->copy_stream);
+    /* handles the caller still holds: their device memory goes now, the host structs stay valid (orphaned)
+     * until the caller frees them -- dnagpu_*_free after dnagpu_destroy is legal and touches no CUDA state */
+    for (dnagpu_seq *c : ctx->seqs) seq_release(c);
+    for (dnagpu_table *c : ctx->tables) table_release(c);
+    for (dnagpu_index *c : ctx->indexes) index_release(c);
+    ctx->seqs.clear();
+    ctx->tables.clear();
+    ctx->indexes.clear();
     cudaStreamSynchronize(ctx->stream);
     for (auto &r : ctx->prof) {
         cudaEventDestroy(r.e0);
@@ -387,7 +421,14 @@ static int seq_new(dnagpu_ctx *ctx, dnagpu_seq **out, dnagpu_seq **s)
     *s = new (std::nothrow) dnagpu_seq();
     if (!*s) return fail(ctx, DNAGPU_ENOMEM, "out of host memory");
     (*s)->ctx = ctx;
-    CU(ctx, cudaSetDevice(ctx->device));
+    ctx->seqs.insert(*s);
+    cudaError_t e = cudaSetDevice(ctx->device);
+    if (e != cudaSuccess) {
+        ctx->seqs.erase(*s);
+        delete *s;
+        *s = nullptr;
+        return fail(ctx, DNAGPU_ECUDA, "cudaSetDevice: %s", cudaGetErrorString(e));
+    }
     return DNAGPU_OK;
 }
 
@@ -403,18 +444,37 @@ static int seq_alloc_words(dnagpu_seq *s, uint64_t payload_words)
     return DNAGPU_OK;
 }
 
-extern "C" void dnagpu_seq_free(dnagpu_seq *s)
+/* give the device memory of a handle back and cut it loose from its ctx (the host struct stays) */
+static void seq_release(dnagpu_seq *s)
 {
-    if (!s) return;
     dnagpu_ctx *ctx = s->ctx;
+    if (!ctx) return;
     cudaSetDevice(ctx->device);
     if (s->own_words) dfree(ctx, s->d_words);
     dfree(ctx, s->d_word_off);
     dfree(ctx, s->d_n_bases);
     dfree(ctx, s->d_row_off);
     dfree(ctx, s->d_item_off);
+    s->d_words = s->d_word_off = s->d_n_bases = s->d_row_off = s->d_item_off = nullptr;
+    s->ctx = nullptr;
+}
+
+extern "C" void dnagpu_seq_free(dnagpu_seq *s)
+{
+    if (!s) return;
+    if (s->ctx) {
+        s->ctx->seqs.erase(s);
+        seq_release(s);
+    }
     delete s;
 }
+
+/* a child handle must belong to the (live) ctx it is used with */
+#define CHECK_OWNED(ctx, child, what)                                                              \
+    do {                                                                                           \
+        if ((child)->ctx != (ctx))                                                                 \
+            return fail(ctx, DNAGPU_EARG, what " belongs to another context or its context was destroyed"); \
+    } while (0)
 
 extern "C" int dnagpu_seq_upload(dnagpu_ctx *ctx, const uint64_t *words, uint64_t n_bases,
                                  dnagpu_seq **out)
@@ -422,7 +482,7 @@ extern "C" int dnagpu_seq_upload(dnagpu_ctx *ctx, const uint64_t *words, uint64_
     dnagpu_seq *s;
     TRY(seq_new(ctx, out, &s));
     if (!words && n_bases) {
-        delete s;
+        dnagpu_seq_free(s);
         return fail(ctx, DNAGPU_EARG, "dnagpu_seq_upload: words is NULL");
     }
     s->layout = kSingle;
@@ -431,6 +491,9 @@ extern "C" int dnagpu_seq_upload(dnagpu_ctx *ctx, const uint64_t *words, uint64_
     if (rc == DNAGPU_OK && s->n_words) {
         cudaError_t e = cudaMemcpyAsync(s->d_words, words, s->n_words * 8, cudaMemcpyHostToDevice,
                                         ctx->stream);
+        /* "Copies; the caller keeps ownership": from pinned memory the copy is truly asynchronous, so it
+         * must have left the caller's buffer before the call returns */
+        if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
         if (e != cudaSuccess) rc = fail(ctx, DNAGPU_ECUDA, "H2D copy: %s", cudaGetErrorString(e));
     }
     if (rc != DNAGPU_OK) {
@@ -448,7 +511,7 @@ extern "C" int dnagpu_seq_upload_reads(dnagpu_ctx *ctx, const uint64_t *words, u
     dnagpu_seq *s;
     TRY(seq_new(ctx, out, &s));
     if ((!words && n_reads) || stride_words < words_of(bases_per_read)) {
-        delete s;
+        dnagpu_seq_free(s);
         return fail(ctx, DNAGPU_EARG, "dnagpu_seq_upload_reads: NULL words or stride < words per read");
     }
     s->layout = kFixed;
@@ -459,6 +522,9 @@ extern "C" int dnagpu_seq_upload_reads(dnagpu_ctx *ctx, const uint64_t *words, u
     if (rc == DNAGPU_OK && s->n_words) {
         cudaError_t e = cudaMemcpyAsync(s->d_words, words, s->n_words * 8, cudaMemcpyHostToDevice,
                                         ctx->stream);
+        /* "Copies; the caller keeps ownership": from pinned memory the copy is truly asynchronous, so it
+         * must have left the caller's buffer before the call returns */
+        if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
         if (e != cudaSuccess) rc = fail(ctx, DNAGPU_ECUDA, "H2D copy: %s", cudaGetErrorString(e));
     }
     if (rc != DNAGPU_OK) {
@@ -476,7 +542,7 @@ extern "C" int dnagpu_seq_upload_ragged(dnagpu_ctx *ctx, const uint64_t *words,
     dnagpu_seq *s;
     TRY(seq_new(ctx, out, &s));
     if (n_seqs && (!words || !word_offsets || !n_bases)) {
-        delete s;
+        dnagpu_seq_free(s);
         return fail(ctx, DNAGPU_EARG, "dnagpu_seq_upload_ragged: NULL argument");
     }
     s->layout = kRagged;
@@ -610,6 +676,42 @@ extern "C" int dnagpu_seq_wrap_reads(dnagpu_ctx *ctx, const void *d_words, uint6
     return DNAGPU_OK;
 }
 
+extern "C" int dnagpu_seq_wrap_pieces(dnagpu_ctx *ctx, const void *const *d_words, const uint64_t *first_base,
+                                      const uint64_t *n_starts, uint32_t n_pieces, uint64_t n_bases_total,
+                                      dnagpu_seq **out)
+{
+    if (!ctx || !out || !d_words || !first_base || !n_starts || n_pieces < 1 || n_pieces > (uint32_t)kMaxPieces)
+        return fail(ctx, DNAGPU_EARG, "dnagpu_seq_wrap_pieces: NULL argument or more than %d pieces", kMaxPieces);
+    /* the ranges must tile the sequence: walk them in base order */
+    std::vector<uint32_t> order(n_pieces);
+    for (uint32_t i = 0; i < n_pieces; ++i) order[i] = i;
+    std::sort(order.begin(), order.end(), [&](uint32_t a, uint32_t b) { return first_base[a] < first_base[b]; });
+    uint64_t next = 0;
+    for (uint32_t q = 0; q < n_pieces; ++q) {
+        const uint32_t i = order[q];
+        if (!d_words[i] || ((uintptr_t)d_words[i] & 15) || (first_base[i] & 31) || first_base[i] != next ||
+            (q + 1 < n_pieces && (n_starts[i] & 31)))
+            return fail(ctx, DNAGPU_EARG,
+                        "piece %u: need a 16-byte aligned device pointer and base ranges (multiples of 32) that tile the sequence", i);
+        next += n_starts[i];
+    }
+    if (next < n_bases_total) return fail(ctx, DNAGPU_EARG, "the pieces cover %llu of %llu bases", (unsigned long long)next,
+                                         (unsigned long long)n_bases_total);
+    dnagpu_seq *s;
+    TRY(seq_new(ctx, out, &s));
+    s->layout = kPieces;
+    s->bases = n_bases_total;
+    s->own_words = false;
+    s->n_words = 0;
+    for (uint32_t i = 0; i < n_pieces; ++i) {
+        s->piece_ptr.push_back((const uint64_t *)d_words[i]);
+        s->piece_first.push_back(first_base[i]);
+        s->piece_starts.push_back(n_starts[i]);
+    }
+    *out = s;
+    return DNAGPU_OK;
+}
+
 extern "C" int dnagpu_seq_set_start_limit(dnagpu_seq *seq, uint64_t n_starts)
 {
     if (!seq || seq->layout != kSingle)
@@ -622,6 +724,7 @@ extern "C" int dnagpu_seq_download(dnagpu_ctx *ctx, const dnagpu_seq *seq, uint6
                                    uint64_t n_words)
 {
     if (!ctx || !seq || (!words && n_words)) return fail(ctx, DNAGPU_EARG, "NULL argument");
+    CHECK_OWNED(ctx, seq, "the sequence");
     if (n_words > seq->n_words) return fail(ctx, DNAGPU_EARG, "n_words exceeds the batch");
     CU(ctx, cudaSetDevice(ctx->device));
     if (n_words) CU(ctx, cudaMemcpyAsync(words, seq->d_words, n_words * 8, cudaMemcpyDeviceToHost, ctx->stream));
@@ -644,6 +747,7 @@ extern "C" uint64_t dnagpu_seq_kmer_count(const dnagpu_seq *seq, int k)
         return seq->start_limit ? std::min(r, seq->start_limit) : r;
     }
     if (seq->layout == kFixed) return seq->n_seqs * rows_of(seq->bases, k);
+    if (seq->layout == kPieces) return rows_of(seq->bases, k);
     uint64_t t = 0;
     for (uint64_t n : seq->h_n_bases) t += rows_of(n, k);
     return t;
@@ -653,6 +757,9 @@ extern "C" uint64_t dnagpu_seq_kmer_count(const dnagpu_seq *seq, int k)
 static int make_view(dnagpu_ctx *ctx, const dnagpu_seq *cseq, int k, SeqView *v)
 {
     dnagpu_seq *seq = const_cast<dnagpu_seq *>(cseq);
+    CHECK_OWNED(ctx, seq, "the sequence");
+    if (seq->layout == kPieces)
+        return fail(ctx, DNAGPU_EARG, "a sequence in pieces is only accepted by dnagpu_count with an owner restriction");
     memset(v, 0, sizeof *v);
     v->words = seq->d_words;
     v->n_seqs = seq->n_seqs;
@@ -868,7 +975,7 @@ extern "C" int dnagpu_extract(dnagpu_ctx *ctx, const dnagpu_seq *seq, int k, uin
         return fail(ctx, DNAGPU_ECAPACITY, "generate_kmers needs room for %llu rows",
                     (unsigned long long)v.n_rows);
     if ((uintptr_t)d_out & 15) return fail(ctx, DNAGPU_EARG, "d_out must be 16-byte aligned");
-    if (((uintptr_t)d_out & 31) == 0 && !getenv("DNAGPU_EXTRACT_PAIRS_ONLY")) { /* 256-bit stores */
+    if (((uintptr_t)d_out & 31) == 0 && !tune_env("DNAGPU_EXTRACT_PAIRS_ONLY")) { /* 256-bit stores */
         const unsigned grid = grid_for((v.n_rows + 3) / 4, (uint64_t)kThreads * kQuadsPerThread);
         DISPATCH_LAYOUT(seq->layout, TRY(launch(ctx, "extract", [&] {
             k_extract4<LY><<<grid, kThreads, 0, ctx->stream>>>(v, kmer_mask(k), d_out);
@@ -1057,6 +1164,7 @@ static int table_new(dnagpu_ctx *ctx, int k, uint64_t rows, dnagpu_table **out)
     dnagpu_table *t = new (std::nothrow) dnagpu_table();
     if (!t) return fail(ctx, DNAGPU_ENOMEM, "out of host memory");
     t->ctx = ctx;
+    ctx->tables.insert(t);
     t->k = k;
     t->rows = rows;
     int rc = dalloc(ctx, (void **)&t->d_kmers, rows * 8);
@@ -1224,11 +1332,11 @@ static int count_hash(dnagpu_ctx *ctx, const CountInput &in, int k, const dnagpu
 /* scatter tile: 16384 keys (one CTA per SM) when the fan-out makes 8192-key runs too short */
 static inline bool scatter_tile32(uint32_t fan, int level = 0)
 {
-    if (const char *e = getenv("DNAGPU_SCATTER_TILE")) return atoi(e) == 16384;
+    if (const char *e = tune_env("DNAGPU_SCATTER_TILE")) return atoi(e) == 16384;
     if (level == 1)
-        if (const char *e = getenv("DNAGPU_SCATTER_TILE_L1")) return atoi(e) == 16384;
+        if (const char *e = tune_env("DNAGPU_SCATTER_TILE_L1")) return atoi(e) == 16384;
     if (level == 2)
-        if (const char *e = getenv("DNAGPU_SCATTER_TILE_L2")) return atoi(e) == 16384;
+        if (const char *e = tune_env("DNAGPU_SCATTER_TILE_L2")) return atoi(e) == 16384;
     /* measured: from packed input (level 1) 16384-key tiles win at every fan-out (256: 15 %, 1024: 12 %, 2048: 2x);
      * from a key list they win 13 % at 2048, 1 % at 1024 and lose 10 % at 256 */
     return level == 1 || fan >= 1024;
@@ -1258,7 +1366,7 @@ static int ceil_log2(uint64_t x)
 /* number of hash bits so that a bucket averages at most half the slots of the shared-memory table */
 static int bucket_bits(uint64_t n)
 {
-    if (const char *e = getenv("DNAGPU_BUCKET_BITS")) /* profiling aid: force the fan-out */
+    if (const char *e = tune_env("DNAGPU_BUCKET_BITS")) /* profiling aid: force the fan-out */
         if (atoi(e) >= 1 && atoi(e) <= 22) return atoi(e);
     return std::max(1, std::min(22, ceil_log2((n + kBucketSlots / 2 - 1) / (kBucketSlots / 2)))); /* mean <= slots / 2 */
 }
@@ -1461,7 +1569,7 @@ static int part_finish_impl(dnagpu_ctx *ctx, Scratch &sc, const uint64_t *keys, 
     const int bsmem = kBucketSlots * 12;
     const unsigned cgrid = (unsigned)std::min<uint64_t>(n_buckets, (uint64_t)ctx->sm_count * (16384 / kBucketSlots));
     /* the aggregates: bin / place / compare for every bucket that fits, the table kernel for the rest */
-    static const bool use_bins = !getenv("DNAGPU_NO_BINS");
+    static const bool use_bins = !tune_env("DNAGPU_NO_BINS");
     if (use_bins) {
         uint32_t *passed;
         TRY(sc.get((void **)&passed, n_buckets * 4 + 16));
@@ -1534,8 +1642,8 @@ static int part_finish(dnagpu_ctx *ctx, Scratch &sc, const uint64_t *keys, uint6
                        dnagpu_stats *stats, uint64_t total_rows, dnagpu_table **table)
 {
     /* optimistic level 2 where no parents merge (one GPU) and the buckets are full-sized */
-    static const bool allow = !getenv("DNAGPU_EXACT_L2");
-    const bool optimistic2 = allow && b2 > 0 && n_groups == n_parents && (n >> (b1 + b2)) >= 512;
+    static const bool allow = !tune_env("DNAGPU_EXACT_L2");
+    const bool optimistic2 = allow && !ctx->force_exact && b2 > 0 && n_groups == n_parents && (n >> (b1 + b2)) >= 512;
     bool full = false;
     TRY(part_finish_impl(ctx, sc, keys, n, parent_off, parent_end, n_parents, n_groups, b1, b2, k, stats, total_rows, table,
                          optimistic2, &full));
@@ -1631,8 +1739,8 @@ static int count_partition_exact(dnagpu_ctx *ctx, const CountInput &in, int k, d
 static int count_partition(dnagpu_ctx *ctx, const CountInput &in, int k, dnagpu_stats *stats,
                            dnagpu_table **table)
 {
-    static const bool no_optimistic = getenv("DNAGPU_EXACT_LEVEL1") != nullptr;
-    if (in.d_keys || in.filtered || no_optimistic) return count_partition_exact(ctx, in, k, stats, table);
+    static const bool no_optimistic = tune_env("DNAGPU_EXACT_LEVEL1") != nullptr;
+    if (in.d_keys || in.filtered || no_optimistic || ctx->force_exact) return count_partition_exact(ctx, in, k, stats, table);
     {
         Scratch sc(ctx);
         int b1, b2;
@@ -1652,6 +1760,21 @@ static int count_partition(dnagpu_ctx *ctx, const CountInput &in, int k, dnagpu_
     return count_partition_exact(ctx, in, k, stats, table); /* a region overflowed: heavily repeated input */
 }
 
+/* one chunk of a pipelined upload: H2D on the copy stream, the compute stream waits for it.  Never returns
+ * early with an event outside `ev` (the callers destroy the events on every path). */
+static int chunk_copy(dnagpu_ctx *ctx, std::vector<cudaEvent_t> &ev, uint64_t *dst, const uint64_t *src, uint64_t bytes)
+{
+    cudaEvent_t e;
+    cudaError_t err = cudaEventCreateWithFlags(&e, cudaEventDisableTiming);
+    if (err != cudaSuccess) return fail(ctx, DNAGPU_ECUDA, "cudaEventCreate: %s", cudaGetErrorString(err));
+    ev.push_back(e);
+    err = cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, ctx->copy_stream);
+    if (err == cudaSuccess) err = cudaEventRecord(e, ctx->copy_stream);
+    if (err == cudaSuccess) err = cudaStreamWaitEvent(ctx->stream, e, 0);
+    if (err != cudaSuccess) return fail(ctx, DNAGPU_ECUDA, "pipelined H2D copy: %s", cudaGetErrorString(err));
+    return DNAGPU_OK;
+}
+
 /* The host-buffer query with the upload hidden behind level 1: the packed words are copied in chunks on
  * a second stream and every chunk is scattered as soon as it has landed (the optimistic level 1 needs no
  * histogram over the whole input first). */
@@ -1660,7 +1783,7 @@ static int count_kmers_pipelined(dnagpu_ctx *ctx, const uint64_t *words, uint64_
 {
     *done = false;
     const uint64_t rows = rows_of(n_bases, k), n_words = words_of(n_bases);
-    if (getenv("DNAGPU_EXACT_LEVEL1") || pick_method(nullptr, k, rows) != DNAGPU_COUNT_PARTITION) return DNAGPU_OK;
+    if (tune_env("DNAGPU_EXACT_LEVEL1") || pick_method(nullptr, k, rows) != DNAGPU_COUNT_PARTITION) return DNAGPU_OK;
     CU(ctx, cudaSetDevice(ctx->device));
     if (!ctx->copy_stream) CU(ctx, cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking));
     Scratch sc(ctx);
@@ -1680,12 +1803,8 @@ static int count_kmers_pipelined(dnagpu_ctx *ctx, const uint64_t *words, uint64_
     for (uint64_t w0 = 0; w0 < n_words && rc == DNAGPU_OK; w0 += chunk_words) {
         const uint64_t w1 = std::min(n_words, w0 + chunk_words);
         const uint64_t copy_end = std::min(n_words, w1 + 1); /* + the halo word of the chunk's last windows */
-        cudaEvent_t e;
-        CU(ctx, cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
-        ev.push_back(e);
-        CU(ctx, cudaMemcpyAsync(d_words + w0, words + w0, (copy_end - w0) * 8, cudaMemcpyHostToDevice, ctx->copy_stream));
-        CU(ctx, cudaEventRecord(e, ctx->copy_stream));
-        CU(ctx, cudaStreamWaitEvent(ctx->stream, e, 0));
+        rc = chunk_copy(ctx, ev, d_words + w0, words + w0, (copy_end - w0) * 8);
+        if (rc != DNAGPU_OK) break;
         const uint64_t row0 = w0 * 32, row1 = std::min(rows, w1 * 32);
         if (row1 <= row0) continue;
         SeqView v;
@@ -1698,7 +1817,9 @@ static int count_kmers_pipelined(dnagpu_ctx *ctx, const uint64_t *words, uint64_
     }
     if (rc == DNAGPU_OK) rc = l1_regions_end(ctx, r);
     if (rc == DNAGPU_OK) rc = part_finish(ctx, sc, r.keys, rows, r.beg, r.end, r.P1, r.P1, b1, b2, k, stats, 0, table);
+    /* on every path: the copy stream must be done with d_words before Scratch hands it back to the pool */
     cudaStreamSynchronize(ctx->copy_stream);
+    if (rc != DNAGPU_OK) cudaStreamSynchronize(ctx->stream);
     for (cudaEvent_t e : ev) cudaEventDestroy(e);
     TRY(rc);
     if (ctx->h_ctr[C_L1OVF]) { /* redo exactly, on the words that are resident now */
@@ -1737,6 +1858,115 @@ static int collect_rows(dnagpu_ctx *ctx, const CountInput &in, int k, uint64_t *
 
 static int count_dense_any(dnagpu_ctx *ctx, const CountInput &in, int k, dnagpu_stats *stats, dnagpu_table **table);
 static int count_partition(dnagpu_ctx *ctx, const CountInput &in, int k, dnagpu_stats *stats, dnagpu_table **table);
+static int count_listed(dnagpu_ctx *ctx, const uint64_t *keys, uint64_t n_match, int k, const dnagpu_count_opts *opts,
+                        dnagpu_stats *stats, dnagpu_table **table);
+
+/* ---- multi-GPU: the k-mers of one owner out of the whole sequence (k_part_scatter_owned) ------------------ */
+static int owned_view(dnagpu_ctx *ctx, const dnagpu_seq *seq, int k, OwnedView *ov)
+{
+    CHECK_OWNED(ctx, seq, "the sequence");
+    memset(ov, 0, sizeof *ov);
+    if (seq->layout == kSingle) {
+        uint64_t r = rows_of(seq->bases, k);
+        if (seq->start_limit) r = std::min(r, seq->start_limit);
+        ov->ptr[0] = seq->d_words;
+        ov->vfirst[1] = (r + 31) / 32;
+        ov->n_rows = r;
+        ov->n_pieces = 1;
+        return DNAGPU_OK;
+    }
+    if (seq->layout != kPieces)
+        return fail(ctx, DNAGPU_EARG, "an owner restriction applies to a single sequence (whole or in pieces)");
+    const uint64_t rows = rows_of(seq->bases, k);
+    ov->n_rows = rows;
+    ov->n_pieces = (uint32_t)seq->piece_ptr.size();
+    uint64_t v = 0;
+    for (uint32_t i = 0; i < ov->n_pieces; ++i) {
+        const uint64_t fb = seq->piece_first[i];
+        const uint64_t starts = rows > fb ? std::min(seq->piece_starts[i], rows - fb) : 0;
+        ov->ptr[i] = seq->piece_ptr[i];
+        ov->gfirst[i] = fb / 32;
+        ov->vfirst[i] = v;
+        v += (starts + 31) / 32;
+    }
+    ov->vfirst[ov->n_pieces] = v;
+    return DNAGPU_OK;
+}
+
+static int count_owned(dnagpu_ctx *ctx, const dnagpu_seq *seq, int k, const dnagpu_count_opts *opts, dnagpu_stats *stats,
+                       dnagpu_table **table)
+{
+    const uint32_t G = opts->owner_parts, me = opts->owner_part;
+    if (G > (uint32_t)kMaxParts || me >= G) return fail(ctx, DNAGPU_EARG, "owner_part must be below owner_parts <= %d", kMaxParts);
+    dnagpu_stats local;
+    if (!stats) stats = &local;
+    stats->total = stats->distinct = stats->unique = 0;
+    if (table) *table = nullptr;
+    OwnedView ov;
+    TRY(owned_view(ctx, seq, k, &ov));
+    if (ov.n_rows == 0) {
+        if (table) TRY(table_new(ctx, k, 0, table));
+        return DNAGPU_OK;
+    }
+    /* owner r holds the hashes [ceil(r 2^32 / G), ceil((r + 1) 2^32 / G)): what (hash * G) >> 32 == r says */
+    const uint64_t lo = (((uint64_t)me << 32) + G - 1) / G, hi = (((uint64_t)(me + 1) << 32) + G - 1) / G;
+    const uint32_t own_lo = (uint32_t)lo, own_span = (uint32_t)(hi - lo);
+    const uint64_t n_expect = ov.n_rows / G + 1;
+    const uint64_t n_vitems = ov.vfirst[ov.n_pieces];
+    const uint64_t mask = kmer_mask(k);
+    const bool exact = (opts->flags & DNAGPU_COUNT_FLAG_EXACT) != 0;
+    if (!exact) {
+        Scratch sc(ctx);
+        int b1, b2;
+        plan_bits(n_expect, 1, &b1, &b2);
+        if (b1 > 10) { /* the owned scatter keeps its per-lane dummy bins behind the digits: fan-out <= 1024 */
+            b2 = std::min(11, b2 + b1 - 10);
+            b1 = 10;
+        }
+        TRY(zero_counters(ctx));
+        L1Regions r;
+        TRY(l1_regions_begin(ctx, sc, n_expect, b1, &r));
+        const int wpt = (int)std::max<uint32_t>(1, G / 2);
+        const int smem = 2 * kOwnList * (int)sizeof(uint64_t) + (int)sizeof(ScatterSmem);
+        const unsigned grid = grid_for(n_vitems, (uint64_t)kScatThreads * wpt);
+        TRY(launch(ctx, "part_scatter_owned", [&] {
+            k_part_scatter_owned<<<grid, kScatThreads, smem, ctx->stream>>>(ov, mask, own_lo, own_span, wpt, 64 - b1, r.P1, r.beg,
+                                                                          r.cur, r.keys, ctx->d_ctr, r.cap);
+        }));
+        TRY(l1_regions_end(ctx, r));
+        ctx->force_exact = false;
+        TRY(part_finish(ctx, sc, r.keys, n_expect, r.beg, r.end, r.P1, r.P1, b1, b2, k, stats, 0, table));
+        if (!ctx->h_ctr[C_L1OVF]) return DNAGPU_OK;
+        if (table && *table) {
+            dnagpu_table_free(*table);
+            *table = nullptr;
+        }
+    }
+    /* exact form: the owned k-mers as a key list, then the exact key-list count */
+    Scratch sc(ctx);
+    uint64_t cap = n_expect + n_expect / 4 + 1024, n_own = 0, *keys = nullptr;
+    for (int attempt = 0; attempt < 2; ++attempt) {
+        TRY(sc.get((void **)&keys, (cap + 2) * 8));
+        TRY(zero_counters(ctx));
+        const unsigned grid = (unsigned)std::min<uint64_t>(grid_for(n_vitems, kScatThreads), (uint64_t)ctx->sm_count * 8);
+        TRY(launch(ctx, "collect_owned", [&] {
+            k_collect_owned<<<grid, kScatThreads, 0, ctx->stream>>>(ov, mask, own_lo, own_span, cap, ctx->d_ctr + C_CURSOR, keys);
+        }));
+        TRY(read_u64(ctx, (const uint64_t *)(ctx->d_ctr + C_CURSOR), &n_own));
+        if (n_own <= cap) break;
+        sc.release(keys);
+        dfree(ctx, keys);
+        cap = n_own;
+    }
+    if (n_own == 0) {
+        if (table) TRY(table_new(ctx, k, 0, table));
+        return DNAGPU_OK;
+    }
+    dnagpu_count_opts o2 = *opts;
+    o2.owner_parts = o2.owner_part = 0;
+    o2.method = DNAGPU_COUNT_AUTO;
+    return count_listed(ctx, keys, n_own, k, &o2, stats, table);
+}
 
 /* GROUP BY over a key list on the device (what a WHERE clause kept) */
 static int count_listed(dnagpu_ctx *ctx, const uint64_t *keys, uint64_t n_match, int k, const dnagpu_count_opts *opts,
@@ -1745,7 +1975,7 @@ static int count_listed(dnagpu_ctx *ctx, const uint64_t *keys, uint64_t n_match,
     CountInput listed;
     listed.d_keys = keys;
     listed.n = n_match;
-    dnagpu_count_opts o2 = opts ? *opts : dnagpu_count_opts{0, 0, 0.0, 0};
+    dnagpu_count_opts o2 = opts ? *opts : dnagpu_count_opts{0, 0, 0.0, 0, 0, 0};
     const int method = pick_method(&o2, k, n_match);
     int rc;
     if (method == DNAGPU_COUNT_DENSE)
@@ -1780,6 +2010,11 @@ static int count_any(dnagpu_ctx *ctx, CountInput &in, int k, const dnagpu_count_
     }
     int method = pick_method(opts, k, in.n);
     int rc;
+    struct ExactScope { /* the flag holds for this query only */
+        dnagpu_ctx *c;
+        ~ExactScope() { c->force_exact = false; }
+    } exact_scope{ctx};
+    ctx->force_exact = opts && (opts->flags & DNAGPU_COUNT_FLAG_EXACT);
     /* A selective WHERE clause: evaluate it once into an ordered key list (two cheap predicate
      * scans: count per tile, then write) and count that list, instead of dragging the whole
      * input through the partition / hash machinery only to drop most of it. */
@@ -1855,6 +2090,13 @@ extern "C" int dnagpu_count(dnagpu_ctx *ctx, const dnagpu_seq *seq, int k,
     TRY(check_k(ctx, k));
     TRY(check_filter_literals(ctx, filter));
     CU(ctx, cudaSetDevice(ctx->device));
+    if (opts && opts->owner_parts > 1) {
+        if (filter && (filter->prefix_len || filter->qkmer))
+            return fail(ctx, DNAGPU_EARG, "an owner restriction cannot be combined with a WHERE clause");
+        if (opts->method != DNAGPU_COUNT_AUTO && opts->method != DNAGPU_COUNT_PARTITION)
+            return fail(ctx, DNAGPU_EARG, "an owner restriction needs method AUTO or PARTITION");
+        return count_owned(ctx, seq, k, opts, stats, table);
+    }
     CountInput in;
     in.seq = seq;
     TRY(make_view(ctx, seq, k, &in.v));
@@ -1907,7 +2149,7 @@ static int count_reads_pipelined(dnagpu_ctx *ctx, const uint64_t *words, uint64_
     *done = false;
     const uint64_t rows_per_read = rows_of(bases_per_read, k), n = n_reads * rows_per_read;
     if (!words || n < (1ull << 24) || stride_words < words_of(bases_per_read) ||
-        pick_method(nullptr, k, n) == DNAGPU_COUNT_DENSE || getenv("DNAGPU_NO_READS_PIPELINE"))
+        pick_method(nullptr, k, n) == DNAGPU_COUNT_DENSE || tune_env("DNAGPU_NO_READS_PIPELINE"))
         return DNAGPU_OK;
     CU(ctx, cudaSetDevice(ctx->device));
     Pred p;
@@ -1930,13 +2172,8 @@ static int count_reads_pipelined(dnagpu_ctx *ctx, const uint64_t *words, uint64_
     int rc = DNAGPU_OK;
     for (uint64_t r0 = 0; r0 < n_reads && rc == DNAGPU_OK; r0 += chunk_reads) {
         const uint64_t r1 = std::min(n_reads, r0 + chunk_reads);
-        cudaEvent_t e;
-        CU(ctx, cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
-        ev.push_back(e);
-        CU(ctx, cudaMemcpyAsync(d_words + r0 * stride_words, words + r0 * stride_words, (r1 - r0) * stride_words * 8,
-                                cudaMemcpyHostToDevice, ctx->copy_stream));
-        CU(ctx, cudaEventRecord(e, ctx->copy_stream));
-        CU(ctx, cudaStreamWaitEvent(ctx->stream, e, 0));
+        rc = chunk_copy(ctx, ev, d_words + r0 * stride_words, words + r0 * stride_words, (r1 - r0) * stride_words * 8);
+        if (rc != DNAGPU_OK) break;
         SeqView v;
         memset(&v, 0, sizeof v);
         v.words = d_words + r0 * stride_words;
@@ -1950,7 +2187,9 @@ static int count_reads_pipelined(dnagpu_ctx *ctx, const uint64_t *words, uint64_
     }
     uint64_t n_match = 0;
     if (rc == DNAGPU_OK) rc = read_u64(ctx, (const uint64_t *)(ctx->d_ctr + C_CURSOR), &n_match);
+    /* on every path: the copy stream must be done with d_words before Scratch hands it back to the pool */
     cudaStreamSynchronize(ctx->copy_stream);
+    if (rc != DNAGPU_OK) cudaStreamSynchronize(ctx->stream);
     for (cudaEvent_t e : ev) cudaEventDestroy(e);
     TRY(rc);
     if (n_match > cap) { /* not selective after all: the ordinary path, on the words that are resident now */
@@ -1998,6 +2237,7 @@ extern "C" int dnagpu_table_fetch(dnagpu_ctx *ctx, const dnagpu_table *t, uint64
                                   uint64_t n, uint64_t *kmers, uint64_t *counts)
 {
     if (!ctx || !t) return fail(ctx, DNAGPU_EARG, "dnagpu_table_fetch: NULL argument");
+    CHECK_OWNED(ctx, t, "the table");
     if (offset > t->rows || n > t->rows - offset) return fail(ctx, DNAGPU_EARG, "row range outside the table");
     CU(ctx, cudaSetDevice(ctx->device));
     if (n && kmers) CU(ctx, cudaMemcpyAsync(kmers, t->d_kmers + offset, n * 8, cudaMemcpyDeviceToHost, ctx->stream));
@@ -2015,19 +2255,30 @@ extern "C" int dnagpu_table_device(const dnagpu_table *t, const uint64_t **d_kme
     return DNAGPU_OK;
 }
 
-extern "C" void dnagpu_table_free(dnagpu_table *t)
+static void table_release(dnagpu_table *t)
 {
-    if (!t) return;
+    if (!t->ctx) return;
     cudaSetDevice(t->ctx->device);
     dfree(t->ctx, t->d_kmers);
     dfree(t->ctx, t->d_counts);
+    t->d_kmers = t->d_counts = nullptr;
+    t->ctx = nullptr;
+}
+
+extern "C" void dnagpu_table_free(dnagpu_table *t)
+{
+    if (!t) return;
+    if (t->ctx) {
+        t->ctx->tables.erase(t);
+        table_release(t);
+    }
     delete t;
 }
 
 /* ---- owner routing --------------------------------------------------------------------------- */
 extern "C" uint32_t dnagpu_owner_of(uint64_t kmer, uint32_t n_parts)
 {
-    return owner_of(mix64(kmer), n_parts);
+    return owner_of(kmer, n_parts ? n_parts : 1);
 }
 
 extern "C" int dnagpu_partition(dnagpu_ctx *ctx, const dnagpu_seq *seq, int k,
@@ -2423,6 +2674,7 @@ extern "C" int dnagpu_index_build(dnagpu_ctx *ctx, const uint64_t *d_keys, uint6
     dnagpu_index *ix = new (std::nothrow) dnagpu_index;
     if (!ix) return fail(ctx, DNAGPU_ENOMEM, "out of host memory");
     ix->ctx = ctx;
+    ctx->indexes.insert(ix);
     ix->k = k;
     ix->rows = n;
     int rc = DNAGPU_OK;
@@ -2456,13 +2708,22 @@ extern "C" int dnagpu_index_build(dnagpu_ctx *ctx, const uint64_t *d_keys, uint6
     return DNAGPU_OK;
 }
 
+static void index_release(dnagpu_index *ix)
+{
+    if (!ix->ctx) return;
+    cudaSetDevice(ix->ctx->device);
+    dfree(ix->ctx, ix->d_skeys);
+    dfree(ix->ctx, ix->d_rows);
+    ix->d_skeys = ix->d_rows = nullptr;
+    ix->ctx = nullptr;
+}
+
 extern "C" void dnagpu_index_free(dnagpu_index *ix)
 {
     if (!ix) return;
     if (ix->ctx) {
-        cudaSetDevice(ix->ctx->device);
-        dfree(ix->ctx, ix->d_skeys);
-        dfree(ix->ctx, ix->d_rows);
+        ix->ctx->indexes.erase(ix);
+        index_release(ix);
     }
     delete ix;
 }
@@ -2517,6 +2778,7 @@ extern "C" int dnagpu_index_equal(dnagpu_ctx *ctx, const dnagpu_index *ix, uint6
                                   uint64_t *d_rows, uint64_t cap, uint64_t *n_out)
 {
     if (!ctx || !ix || !n_out) return fail(ctx, DNAGPU_EARG, "dnagpu_index_equal: NULL argument");
+    CHECK_OWNED(ctx, ix, "the index");
     CU(ctx, cudaSetDevice(ctx->device));
     *n_out = 0;
     /* kmer_eq compares the lengths first (dna.c:655-668): a k-mer of another length equals no row */
@@ -2532,6 +2794,7 @@ extern "C" int dnagpu_index_search(dnagpu_ctx *ctx, const dnagpu_index *ix, cons
                                    uint64_t cap, uint64_t *n_out)
 {
     if (!ctx || !ix || !n_out) return fail(ctx, DNAGPU_EARG, "dnagpu_index_search: NULL argument");
+    CHECK_OWNED(ctx, ix, "the index");
     CU(ctx, cudaSetDevice(ctx->device));
     *n_out = 0;
     TRY(check_filter_literals(ctx, where));

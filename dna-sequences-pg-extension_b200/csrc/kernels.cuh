@@ -26,7 +26,7 @@ namespace dnagpu {
 constexpr int kThreads = 256;
 constexpr uint64_t kEmpty = ~0ull; /* hash-slot sentinel; a real k-mer only for k = 32 ('G' x 32) */
 
-enum Layout { kSingle = 0, kFixed = 1, kRagged = 2 };
+enum Layout { kSingle = 0, kFixed = 1, kRagged = 2, kPieces = 3 /* host side only: see OwnedView */ };
 
 /* Device view of a dnagpu_seq for one value of k. */
 struct SeqView {
@@ -63,10 +63,16 @@ __host__ __device__ __forceinline__ uint64_t mix64(uint64_t x)
     x ^= x >> 33;
     return x;
 }
-/* owner rank: low half of the hash; table slot: high bits (mulhi) -> independent */
-__host__ __device__ __forceinline__ uint32_t owner_of(uint64_t h, uint32_t n_parts)
+/* Owner rank of a k-mer among n_parts GPUs: a multiplicative hash of the k-mer's low word (its first 16
+ * bases; the whole k-mer for k <= 16), top bits -> rank.  One IMAD per start position, because the
+ * multi-GPU count tests EVERY start position of the sequence for ownership (k_part_scatter_owned) and
+ * keeps one in n_parts.  Independent of the partition digits (64-bit multiply-shift over the whole
+ * k-mer) and of the bucket / bin hashes (fold of both words, another multiplier). */
+constexpr uint32_t kOwnerMul = 0x85EBCA6Bu;
+__host__ __device__ __forceinline__ uint32_t owner_hash(uint64_t kmer) { return (uint32_t)kmer * kOwnerMul; }
+__host__ __device__ __forceinline__ uint32_t owner_of(uint64_t kmer, uint32_t n_parts)
 {
-    return (uint32_t)(((h & 0xffffffffull) * (uint64_t)n_parts) >> 32);
+    return (uint32_t)(((uint64_t)owner_hash(kmer) * (uint64_t)n_parts) >> 32);
 }
 
 __device__ __forceinline__ bool pred_ok(const Pred &p, uint64_t x)
@@ -878,7 +884,7 @@ __global__ void __launch_bounds__(kThreads) k_dense_compact(const CT *__restrict
 
 /* =================================================================================
  * K6  owner routing for the multi-GPU GROUP BY: bucket k-mers by
- * owner_of(mix64(kmer)).  Pass 1 counts per owner; pass 2 claims one contiguous
+ * owner_of(kmer).  Pass 1 counts per owner; pass 2 claims one contiguous
  * run per (CTA, owner) with a single atomic per owner, ranks inside the CTA in
  * shared memory, and writes each run coalesced.
  * ================================================================================= */
@@ -900,7 +906,7 @@ __global__ void __launch_bounds__(kThreads) k_partition_count(SeqView sv, Pred p
         uint64_t w0 = ld_nc(w), w1 = ld_nc(w + 1);
         roll_item<8>(w0, w1, c, [&](uint64_t x, int) {
             if (FILTER && !pred_ok(p, x)) return;
-            atomicAdd(&cnt[owner_of(mix64(x & mask), n_parts)], 1u);
+            atomicAdd(&cnt[owner_of(x & mask, n_parts)], 1u);
         });
     }
     __syncthreads();
@@ -930,7 +936,7 @@ __global__ void __launch_bounds__(kThreads) k_partition_write(SeqView sv, Pred p
         w1 = ld_nc(w + 1);
         roll_item<8>(w0, w1, c, [&](uint64_t x, int) {
             if (FILTER && !pred_ok(p, x)) return;
-            atomicAdd(&cnt[owner_of(mix64(x & mask), n_parts)], 1u);
+            atomicAdd(&cnt[owner_of(x & mask, n_parts)], 1u);
         });
     }
     __syncthreads();
@@ -949,7 +955,7 @@ __global__ void __launch_bounds__(kThreads) k_partition_write(SeqView sv, Pred p
     roll_item<8>(w0, w1, c, [&](uint64_t x, int) {
         if (FILTER && !pred_ok(p, x)) return;
         uint64_t key = x & mask;
-        uint32_t o = owner_of(mix64(key), n_parts);
+        uint32_t o = owner_of(key, n_parts);
         stage[loc[o] + atomicAdd(&fill[o], 1u)] = key;
     });
     __syncthreads();

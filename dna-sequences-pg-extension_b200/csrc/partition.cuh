@@ -422,6 +422,204 @@ __global__ void __launch_bounds__(kScatThreads, (PER == 16 ? 2 : 1)) k_part_scat
     }
 }
 
+/* ---- multi-GPU level 1: every GPU reads the WHOLE sequence and keeps the k-mers it owns ---------------
+ * The sequence is resident as base-range shards, one per GPU, each with its (k-1)-base overlap and each
+ * mapped into every GPU's address space (peer memory over NVLink).  What crosses NVLink is the 2-bit
+ * packed bases (0.25 B per start position) instead of 8-byte k-mers: GPU g walks all pieces -- its own
+ * first, the others in ring order so that no shard is read by everybody at once -- tests every start
+ * position for owner_of(kmer) == g with one IMAD on the window's low word, and scatters the ones it keeps
+ * exactly like the single-GPU level 1 (optimistic regions, one run per (tile, digit)).  There is no
+ * exchange step and nothing to merge: level 2 and the bucket count then run on local data only.
+ *
+ * A CTA examines 512 * wpt packed words (wpt = n_parts / 2, so that it keeps ~ 8192 k-mers).  Kept k-mers
+ * are appended to a shared-memory list -- a compact segment per warp, filled through a warp scan of the
+ * per-word keep masks, plus a small shared overflow area -- and then read back lane-strided, so the rank /
+ * place / flush phases work on balanced, statically indexed register arrays. */
+constexpr int kMaxPieces = 16;
+constexpr int kOwnSeg = 576;                                   /* list slots of one warp (mean 512, sigma ~ 21) */
+constexpr int kOwnPer = kOwnSeg / 32;                          /* 18 keys per lane from the warp's segment      */
+constexpr int kOwnOvf = 1024;                                  /* shared overflow slots                         */
+constexpr int kOwnOvfPer = kOwnOvf / kScatThreads;             /* 2 per thread                                  */
+constexpr int kOwnList = (kScatThreads / 32) * kOwnSeg + kOwnOvf; /* 10240 keys                                 */
+constexpr int kOwnRows = kOwnPer + kOwnOvfPer;                 /* keys one thread ranks and places              */
+constexpr uint32_t kOwnMaxFan = 1024;                          /* cur[fan .. fan + 31] are the per-lane dummies */
+
+struct OwnedView {
+    const uint64_t *ptr[kMaxPieces];  /* first packed word of piece i (local or peer-mapped)                      */
+    uint64_t vfirst[kMaxPieces + 1];  /* this GPU walks the items in the order of its piece list: [vfirst[i], vfirst[i+1]) */
+    uint64_t gfirst[kMaxPieces];      /* index of the piece's first item (= packed word) in the whole sequence     */
+    uint64_t n_rows;                  /* generate_kmers rows of the whole sequence                                */
+    uint32_t n_pieces;
+};
+
+/* bit j of the result: start j of the item (w0, w1) is a k-mer this GPU owns */
+__device__ __forceinline__ uint32_t owned_mask(uint64_t w0, uint64_t w1, uint32_t mask_lo, uint32_t own_lo,
+                                               uint32_t own_span)
+{
+    const uint32_t a0 = (uint32_t)w0, a1 = (uint32_t)(w0 >> 32), a2 = (uint32_t)w1;
+    uint32_t km = 0;
+#pragma unroll
+    for (int j = 0; j < 32; ++j) {
+        const uint32_t lo = j == 0 ? a0 : j < 16 ? __funnelshift_r(a0, a1, 2 * j) : j == 16 ? a1
+                                                                                             : __funnelshift_r(a1, a2, 2 * j - 32);
+        const uint32_t h = (lo & mask_lo) * kOwnerMul;
+        km |= (uint32_t)((h - own_lo) < own_span) << j;
+    }
+    return km;
+}
+
+/* virtual item v -> packed words and number of valid starts */
+__device__ __forceinline__ int owned_item(const OwnedView &ov, uint64_t v, uint64_t &w0, uint64_t &w1)
+{
+    uint32_t i = 0;
+    while (i + 1 < ov.n_pieces && v >= ov.vfirst[i + 1]) ++i;
+    const uint64_t off = v - ov.vfirst[i];
+    const uint64_t *w = ov.ptr[i] + off;
+    w0 = ld_nc(w);
+    w1 = ld_nc(w + 1);
+    const uint64_t left = ov.n_rows - (ov.gfirst[i] + off) * 32;
+    return left < 32 ? (int)left : 32;
+}
+
+__global__ void __launch_bounds__(kScatThreads, 1) k_part_scatter_owned(OwnedView ov, uint64_t mask, uint32_t own_lo,
+                                                                       uint32_t own_span, int wpt, int shift,
+                                                                       uint32_t fan,
+                                                                       const uint64_t *__restrict__ child_off,
+                                                                       unsigned long long *__restrict__ child_cur,
+                                                                       uint64_t *__restrict__ out,
+                                                                       unsigned long long *__restrict__ ctr,
+                                                                       uint64_t cap)
+{
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    uint64_t *list = reinterpret_cast<uint64_t *>(smem_raw);
+    uint64_t *stage = list + kOwnList;
+    ScatterSmem &s = *reinterpret_cast<ScatterSmem *>(smem_raw + sizeof(uint64_t) * 2 * kOwnList);
+    __shared__ uint32_t n_ovf_s;
+    const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    for (uint32_t i = tid; i < fan + 32; i += kScatThreads) s.cur[i] = 0;
+    if (tid == 0) n_ovf_s = 0;
+    __syncthreads();
+    const uint32_t fm = fan - 1, mask_lo = (uint32_t)mask;
+    const uint64_t n_vitems = ov.vfirst[ov.n_pieces];
+    const uint64_t v0 = (uint64_t)blockIdx.x * ((uint64_t)kScatThreads * wpt);
+    uint32_t wcur = 0, kept = 0, side = 0;
+    /* phase 1: keep masks, warp scan, append */
+    for (int it = 0; it < wpt; ++it) {
+        const uint64_t v = v0 + (uint64_t)it * kScatThreads + tid;
+        uint64_t w0 = 0, w1 = 0;
+        uint32_t km = 0;
+        if (v < n_vitems) {
+            const int c = owned_item(ov, v, w0, w1);
+            km = owned_mask(w0, w1, mask_lo, own_lo, own_span);
+            if (c < 32) km &= (1u << c) - 1u;
+        }
+        const uint32_t n = __popc(km);
+        uint32_t inc = n;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const uint32_t y = __shfl_up_sync(0xffffffffu, inc, o);
+            if (lane >= (uint32_t)o) inc += y;
+        }
+        uint32_t p = wcur + inc - n;
+        wcur += __shfl_sync(0xffffffffu, inc, 31);
+        kept += n;
+        while (km) {
+            const int j = __ffs(km) - 1;
+            km &= km - 1;
+            const uint64_t x = window(w0, w1, 2 * j) & mask;
+            side += x == kEmpty; /* 'G' x 32 (k = 32): stays in the list as a slot that is not scattered */
+            if (p < (uint32_t)kOwnSeg) {
+                list[warp * kOwnSeg + p] = x;
+            } else {
+                const uint32_t q = atomicAdd(&n_ovf_s, 1u);
+                if (q < (uint32_t)kOwnOvf) list[(kScatThreads / 32) * kOwnSeg + q] = x;
+            }
+            ++p;
+        }
+    }
+    __syncthreads();
+    const uint32_t n_ovf = n_ovf_s;
+    if (n_ovf > (uint32_t)kOwnOvf && tid == 0) atomicExch(&ctr[C_L1OVF], 1ull); /* keys were dropped: the caller redoes exactly */
+    const uint32_t wn = min(wcur, (uint32_t)kOwnSeg), on = min(n_ovf, (uint32_t)kOwnOvf);
+    /* phase 2: balanced read-back, then rank / plan / place / flush as in the local scatter */
+    uint64_t x[kOwnRows];
+    uint32_t rk[kOwnRows / 2];
+#pragma unroll
+    for (int u = 0; u < kOwnPer; ++u) {
+        const uint32_t idx = (uint32_t)u * 32 + lane;
+        x[u] = idx < wn ? list[warp * kOwnSeg + idx] : kEmpty;
+    }
+#pragma unroll
+    for (int u = 0; u < kOwnOvfPer; ++u) {
+        const uint32_t idx = (uint32_t)u * kScatThreads + tid;
+        x[kOwnPer + u] = idx < on ? list[(kScatThreads / 32) * kOwnSeg + idx] : kEmpty;
+    }
+#pragma unroll
+    for (int u = 0; u < kOwnRows; ++u) {
+        const uint32_t d = x[u] != kEmpty ? digit_of(part_hash(x[u]), shift, fm) : fan + lane;
+        const uint32_t r = atomicAdd(&s.cur[d], 1u);
+        rk[u >> 1] = (u & 1) ? __byte_perm(rk[u >> 1], r, 0x5410) : r;
+    }
+    __syncthreads();
+    ScatterClaim cl;
+    const uint32_t total = scatter_plan(s, fan, child_cur, cl);
+#pragma unroll
+    for (int u = 0; u < kOwnRows; ++u) {
+        const uint32_t r = (u & 1) ? (rk[u >> 1] >> 16) : (rk[u >> 1] & 0xffffu);
+        if (x[u] != kEmpty) stage[s.cur[digit_of(part_hash(x[u]), shift, fm)] + r] = x[u];
+    }
+    scatter_publish(s, fan, child_off, cl, cap, ctr);
+    __syncthreads();
+    scatter_flush<kOwnRows>(s, stage, total, shift, fm, out);
+    kept = warp_sum32(kept);
+    side = warp_sum32(side);
+    if (lane == 0) {
+        if (kept) atomicAdd(&ctr[C_TOTAL], (unsigned long long)kept);
+        if (side) atomicAdd(&ctr[C_SIDE], (unsigned long long)side);
+    }
+}
+
+/* The exact fallback of the owned count (a region or a list overflowed: heavily repeated input): the owned
+ * k-mers as a plain key list, appended warp by warp through one cursor; tiles past `cap` write nothing but
+ * still count, so the caller can retry with a buffer of the right size.  The list is then counted by the
+ * exact key-list path. */
+__global__ void __launch_bounds__(kScatThreads) k_collect_owned(OwnedView ov, uint64_t mask, uint32_t own_lo,
+                                                                uint32_t own_span, uint64_t cap,
+                                                                unsigned long long *__restrict__ cursor,
+                                                                uint64_t *__restrict__ out)
+{
+    const uint32_t lane = threadIdx.x & 31;
+    const uint64_t n_vitems = ov.vfirst[ov.n_pieces];
+    for (uint64_t vb = (uint64_t)blockIdx.x * kScatThreads; vb < n_vitems; vb += (uint64_t)gridDim.x * kScatThreads) {
+        const uint64_t v = vb + threadIdx.x;
+        uint64_t w0 = 0, w1 = 0;
+        uint32_t km = 0;
+        if (v < n_vitems) {
+            const int c = owned_item(ov, v, w0, w1);
+            km = owned_mask(w0, w1, (uint32_t)mask, own_lo, own_span);
+            if (c < 32) km &= (1u << c) - 1u;
+        }
+        const uint32_t n = __popc(km);
+        uint32_t inc = n;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const uint32_t y = __shfl_up_sync(0xffffffffu, inc, o);
+            if (lane >= (uint32_t)o) inc += y;
+        }
+        const uint32_t wtotal = __shfl_sync(0xffffffffu, inc, 31);
+        unsigned long long base = 0;
+        if (lane == 31 && wtotal) base = atomicAdd(cursor, (unsigned long long)wtotal);
+        base = __shfl_sync(0xffffffffu, base, 31);
+        if (base + wtotal > cap) continue; /* warp-uniform */
+        uint64_t p = base + inc - n;
+        while (km) {
+            const int j = __ffs(km) - 1;
+            km &= km - 1;
+            out[p++] = window(w0, w1, 2 * j) & mask;
+        }
+    }
+}
+
 /* ---- count: one bucket at a time in a shared-memory table ------------------------------------- */
 constexpr int kPre = kBucketSlots / 2 / kThreads; /* keys per thread fetched one bucket ahead (covers the mean bucket) */
 

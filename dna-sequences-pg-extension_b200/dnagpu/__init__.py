@@ -9,6 +9,7 @@ in include/dnagpu.h; this package only marshals buffers.  Nothing here falls
 back to the CPU: without the built library or without a B200 it raises.
 """
 import ctypes as C
+import weakref
 from dataclasses import dataclass
 
 import numpy as np
@@ -18,6 +19,7 @@ from ._lib import CountOpts, ShufflePlan, Stats, Where
 from .types import Dna, DnaError, Kmer, Qkmer, QKMER_ALPHABET, kmer_strings
 
 COUNT_AUTO, COUNT_DENSE, COUNT_HASH, COUNT_PARTITION = 0, 1, 2, 3
+COUNT_FLAG_EXACT = 1  # DNAGPU_COUNT_FLAG_EXACT: exact two-pass partition levels from the start
 MAX_K = 32
 
 __all__ = ["Context", "Seq", "Table", "Dna", "Kmer", "Qkmer", "DnaError", "KmerArray",
@@ -67,6 +69,7 @@ class Seq:
 
     def __init__(self, ctx, handle, keep=None):
         self.ctx, self.handle, self._keep = ctx, handle, keep
+        ctx._children.add(self)
 
     def kmer_count(self, k):
         return int(self.ctx.lib.dnagpu_seq_kmer_count(self.handle, k))
@@ -105,6 +108,7 @@ class Table:
 
     def __init__(self, ctx, handle):
         self.ctx, self.handle = ctx, handle
+        ctx._children.add(self)
 
     @property
     def rows(self):
@@ -151,6 +155,7 @@ class Index:
 
     def __init__(self, ctx, handle):
         self.ctx, self.handle = ctx, handle
+        ctx._children.add(self)
 
     @property
     def rows(self):
@@ -168,6 +173,7 @@ class Index:
         out = torch.empty(max(int(n.value), 1), dtype=torch.int64, device=f"cuda:{self.ctx.device}")
         if n.value:
             self.ctx._ok(call(out.data_ptr(), out.numel(), C.byref(n)))
+        self.ctx._before_torch()
         return out[:n.value]
 
     def equal(self, kmer):
@@ -220,6 +226,7 @@ class Context:
 
     def __init__(self, device=0, torch_stream=False):
         self.lib = _lib.load()
+        self._children = weakref.WeakSet()  # live Seq / Table / Index objects (freed by close())
         h = C.c_void_p()
         rc = self.lib.dnagpu_create(C.byref(h), device)
         if rc != 0:
@@ -231,8 +238,9 @@ class Context:
             import torch
             with torch.cuda.device(device):
                 s = torch.cuda.current_stream().cuda_stream
-            # stream 0 is the legacy default stream: pass it through as "lent"
-            _check(self.lib, self.handle, self.lib.dnagpu_set_stream(self.handle, C.c_void_p(s) if s else None))
+            # handle 0 is torch's legacy default stream; NULL would mean "the library's own stream", so lend
+            # cudaStreamLegacy (0x1), which names the same stream explicitly
+            _check(self.lib, self.handle, self.lib.dnagpu_set_stream(self.handle, C.c_void_p(s if s else 1)))
 
     def _after_torch(self):
         """Call before handing a torch tensor to the library: unless the ctx runs on torch's stream, whatever torch
@@ -241,8 +249,19 @@ class Context:
             import torch
             torch.cuda.current_stream(self.device).synchronize()
 
+    def _before_torch(self):
+        """Call before returning a torch tensor the library wrote: unless the ctx runs on torch's stream, the
+        kernel that fills it is still queued on the library's own (non-blocking) stream, which torch's streams do
+        not order against."""
+        if not self.shares_torch_stream:
+            self.synchronize()
+
     def close(self):
+        """dnagpu_destroy.  Seq / Table / Index objects that are still alive are freed first (their device memory
+        belongs to the context); using them afterwards raises, dropping them is harmless."""
         if getattr(self, "handle", None):
+            for child in list(getattr(self, "_children", ())):
+                child.free()
             self.lib.dnagpu_destroy(self.handle)
             self.handle = None
 
@@ -333,6 +352,18 @@ class Context:
         self._ok(self.lib.dnagpu_seq_wrap(self.handle, tensor.data_ptr(), n_bases, tensor.numel(), C.byref(h)))
         return Seq(self, h, keep=tensor)
 
+    def wrap_pieces(self, addrs, first_bases, n_starts, n_bases_total, keep=None):
+        """One dna value resident as base-range pieces at raw device addresses (local or peer-mapped), walked in the
+        order given: dnagpu_seq_wrap_pieces."""
+        n = len(addrs)
+        ptrs = (C.c_void_p * n)(*[C.c_void_p(int(a)) for a in addrs])
+        fb = np.ascontiguousarray(first_bases, dtype=np.uint64)
+        ns = np.ascontiguousarray(n_starts, dtype=np.uint64)
+        h = C.c_void_p()
+        self._ok(self.lib.dnagpu_seq_wrap_pieces(self.handle, ptrs, fb.ctypes.data_as(_lib.u64p),
+                                                 ns.ctypes.data_as(_lib.u64p), n, n_bases_total, C.byref(h)))
+        return Seq(self, h, keep=keep)
+
     def wrap_reads(self, tensor, n_reads, bases_per_read, stride_words):
         self._after_torch()
         h = C.c_void_p()
@@ -380,6 +411,7 @@ class Context:
             out = torch.empty(max(rows, 2), dtype=torch.int64, device=f"cuda:{self.device}")
         n = C.c_uint64()
         self._ok(self.lib.dnagpu_extract(self.handle, seq.handle, k, out.data_ptr(), out.numel(), C.byref(n)))
+        self._before_torch()
         return out[:n.value]
 
     # ---- WHERE ^@ / @> ---------------------------------------------------------------
@@ -418,6 +450,7 @@ class Context:
             rc = self.lib.dnagpu_filter(self.handle, seq.handle, k, wp, out.data_ptr(), out.numel(), C.byref(n))
             if rc != 21:  # DNAGPU_ECAPACITY: n holds the need
                 self._ok(rc)
+                self._before_torch()
                 return out[:n.value]
             guess = n.value
         self._ok(rc)
@@ -434,6 +467,7 @@ class Context:
             rc = self.lib.dnagpu_collect(self.handle, seq.handle, k, wp, out.data_ptr(), out.numel(), C.byref(n))
             if rc != 21:  # DNAGPU_ECAPACITY: n holds the need
                 self._ok(rc)
+                self._before_torch()
                 return out[:n.value]
             guess = n.value
         self._ok(rc)
@@ -452,6 +486,7 @@ class Context:
                                              out.numel(), C.byref(n))
             if rc != 21:
                 self._ok(rc)
+                self._before_torch()
                 return out[:n.value]
             guess = n.value
         self._ok(rc)
@@ -465,18 +500,22 @@ class Context:
 
     # ---- GROUP BY kmer ------------------------------------------------------------------
     @staticmethod
-    def _opts(method, load_factor, expected_keys):
-        if method == COUNT_AUTO and not load_factor and not expected_keys:
+    def _opts(method, load_factor, expected_keys, exact=False, owner=None):
+        if method == COUNT_AUTO and not load_factor and not expected_keys and not exact and owner is None:
             return None
         o = CountOpts()
         o.method, o.load_factor, o.expected_keys = method, load_factor or 0.0, expected_keys or 0
+        o.flags = COUNT_FLAG_EXACT if exact else 0
+        if owner is not None:
+            o.owner_parts, o.owner_part = owner
         return o
 
     def count(self, seq, k, prefix=None, pattern=None, table=False, method=COUNT_AUTO,
-              load_factor=0.0, expected_keys=0):
-        """GROUP BY kmer over device-resident sequences -> (Stats, Table | None)."""
+              load_factor=0.0, expected_keys=0, exact=False, owner=None):
+        """GROUP BY kmer over device-resident sequences -> (Stats, Table | None).
+        owner=(n_parts, part): only the k-mers dnagpu_owner_of assigns to `part` (one GPU's share of a multi-GPU count)."""
         w, _keep = _where(prefix, pattern)
-        o = self._opts(method, load_factor, expected_keys)
+        o = self._opts(method, load_factor, expected_keys, exact, owner)
         st, th = Stats(), C.c_void_p()
         self._ok(self.lib.dnagpu_count(self.handle, seq.handle, k, C.byref(w) if w is not None else None,
                                        C.byref(o) if o is not None else None, C.byref(st),

@@ -30,8 +30,9 @@ class ShufflePlan(C.Structure):
 
 
 class CountOpts(C.Structure):
-    _fields_ = [("method", C.c_int32), ("warp_aggregate", C.c_int32),
-                ("load_factor", C.c_double), ("expected_keys", C.c_uint64)]
+    _fields_ = [("method", C.c_int32), ("flags", C.c_int32),
+                ("load_factor", C.c_double), ("expected_keys", C.c_uint64),
+                ("owner_parts", C.c_uint32), ("owner_part", C.c_uint32)]
 
 
 # name -> (restype, argtypes); every symbol include/dnagpu.h declares
@@ -54,6 +55,7 @@ SIGNATURES = {
     "dnagpu_seq_synth_reads": (C.c_int, [vp, u64, u64, C.c_uint32, C.c_uint32, u64, C.c_uint32, C.POINTER(vp)]),
     "dnagpu_seq_wrap": (C.c_int, [vp, vp, u64, u64, C.POINTER(vp)]),
     "dnagpu_seq_wrap_reads": (C.c_int, [vp, vp, u64, C.c_uint32, C.c_uint32, u64, C.POINTER(vp)]),
+    "dnagpu_seq_wrap_pieces": (C.c_int, [vp, C.POINTER(vp), u64p, u64p, C.c_uint32, u64, C.POINTER(vp)]),
     "dnagpu_seq_set_start_limit": (C.c_int, [vp, u64]),
     "dnagpu_seq_download": (C.c_int, [vp, vp, vp, u64]),
     "dnagpu_seq_words": (u64, [vp]),

@@ -119,11 +119,23 @@ enum {
     DNAGPU_COUNT_PARTITION = 3  /* two-level radix partition, then one shared-memory table per bucket */
 };
 
+/* DNAGPU_COUNT_PARTITION sizes its partitions optimistically (fixed regions of mean + slack, no histogram
+ * pass; a full region makes the library redo that level exactly).  This flag takes the exact two-pass form
+ * from the start: same result, for inputs known to be heavily repeated -- and for the tests of that path. */
+#define DNAGPU_COUNT_FLAG_EXACT 1
+
 typedef struct dnagpu_count_opts {
     int32_t method;        /* DNAGPU_COUNT_*                                    */
-    int32_t warp_aggregate;/* reserved, must be 0 (MATCH.ANY measured too slow)  */
+    int32_t flags;         /* DNAGPU_COUNT_FLAG_*; 0 = default                    */
     double load_factor;    /* hash table target load, 0 = default (0.5)         */
     uint64_t expected_keys;/* 0 = derive from input (n_kmers, 4^k)              */
+    /* Multi-GPU: count only the k-mers that dnagpu_owner_of(kmer, owner_parts) assigns to owner_part
+     * (0 parts = no restriction).  Every GPU of a box runs the same query over the same sequence --
+     * resident as one piece per GPU, see dnagpu_seq_wrap_pieces -- with its own owner_part; the key sets
+     * are disjoint, so the aggregates add and the grouped rows concatenate.  Single sequences only, no
+     * WHERE clause. */
+    uint32_t owner_parts;
+    uint32_t owner_part;
 } dnagpu_count_opts;
 
 /* ---- context ------------------------------------------------------------- */
@@ -183,6 +195,17 @@ int dnagpu_seq_wrap(dnagpu_ctx *ctx, const void *d_words, uint64_t n_bases,
 int dnagpu_seq_wrap_reads(dnagpu_ctx *ctx, const void *d_words, uint64_t n_reads,
                           uint32_t bases_per_read, uint32_t stride_words,
                           uint64_t n_words_alloc, dnagpu_seq **out);
+/* One dna value resident as n_pieces base-range pieces (multi-GPU: one shard per GPU, each mapped into this
+ * GPU's address space -- its own memory, or peer memory opened with dnagpu_peer_open).  Piece i holds the
+ * packed words of the bases from first_base[i] on and serves the k-mers that START in
+ * [first_base[i], first_base[i] + n_starts[i]): it must reach 31 bases past that range (the (k-1)-base
+ * overlap for any k <= 32) and end in one zero pad word, first_base[i] must be a multiple of 32, and the
+ * ranges must tile [0, n_bases_total) when sorted.  The pieces are walked in the order given (put this GPU's
+ * own piece first and the others in ring order, so that no shard is read by every GPU at once).  Such a
+ * sequence is accepted by dnagpu_count with an owner restriction (dnagpu_count_opts.owner_parts) only. */
+int dnagpu_seq_wrap_pieces(dnagpu_ctx *ctx, const void *const *d_words, const uint64_t *first_base,
+                           const uint64_t *n_starts, uint32_t n_pieces, uint64_t n_bases_total,
+                           dnagpu_seq **out);
 /* Restrict a single sequence to the k-mers starting in its first n_starts
  * bases (multi-GPU shards with overlap).  0 = no restriction. */
 int dnagpu_seq_set_start_limit(dnagpu_seq *seq, uint64_t n_starts);

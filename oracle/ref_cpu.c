@@ -711,6 +711,204 @@ int ref_count_query_mt(const uint64_t *words, uint64_t n_seqs, uint64_t bases_pe
     return rc;
 }
 
+/* ---- the same query for inputs whose grouped result does not fit in memory ----------------------- */
+/* SURVEY.md section 7, hard part 4: the 3.1 Gbp / k = 31 result is ~ 50 GB as a sorted list.  The rows are
+ * produced exactly as in ref_count_range (window form or the faithful per-k-mer decode, same WHERE
+ * evaluation), but grouped in `passes` x P disjoint hash partitions: pass g keeps the rows whose
+ * partition hash falls in group g, lays them out by sub-partition, and every sub-partition is then
+ * aggregated by the oracle's own hash aggregate (ref_agg: ref_kmer_hash + ref_kmer_eq).  Partitions
+ * hold disjoint key sets, so total / distinct / unique add and the order-independent digest combines
+ * (+ for the sums, ^ for the xors).  Memory: rows / passes * 8 bytes. */
+typedef struct ref_big_job {
+    const uint64_t *words;
+    uint64_t n_words_seq, rows_per_seq, stride_words, row_first, row_last; /* global rows [first, last) */
+    int k, prefix_len, faithful, pass, passes, rc;
+    uint64_t prefix_bits, sub_mask;
+    const char *pattern;
+    uint64_t *hist;     /* P counters of this thread */
+    uint64_t *cursor;   /* P write positions of this thread (scatter phase) */
+    uint64_t *keys;     /* the pass's key array */
+    /* aggregate phase */
+    const uint64_t *sub_off;
+    uint64_t n_sub;
+    volatile uint64_t *next_sub;
+    uint64_t stats[3], digest[4];
+} ref_big_job;
+
+static inline uint64_t ref_big_hash(uint64_t key) { return dnagpu_splitmix64(key ^ 0x6A09E667F3BCC909ull); }
+
+/* walk the rows of one thread; mode 0 = histogram, 1 = scatter */
+static int ref_big_walk(ref_big_job *j, int mode)
+{
+    uint64_t r = j->row_first;
+    uint64_t s = j->rows_per_seq ? r / j->rows_per_seq : 0, i = j->rows_per_seq ? r % j->rows_per_seq : 0;
+    int err;
+    for (; r < j->row_last; r++) {
+        const uint64_t *w = j->words + s * j->stride_words;
+        uint64_t bits, h;
+        if (j->faithful) {
+            int rc = ref_generate_one(w, i, j->k, &bits);
+            if (rc != REF_OK) return rc;
+        } else {
+            bits = ref_window(w, j->n_words_seq, i, j->k);
+        }
+        if (++i == j->rows_per_seq) {
+            i = 0;
+            s++;
+        }
+        if (j->prefix_len > 0 && !ref_starts_with(bits, j->k, j->prefix_bits, j->prefix_len, &err)) continue;
+        if (j->pattern != NULL && !ref_contains(j->pattern, bits, j->k, &err)) continue;
+        h = ref_big_hash(bits);
+        if ((int)((h >> 40) % (uint64_t)j->passes) != j->pass) continue;
+        if (mode == 0)
+            j->hist[h & j->sub_mask]++;
+        else
+            j->keys[j->cursor[h & j->sub_mask]++] = bits;
+    }
+    return REF_OK;
+}
+
+static void *ref_big_hist_main(void *arg)
+{
+    ref_big_job *j = (ref_big_job *)arg;
+    j->rc = ref_big_walk(j, 0);
+    return NULL;
+}
+static void *ref_big_scatter_main(void *arg)
+{
+    ref_big_job *j = (ref_big_job *)arg;
+    j->rc = ref_big_walk(j, 1);
+    return NULL;
+}
+static void *ref_big_agg_main(void *arg)
+{
+    ref_big_job *j = (ref_big_job *)arg;
+    for (;;) {
+        uint64_t sub = __sync_fetch_and_add(j->next_sub, 1), beg, end, q, t, d, u, dg[4];
+        ref_agg *a;
+        if (sub >= j->n_sub) break;
+        beg = j->sub_off[sub];
+        end = j->sub_off[sub + 1];
+        if (end == beg) continue;
+        a = ref_agg_new((end - beg) < 1024 ? 1024 : (end - beg));
+        if (!a) {
+            j->rc = -1;
+            break;
+        }
+        a->k = j->k;
+        for (q = beg; q < end; q++) ref_agg_add(a, j->keys[q], 1);
+        ref_agg_stats(a, &t, &d, &u);
+        ref_agg_digest(a, dg);
+        ref_agg_free(a);
+        j->stats[0] += t;
+        j->stats[1] += d;
+        j->stats[2] += u;
+        j->digest[0] += dg[0];
+        j->digest[1] ^= dg[1];
+        j->digest[2] += dg[2];
+        j->digest[3] ^= dg[3];
+    }
+    return NULL;
+}
+
+int ref_count_query_big(const uint64_t *words, uint64_t n_seqs, uint64_t bases_per_seq,
+                        uint64_t stride_words, int k, uint64_t prefix_bits, int prefix_len,
+                        const char *pattern, int faithful, int passes, int threads,
+                        uint64_t stats[3], uint64_t digest[4])
+{
+    const uint64_t rows_per_seq = ref_kmer_rows(bases_per_seq, k), rows = n_seqs * rows_per_seq;
+    uint64_t P = 1, sub, *hist, *cursor, *sub_off, next_sub;
+    ref_big_job *jobs;
+    pthread_t *tids;
+    int t, g, rc = ref_query_check(n_seqs, bases_per_seq, k, prefix_len, pattern);
+    stats[0] = stats[1] = stats[2] = 0;
+    digest[0] = digest[1] = digest[2] = digest[3] = 0;
+    if (rc != REF_OK) return rc;
+    if (rows == 0) return REF_OK;
+    if (passes < 1) passes = 1;
+    if (threads < 1) threads = 1;
+    while (P < (1u << 16) && rows / (uint64_t)passes / P > 32768) P <<= 1; /* sub-partitions of ~32 K rows */
+    jobs = (ref_big_job *)calloc((size_t)threads, sizeof(*jobs));
+    tids = (pthread_t *)calloc((size_t)threads, sizeof(*tids));
+    hist = (uint64_t *)calloc((size_t)threads * P, sizeof(uint64_t));
+    cursor = (uint64_t *)calloc((size_t)threads * P, sizeof(uint64_t));
+    sub_off = (uint64_t *)calloc(P + 1, sizeof(uint64_t));
+    if (!jobs || !tids || !hist || !cursor || !sub_off) return -1;
+    for (g = 0; g < passes && rc == REF_OK; g++) {
+        uint64_t n_pass = 0, *keys;
+        memset(hist, 0, (size_t)threads * P * sizeof(uint64_t));
+        for (t = 0; t < threads; t++) {
+            ref_big_job *j = &jobs[t];
+            memset(j, 0, sizeof(*j));
+            j->words = words;
+            j->n_words_seq = ref_dna_words(bases_per_seq);
+            j->rows_per_seq = rows_per_seq;
+            j->stride_words = stride_words;
+            j->row_first = rows / (uint64_t)threads * (uint64_t)t;
+            j->row_last = t == threads - 1 ? rows : rows / (uint64_t)threads * (uint64_t)(t + 1);
+            j->k = k;
+            j->prefix_bits = prefix_bits;
+            j->prefix_len = prefix_len;
+            j->pattern = pattern;
+            j->faithful = faithful;
+            j->pass = g;
+            j->passes = passes;
+            j->sub_mask = P - 1;
+            j->hist = hist + (size_t)t * P;
+            j->cursor = cursor + (size_t)t * P;
+            pthread_create(&tids[t], NULL, ref_big_hist_main, j);
+        }
+        for (t = 0; t < threads; t++) {
+            pthread_join(tids[t], NULL);
+            if (jobs[t].rc != REF_OK) rc = jobs[t].rc;
+        }
+        if (rc != REF_OK) break;
+        for (sub = 0; sub < P; sub++) { /* sub-partition major, thread minor: deterministic layout */
+            sub_off[sub] = n_pass;
+            for (t = 0; t < threads; t++) {
+                cursor[(size_t)t * P + sub] = n_pass;
+                n_pass += hist[(size_t)t * P + sub];
+            }
+        }
+        sub_off[P] = n_pass;
+        keys = (uint64_t *)malloc((n_pass ? n_pass : 1) * sizeof(uint64_t));
+        if (!keys) {
+            rc = -1;
+            break;
+        }
+        for (t = 0; t < threads; t++) {
+            jobs[t].keys = keys;
+            pthread_create(&tids[t], NULL, ref_big_scatter_main, &jobs[t]);
+        }
+        for (t = 0; t < threads; t++) pthread_join(tids[t], NULL);
+        next_sub = 0;
+        for (t = 0; t < threads; t++) {
+            jobs[t].sub_off = sub_off;
+            jobs[t].n_sub = P;
+            jobs[t].next_sub = &next_sub;
+            pthread_create(&tids[t], NULL, ref_big_agg_main, &jobs[t]);
+        }
+        for (t = 0; t < threads; t++) {
+            pthread_join(tids[t], NULL);
+            if (jobs[t].rc != REF_OK) rc = jobs[t].rc;
+            stats[0] += jobs[t].stats[0];
+            stats[1] += jobs[t].stats[1];
+            stats[2] += jobs[t].stats[2];
+            digest[0] += jobs[t].digest[0];
+            digest[1] ^= jobs[t].digest[1];
+            digest[2] += jobs[t].digest[2];
+            digest[3] ^= jobs[t].digest[3];
+        }
+        free(keys);
+    }
+    free(jobs);
+    free(tids);
+    free(hist);
+    free(cursor);
+    free(sub_off);
+    return rc;
+}
+
 /* ---- synthetic inputs ---------------------------------------------------------------------------- */
 void ref_synth_seq(uint64_t seed, uint32_t repeat_every, uint64_t n_bases, uint64_t first_word,
                    uint64_t n_words, uint64_t *words)

@@ -111,6 +111,14 @@ int ref_count_query_mt(const uint64_t *words, uint64_t n_seqs, uint64_t bases_pe
                        int prefix_len, const char *pattern, int faithful, int threads,
                        ref_agg *agg);
 
+/* The same query for inputs whose grouped result does not fit in memory (3.1 Gbp, k = 31): rows grouped in
+ * `passes` x P disjoint hash partitions, each aggregated by ref_agg; the three aggregates add and the
+ * digest (same definition as ref_agg_digest) combines across partitions.  Memory ~ rows / passes * 8 B. */
+int ref_count_query_big(const uint64_t *words, uint64_t n_seqs, uint64_t bases_per_seq,
+                        uint64_t stride_words, int k, uint64_t prefix_bits, int prefix_len,
+                        const char *pattern, int faithful, int passes, int threads,
+                        uint64_t stats[3], uint64_t digest[4]);
+
 /* synthetic inputs (include/dnagpu_synth.h) */
 void ref_synth_seq(uint64_t seed, uint32_t repeat_every, uint64_t n_bases,
                    uint64_t first_word, uint64_t n_words, uint64_t *words);

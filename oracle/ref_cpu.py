@@ -55,6 +55,8 @@ def lib():
         "ref_count_query": (C.c_int, [vp, u64, u64, u64, C.c_int, u64, C.c_int, C.c_char_p, C.c_int, vp]),
         "ref_count_query_mt": (C.c_int, [vp, u64, u64, u64, C.c_int, u64, C.c_int, C.c_char_p, C.c_int,
                                          C.c_int, vp]),
+        "ref_count_query_big": (C.c_int, [vp, u64, u64, u64, C.c_int, u64, C.c_int, C.c_char_p, C.c_int,
+                                          C.c_int, C.c_int, vp, vp]),
         "ref_synth_seq": (None, [u64, C.c_uint32, u64, u64, u64, vp]),
         "ref_synth_reads": (None, [u64, C.c_uint32, u64, u64, C.c_uint32, C.c_uint32, vp]),
     }
@@ -187,6 +189,20 @@ def count_query(words, n_seqs, bases_per_seq, stride_words, k, prefix=None, patt
         return CountResult(t.value, d.value, u.value, kmers, counts, digest)
     finally:
         L.ref_agg_free(agg)
+
+
+def count_query_big(words, n_seqs, bases_per_seq, stride_words, k, prefix=None, pattern=None, faithful=False,
+                    passes=1, threads=8):
+    """count_query for results that do not fit in memory: rows grouped in hash partitions, each aggregated by the
+    oracle's own ref_agg -> CountResult without rows (stats + order-independent digest)."""
+    words = _padded(words)
+    pb, pl = (0, 0) if prefix is None else prefix
+    stats = np.zeros(3, dtype=np.uint64)
+    digest = np.zeros(4, dtype=np.uint64)
+    _ok(lib().ref_count_query_big(words.ctypes.data, n_seqs, bases_per_seq, stride_words, k, pb, pl,
+                                  None if pattern is None else pattern.encode("ascii", "replace"),
+                                  1 if faithful else 0, passes, threads, stats.ctypes.data, digest.ctypes.data))
+    return CountResult(int(stats[0]), int(stats[1]), int(stats[2]), None, None, digest)
 
 
 def count_ragged(seqs, k, prefix=None, pattern=None, faithful=True):
