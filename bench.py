@@ -3,21 +3,37 @@
 
 Workload (BASELINE.json configs[3], the one the metric is quoted on): one synthetic
 3.1 Gbp sequence (seeded generator of include/dnagpu_synth.h, every 8th 1024-base block a
-planted repeat), k = 31, `GROUP BY kmer` with total / distinct / unique.  At N > 1 the
-sequence is sharded by base range with a (k-1)-base overlap, k-mers are routed to their
-owner rank by hash (NCCL all-to-all) and each rank counts its partition: total work is
-fixed, so scaling is "strong".
+planted repeat), k = 31, `GROUP BY kmer` with total / distinct / unique.  Total work is fixed,
+so scaling is "strong".
 
-  value   Gkmer/s with the packed words already resident in HBM (table init + extract +
-          count + aggregates; at N > 1 also partition + exchange), CUDA-event timed.
-  e2e     the same query through the host-buffer C-ABI call dnagpu_count_kmers():
-          pinned host words -> H2D -> count -> D2H of the three aggregates, every step.
+N > 1 (one process per GPU, torch.distributed / NCCL for the plumbing), `--exchange`:
+  gather (default)  the sequence stays sharded by base range, one shard per GPU with its (k-1)-base
+          overlap, every shard mapped into every GPU's address space (CUDA IPC peer memory); each GPU
+          walks ALL shards over NVLink and counts the k-mers dnagpu_owner_of assigns to it.  What
+          crosses NVLink is the 2-bit packed bases, not 8-byte k-mers; the only collective is the
+          final all-reduce of the three aggregates.
+  peer / fused / routed   k-mers routed to their owners (scatter kernel storing into peer memory /
+          NCCL all-to-all); kept for comparison and used by the reads workload (WHERE clause).
+
+  value   Gkmer/s with the packed words already resident in HBM (every kernel of the query:
+          extract + partition + count + aggregates), CUDA-event timed, max over ranks.
+  e2e     the same query from HOST buffers: pinned host words -> H2D -> count -> D2H of the three
+          aggregates, every step.  N = 1: the C-ABI call dnagpu_count_kmers().  N > 1: every rank
+          uploads its shard, then the same count.
   roofline  the kernel with the largest share of the step (CUDA events around every launch, taken
           inside the timed region): its algorithmic bytes / its average duration, plus the same
-          figure for every kernel of the pipeline and for the whole step.
+          figure for every kernel of the pipeline and for the whole step.  Kernels that read
+          0.25 B/base and test every position (the fused WHERE scan) carry "bound": "issue" and are
+          measured against the instruction-issue peak instead.
   cpu_baseline  the reference's own dna.c (oracle/_ref: compiled unmodified against a PostgreSQL
-          API shim and driven like the executor) on the host cores, bounded sample; falls back
-          to the oracle's faithful restatement when that library is not built.
+          API shim and driven like the executor) on the host cores, bounded sample, all threads;
+          cpu_baseline_1thread is the same on ONE thread, which is how PostgreSQL runs this plan
+          (generate_kmers is not PARALLEL SAFE).
+
+Other workloads: --workload c1 (10 kb, k = 5: BASELINE configs[0], the CPU reference timed in full),
+c2 (100 Mbp, k = 21), c3 (100 M reads, fused WHERE + count), c5 (k = 3..32 sweep over 1 Gbp, one line).
+Every result is compared with the CPU oracle's answer for the exact workload
+(tests/golden/big_expected.json); a run that differs prints no line.
 
 `--impl reference` times the reference's CPU implementation of the same query
 (oracle/_ref = the reference's own dna.c when it could be compiled, else the oracle port).
@@ -38,10 +54,12 @@ for _p in (ROOT, PKG):
         sys.path.insert(0, _p)
 
 WORKLOADS = {
-    # name: (n_bases, k, seed, description)      -- BASELINE.json configs[3], [1], [4]
+    # name: (n_bases, k, seed, description)      -- BASELINE.json configs[3], [1], [4], [0]
     "c4": (3_100_000_000, 31, 4, "3.1 Gbp synthetic sequence, k=31 GROUP BY kmer count + total/distinct/unique"),
     "c2": (100_000_000, 21, 2, "100 Mbp synthetic sequence, k=21 full count + total/distinct/unique"),
-    "c5": (1_000_000_000, 31, 5, "1 Gbp synthetic sequence, k=31 count"),
+    "c5": (1_000_000_000, 31, 5, "k-sweep 3..32 over a 1 Gbp synthetic sequence (dense tables, partition path, "
+                                 "k=32 full-uint64 sentinel)"),
+    "c1": (10_000, 5, 1, "generate_kmers + GROUP BY count, k=5, one 10 kb synthetic sequence"),
     # BASELINE.json configs[2]: reads (each its own dna value), WHERE ^@ AND @> fused into the count
     "c3": (100_000_000 * 150, 31, 3, "100M synthetic 150 bp reads, k=31, WHERE kmer ^@ 'AC' AND "
                                      "'NNNNNNNNNNNNWSNNNNNNNNNNNNNNNRY' @> kmer, fused filter-count"),
@@ -50,6 +68,8 @@ READS = {"c3": {"n_reads": 100_000_000, "bases": 150, "stride": 5, "prefix": "AC
                 "pattern": "NNNNNNNNNNNNWSNNNNNNNNNNNNNNNRY"}}
 REPEAT_EVERY = 8
 METRIC = "Gkmer/s counted (k=31) at 1/2/4/8 B200; extraction HBM GB/s vs peak"
+NVLINK_PEER_GBS = 770.0   # measured peer-copy rate per direction per GPU (B200_PROFILING.md)
+SM_COUNT, LANES_PER_SM = 148, 128
 
 
 def measured_peaks():
@@ -58,6 +78,14 @@ def measured_peaks():
             return float(json.load(f)["hbm_gbs"]), "measured"
     except Exception:
         return 6650.0, "fallback"
+
+
+def golden(name):
+    try:
+        with open(os.path.join(ROOT, "tests", "golden", "big_expected.json")) as f:
+            return json.load(f).get(name)
+    except Exception:
+        return None
 
 
 class ClockSampler:
@@ -129,8 +157,9 @@ def cpu_reference_rate(n_bases, k, seed, threads, sample_bases, reads=None):
     else the oracle's faithful restatement.  The prefix is cut into chunks of 65536 start positions
     (each chunk a dna value overlapping the next by k-1 bases, so every k-mer is produced once) so
     that all host threads have work; PostgreSQL itself would run the plan on ONE core because
-    generate_kmers is not PARALLEL SAFE (dna--1.0.sql:188-191).
-    Returns (Gkmer/s, seconds, (total, distinct, unique), kind)."""
+    generate_kmers is not PARALLEL SAFE (dna--1.0.sql:188-191).  A workload no longer than one chunk
+    (c1) is run whole, as one dna value.
+    Returns (Gkmer/s, seconds, (total, distinct, unique), kind, bases)."""
     from oracle import ref_cpu as R
     from oracle import ref_real as P
     kind = "reference" if os.path.exists(P.SO) else "port"
@@ -148,6 +177,16 @@ def cpu_reference_rate(n_bases, k, seed, threads, sample_bases, reads=None):
         dt = time.perf_counter() - t0
         rows = n * (reads["bases"] - k + 1)  # k-mers generated and tested, the unit of the metric
         return rows / dt / 1e9, dt, (rows,) + tuple(r.stats[1:]), kind, n * reads["bases"]
+    if n_bases <= CHUNK_BASES:
+        import numpy as np
+        words = np.concatenate([R.synth_seq(seed, n_bases, REPEAT_EVERY), np.zeros(1, dtype=np.uint64)])
+        t0 = time.perf_counter()
+        if kind == "reference":
+            r = P.count(words, 1, n_bases, words.size, k, threads=1, want_rows=False)
+        else:
+            r = R.count_query(words, 1, n_bases, words.size, k, faithful=True, threads=1, want_rows=False)
+        dt = time.perf_counter() - t0
+        return r.total / dt / 1e9, dt, r.stats, kind, n_bases
     n_chunks = max(1, (sample_bases - (k - 1)) // CHUNK_BASES)
     sample = n_chunks * CHUNK_BASES + k - 1
     words = R.synth_seq(seed, n_bases, REPEAT_EVERY, first_word=0, n_words=(sample + 31) // 32 + 1)
@@ -162,18 +201,42 @@ def cpu_reference_rate(n_bases, k, seed, threads, sample_bases, reads=None):
     return r.total / dt / 1e9, dt, r.stats, kind, sample
 
 
+REF_WHAT = {"reference": "the reference's own dna.c (unmodified, PostgreSQL API shim) driven like the executor: "
+                         "generate_kmers SRF loop + hash aggregate through kmer_hash/kmer_eq",
+            "port": "oracle port: faithful per-k-mer decode/validate/encode of dna.c:803-825 + kmer_hash/kmer_eq "
+                    "hash aggregate"}
+
+
+def cpu_baselines(n_bases, k, seed, reads, sample, sample_1t):
+    """(all-threads baseline, one-thread baseline) objects for the JSON line."""
+    threads = max(1, min(os.cpu_count() or 1, 64))
+    cv, cdt, _, ckind, csample = cpu_reference_rate(n_bases, k, seed, threads, sample, reads)
+    cpu = {"value": cv, "unit": "Gkmer/s", "cores": threads if csample > CHUNK_BASES or reads else 1, "kind": ckind,
+           "sample": f"first {csample} bases of the workload ({cdt:.1f} s), {REF_WHAT[ckind]}"
+                     + ("" if csample < n_bases else " -- the whole workload")}
+    ov, odt, _, okind, osample = cpu_reference_rate(n_bases, k, seed, 1, sample_1t, reads)
+    one = {"value": ov, "unit": "Gkmer/s", "cores": 1, "kind": okind,
+           "sample": f"first {osample} bases of the workload ({odt:.1f} s) on ONE thread -- how PostgreSQL runs this "
+                     "plan: generate_kmers / ^@ / @> are not PARALLEL SAFE (dna--1.0.sql:188-201, 268-276)"}
+    return cpu, one
+
+
 def run_reference(args):
     rank, world, local = dist_env()
     if rank != 0:
         return 0
     n_bases, k, seed, desc = WORKLOADS[args.workload]
+    k = args.k or k
     threads = max(1, min(os.cpu_count() or 1, 64))
-    # calibrate the per-step sample so that the whole run ends within a few minutes
     reads = READS.get(args.workload)
-    rate, dt, _, kind, _ = cpu_reference_rate(n_bases, k, seed, threads, 4_000_000, reads)
-    # the rate on a small (cache-friendly) sample is optimistic: keep 40 % of the time budget
-    budget_s = 0.4 * max(0.5, min(4.0, 100.0 / max(1, args.steps + args.warmup)))
-    sample = int(max(1_000_000, min(16_000_000, rate * 1e9 * budget_s)))
+    if args.cpu_large_sample:
+        sample = args.cpu_large_sample
+    else:
+        # calibrate the per-step sample so that the whole run ends within a few minutes
+        rate, dt, _, kind, _ = cpu_reference_rate(n_bases, k, seed, threads, 4_000_000, reads)
+        # the rate on a small (cache-friendly) sample is optimistic: keep 40 % of the time budget
+        budget_s = 0.4 * max(0.5, min(4.0, 100.0 / max(1, args.steps + args.warmup)))
+        sample = int(max(1_000_000, min(16_000_000, rate * 1e9 * budget_s)))
     for _ in range(args.warmup):
         cpu_reference_rate(n_bases, k, seed, threads, sample, reads)
     wall, total = 0.0, 0
@@ -182,11 +245,10 @@ def run_reference(args):
         wall += dt
         total += stats[0]
     value = total / wall / 1e9
-    what = ("the reference's own dna.c (unmodified, PostgreSQL API shim): generate_kmers SRF loop + hash aggregate "
-            "through kmer_hash/kmer_eq" if kind == "reference" else
-            "oracle port: faithful per-k-mer decode/validate/encode (dna.c:803-825) + kmer_hash/kmer_eq aggregate")
-    sample_desc = (f"first {sample_used} bases of the workload per step, {what}, {threads} threads "
-                   "(Postgres itself would run this serially: generate_kmers is PARALLEL UNSAFE)")
+    sample_desc = (f"first {sample_used} bases of the workload per step, {REF_WHAT[kind]}, {threads} threads "
+                   "(Postgres itself would run this serially: generate_kmers is PARALLEL UNSAFE; the hash table of a "
+                   "sample this small is cache-resident, which flatters the CPU side)")
+    ov, odt, _, okind, osample = cpu_reference_rate(n_bases, k, seed, 1, min(sample, 1_000_000), reads)
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": "Gkmer/s", "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * wall / max(1, args.steps),
@@ -194,6 +256,8 @@ def run_reference(args):
         "config": {"workload": desc, "n_bases": n_bases, "k": k, "seed": seed, "repeat_every": REPEAT_EVERY,
                    "sample_bases_per_step": sample_used},
         "cpu_baseline": {"value": value, "unit": "Gkmer/s", "cores": threads, "kind": kind, "sample": sample_desc},
+        "cpu_baseline_1thread": {"value": ov, "unit": "Gkmer/s", "cores": 1, "kind": okind,
+                                 "sample": f"first {osample} bases ({odt:.1f} s), one thread"},
         "e2e": {"value": value, "unit": "Gkmer/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
@@ -202,16 +266,106 @@ def run_reference(args):
 
 
 # ================================= our arm =====================================
+# static SASS instructions of one item (32 start positions) of the fused WHERE scan, per start position
+# (cuobjdump -sass of k_filter_collect<kFixed>: 936 instructions per item incl. staging; profiles/r02_sass_hot_kernels.txt);
+# replaced by the executed-instruction count of an ncu capture when profiles/issue.json holds one
+ISSUE_INSTR_PER_POSITION = {"filter_collect": 936 / 32.0, "filter_count": 936 / 32.0}
+
+
+def issue_table():
+    try:
+        with open(os.path.join(ROOT, "profiles", "issue.json")) as f:
+            t = dict(ISSUE_INSTR_PER_POSITION)
+            t.update({k_: float(v) for k_, v in json.load(f).items() if not k_.startswith("_")})
+            return t
+    except Exception:
+        return dict(ISSUE_INSTR_PER_POSITION)
+
+
+def run_sweep(args, ctx, torch, dev, stream, peak, peak_src):
+    """--workload c5: GROUP BY kmer for every k from 3 to 32 over the 1 Gbp sequence, method AUTO.  One line:
+    per-k time, method and result, each checked against the oracle; value = all k-mers of the sweep / its time."""
+    n_bases, _, seed, desc = WORKLOADS["c5"]
+    n_bases = args.n_bases or n_bases
+    seq = ctx.synth(n_bases, seed, REPEAT_EVERY)
+    host = torch.empty(seq.n_words + 2, dtype=torch.int64, pin_memory=True)
+    host.zero_()
+    assert ctx.lib.dnagpu_seq_download(ctx.handle, seq.handle, C.c_void_p(host.data_ptr()), seq.n_words) == 0
+    ks = list(range(3, 33))
+    per_k, total_rows, total_ms, launches = {}, 0, 0.0, 0
+    sampler = ClockSampler(dev.index)
+    sampler.start()
+    for k in ks:
+        for _ in range(max(1, min(args.warmup, 3))):
+            st, _ = ctx.count(seq, k)
+        ctx.profile(True)
+        ctx.profile_reset()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        torch.cuda.synchronize(dev)
+        e0.record(stream)
+        for _ in range(args.steps):
+            st, _ = ctx.count(seq, k)
+        e1.record(stream)
+        torch.cuda.synchronize(dev)
+        kernels = ctx.profile_dump()
+        ctx.profile(False)
+        ms = e0.elapsed_time(e1) / args.steps
+        g = golden(f"c5_k{k}") if not args.n_bases else None
+        res = (st.total, st.distinct, st.unique)
+        if g is not None and res != (g["total"], g["distinct"], g["unique"]):
+            print(f"bench: k={k}: result {res} differs from the oracle's {(g['total'], g['distinct'], g['unique'])}: "
+                  "no line printed", file=sys.stderr)
+            return 1
+        method = ("dense" if any(n.startswith("count_dense") for n in kernels) else
+                  "partition" if "count_buckets" in kernels else "hash")
+        per_k[str(k)] = {"ms": ms, "gkmer_s": st.total / ms / 1e6, "method": method, "distinct": st.distinct,
+                         "unique": st.unique, "oracle": "equal" if g is not None else "not compared"}
+        total_rows += st.total
+        total_ms += ms
+        launches += sum(v["launches"] for v in kernels.values())
+    clocks = sampler.stop()
+    t0 = time.perf_counter()
+    for k in ks:  # the host-buffer call for every k: 250 MB H2D each
+        ctx.count_kmers_ptr(C.c_void_p(host.data_ptr()), n_bases, k)
+    e2e_s = time.perf_counter() - t0
+    slow = max(per_k, key=lambda q: per_k[q]["ms"])
+    cpu, one = cpu_baselines(n_bases, 31, seed, None, args.cpu_sample, 1_000_000)
+    # roofline of the slowest k: the partition pipeline moves 0.25 B/base + 8 + 16 + 8 B per k-mer (DESIGN.md 4)
+    pipe_bytes = 0.25 * n_bases + 32.0 * per_k[slow]["gkmer_s"] * per_k[slow]["ms"] * 1e6
+    line = {
+        "metric": METRIC, "value": total_rows / total_ms / 1e6, "unit": "Gkmer/s", "n_gpus": 1, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": total_ms, "higher_is_better": True, "scaling": "strong",
+        "vs_baseline": None, "dtype": "u64", "data": "synthetic",
+        "config": {"workload": desc, "n_bases": n_bases, "k": "3..32", "seed": seed, "repeat_every": REPEAT_EVERY,
+                   "unit_of_value": "k-mers counted per second over the 30 runs of the sweep (a step = all 30)",
+                   "l2": "inputs larger than L2 for k >= 13; k <= 12 tables are L2-resident by design"},
+        "per_k": per_k,
+        "result": {"oracle": "every k equal to tests/golden/big_expected.json" if not args.n_bases else "not compared"},
+        "e2e": {"value": total_rows / e2e_s / 1e9, "unit": "Gkmer/s", "ms_per_step": 1e3 * e2e_s,
+                "h2d_bytes_per_step": int(8 * ((n_bases + 31) // 32)) * len(ks), "d2h_bytes_per_step": 24 * len(ks),
+                "api": "dnagpu_count_kmers(ctx, host_words, n_bases, k, NULL, &stats, NULL) for k = 3..32"},
+        "gpu_launches": launches,
+        "roofline": {"bound": "hbm", "kernel": f"whole count pipeline at k={slow} (the slowest k)",
+                     "achieved": pipe_bytes / per_k[slow]["ms"] / 1e6, "peak": peak, "unit": "GB/s",
+                     "frac": pipe_bytes / per_k[slow]["ms"] / 1e6 / peak, "traffic": None, "peak_source": peak_src},
+        "cpu_baseline": cpu, "cpu_baseline_1thread": one, "clocks": clocks,
+    }
+    print(json.dumps(line), flush=True)
+    seq.free()
+    return 0
+
+
 def run_b200(args):
-    import numpy as np
+    import numpy as np  # noqa: F401
     import torch
     import torch.distributed as dist
     import dnagpu
-    from dnagpu.distributed import (GpuEngine, PeerExchange, count_sharded, count_sharded_fused, count_sharded_peer,
-                                    reads_shard_of, shard_of)
+    from dnagpu.distributed import (GpuEngine, PeerExchange, ShardRing, count_sharded, count_sharded_fused,
+                                    count_sharded_gather, count_sharded_peer, reads_shard_of, shard_of)
 
     rank, world, local = dist_env()
     n_bases, k, seed, desc = WORKLOADS[args.workload]
+    k = args.k or k
     reads = READS.get(args.workload)
     if args.n_bases:
         n_bases = args.n_bases
@@ -225,19 +379,34 @@ def run_b200(args):
         dist.init_process_group("nccl", device_id=dev)
     stream = torch.cuda.Stream(device=dev)
     peak, peak_src = measured_peaks()
+    if reads and args.exchange == "gather":
+        args.exchange = "peer"  # a WHERE clause: the rows that pass are routed (few), not the bases
+    gather = world > 1 and args.exchange == "gather"
 
     with torch.cuda.stream(stream):
         ctx = dnagpu.Context(local, torch_stream=True)
+        if args.workload == "c5" and not args.k:
+            if world > 1:
+                if rank == 0:
+                    print("bench: the k-sweep workload is a single-GPU line", file=sys.stderr)
+                return 2
+            return run_sweep(args, ctx, torch, dev, stream, peak, peak_src)
+        ring = None
         if reads:
             first, starts = reads_shard_of(reads["n_reads"], world, rank)  # first read, reads of this rank
             seq = ctx.synth_reads(first, starts, reads["bases"], reads["stride"], seed, REPEAT_EVERY)
             n_rows_total = reads["n_reads"] * (reads["bases"] - k + 1)
+        elif gather:
+            ring = ShardRing(ctx, world, rank, n_bases)  # collective
+            first, starts = ring.my_shard
+            seq = ctx.synth_range(n_bases, seed, REPEAT_EVERY, first, starts, 32)
+            n_rows_total = n_bases - k + 1
         else:
             first, starts = shard_of(n_bases, k, world, rank)
             seq = ctx.synth_range(n_bases, seed, REPEAT_EVERY, first, starts, k)
             n_rows_total = n_bases - k + 1
-        n_rows_local = seq.kmer_count(k)
         n_words_local = seq.n_words
+        n_words_total = (n_bases + 31) // 32 if not reads else reads["n_reads"] * reads["stride"]
         # host copy of this rank's packed words, pinned (the dna value a backend would hold)
         host = torch.empty(n_words_local + 2, dtype=torch.int64, pin_memory=True)
         host.zero_()
@@ -245,6 +414,9 @@ def run_b200(args):
         rc = ctx.lib.dnagpu_seq_download(ctx.handle, seq.handle, C.c_void_p(host.data_ptr()), n_words_local)
         assert rc == 0
         local_bases = starts * reads["bases"] if reads else min(n_bases - first, starts + k - 1)
+        if gather:
+            ctx.fill_words(ring.local, seq, ring.n_words[rank])
+            ring.publish()
 
         def barrier():
             if world > 1:
@@ -267,6 +439,8 @@ def run_b200(args):
             if world == 1:
                 st, _ = ctx.count(s, k, table=False, load_factor=args.load_factor, **where)
                 return st.total, st.distinct, st.unique
+            if gather:
+                return count_sharded_gather(ctx, ring, k)
             if args.exchange == "peer":
                 return count_sharded_peer(ctx, s, k, n_rows_total, world, rank, px, **where)
             if args.exchange == "fused":
@@ -274,7 +448,7 @@ def run_b200(args):
             return count_sharded(engine, s, k, world, load_factor=args.load_factor, **where)
 
         def count_e2e():
-            """The reference-facing call: host words in, aggregates out (H2D and D2H inside)."""
+            """Host words in, aggregates out (H2D and D2H inside)."""
             hp = C.c_void_p(host.data_ptr())
             if world == 1 and reads:
                 st = ctx.count_reads_ptr(hp, starts, reads["bases"], reads["stride"], k, **where)
@@ -282,6 +456,10 @@ def run_b200(args):
             if world == 1:
                 st = ctx.count_kmers_ptr(hp, local_bases, k)
                 return st.total, st.distinct, st.unique
+            if gather:  # this rank's shard: pinned host -> its ring buffer; then everybody reads everybody's
+                ctx.upload_to(ring.local, host[:n_words_local], ring.n_words[rank])
+                ring.publish()
+                return count_sharded_gather(ctx, ring, k)
             if reads:
                 s = ctx.upload_reads_ptr(hp, starts, reads["bases"], reads["stride"])
             else:
@@ -312,7 +490,7 @@ def run_b200(args):
         ctx.profile(False)
         ctx.profile_reset()
 
-        # ---- e2e leg: host buffers through the C ABI, wall clock around synchronous calls ----
+        # ---- e2e leg: host buffers in, aggregates out, wall clock around synchronous calls ----
         for _ in range(min(args.warmup, 2)):
             count_e2e()
         barrier()
@@ -324,7 +502,7 @@ def run_b200(args):
 
         # ---- extraction GB/s (the second half of the metric), timed on its own ----
         extract = None
-        if not args.no_extract and not reads:
+        if not args.no_extract and not reads and n_bases >= 1_000_000:
             xs_bases = min(local_bases, 1_000_000_000)
             xs = ctx.synth_range(n_bases, seed, REPEAT_EVERY, first, max(0, xs_bases - k + 1), k)
             xr = xs.kmer_count(k)
@@ -382,10 +560,8 @@ def run_b200(args):
     # tests/golden/make_golden_big.py).  A run whose result differs prints NO line.
     gold = None
     if not args.n_bases:
-        try:
-            with open(os.path.join(ROOT, "tests", "golden", "big_expected.json")) as f:
-                gold = json.load(f).get({"c4": "c4", "c2": "c2", "c5": "c5_k31", "c3": "c3"}[args.workload])
-        except Exception:
+        gold = golden({"c4": "c4", "c2": "c2", "c5": f"c5_k{k}", "c3": "c3", "c1": "c1"}[args.workload])
+        if gold is not None and gold.get("k") != k:
             gold = None
         if gold is not None and tuple(stats) != (gold["total"], gold["distinct"], gold["unique"]):
             if rank == 0:
@@ -400,25 +576,46 @@ def run_b200(args):
         # algorithmic bytes per launch of every kernel of the count pipeline:
         # rows = k-mers one launch handles on this rank; base reads are 0.25 B/base
         rows_r = stats[0] / world          # keys that reach the partition / count stages (after WHERE)
+        rows_tested_r = n_rows_total / world   # start positions one rank's predicate scan tests
         base_b = 8.0 * n_words_local       # the packed words one launch reads (0.25 B/base)
         listed = "filter_collect" in kernels and kernels["filter_collect"]["launches"] > 0
+        from_keys = world > 1 or listed    # level 1 reads a key list (8 B/key) instead of packed words
         ALG = {
             "count_hash": base_b + 16.0 * rows_r, "count_hash_keys": 8.0 * rows_r + 16.0 * rows_r,
             "count_dense": base_b + 4.0 * rows_r, "count_dense_smem": base_b,
-            "part_hist": base_b if world == 1 and not listed else 8.0 * rows_r,
-            "part_scatter": (base_b if world == 1 and not listed else 8.0 * rows_r) + 8.0 * rows_r,
+            # exact level 1 (N > 1 routed forms, WHERE clause): histogram over the packed words or the key list
+            "part_hist": 8.0 * rows_r if listed else base_b,
+            "part_scatter": (8.0 * rows_r if from_keys and listed else base_b) + 8.0 * rows_r,
+            # level 1 fused with the exchange: packed words in, 8 B per k-mer out (local or over NVLink)
+            "part_scatter_peer": (8.0 * rows_r if listed else base_b) + 8.0 * rows_r,
+            # gather form: EVERY base of the sequence is read (all shards), the owned k-mers are written
+            "part_scatter_owned": 8.0 * n_words_total + 8.0 * rows_r,
+            "collect_owned": 8.0 * n_words_total + 8.0 * rows_r,
             # a WHERE clause is evaluated once into a key list: packed words in, matching rows out
             "filter_collect": base_b + 8.0 * rows_r,
             "part_hist2": 8.0 * rows_r, "part_scatter2": 16.0 * rows_r, "count_buckets": 8.0 * rows_r,
             "partition_count": base_b, "partition_write": base_b + 8.0 * rows_r,
         }
+        issue = issue_table()
+        clk_hz = 1e6 * float((clocks or {}).get("sm_mhz") or 1965.0)
+        issue_peak = SM_COUNT * LANES_PER_SM * clk_hz / 1e12  # T lane-instructions / s
         timed = {n: v for n, v in kernels.items() if n in ALG and v["launches"]}
+
+        def kernel_roofline(name, v):
+            per_ms = v["ms"] / v["launches"]
+            if name in issue:  # 0.25 B/base in, every start position tested: instruction issue is the bound
+                ach = issue[name] * rows_tested_r / per_ms / 1e9
+                return {"bound": "issue", "ms_per_launch": per_ms, "achieved": ach, "peak": issue_peak,
+                        "unit": "T lane-instr/s", "frac": ach / issue_peak,
+                        "instructions_per_position": issue[name], "positions_per_launch": rows_tested_r,
+                        "hbm_gbs": ALG[name] / per_ms / 1e6, "hbm_frac": ALG[name] / per_ms / 1e6 / peak}
+            return {"bound": "hbm", "ms_per_launch": per_ms, "achieved": ALG[name] / per_ms / 1e6, "peak": peak,
+                    "unit": "GB/s", "frac": ALG[name] / per_ms / 1e6 / peak}
         roofline = None
         if timed:
             dom = max(timed, key=lambda n: timed[n]["ms"])
             d = timed[dom]
-            per_launch_ms = d["ms"] / d["launches"]
-            achieved = ALG[dom] / per_launch_ms / 1e6
+            r = kernel_roofline(dom, d)
             traffic = None
             try:
                 with open(os.path.join(ROOT, "profiles", "traffic.json")) as f:
@@ -426,28 +623,42 @@ def run_b200(args):
             except Exception:
                 pass
             pipe_bytes = sum(ALG[n] * v["launches"] / args.steps for n, v in timed.items())
-            roofline = {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak, "unit": "GB/s",
-                        "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
-                        "algorithmic_bytes_per_launch": ALG[dom], "ms_per_launch": per_launch_ms,
+            roofline = {"bound": r["bound"], "kernel": dom, "achieved": r["achieved"], "peak": r["peak"],
+                        "unit": r["unit"], "frac": r["frac"], "traffic": traffic, "peak_source": peak_src,
+                        "algorithmic_bytes_per_launch": ALG[dom], "ms_per_launch": r["ms_per_launch"],
                         "share_of_step": d["ms"] / ms,
                         "pipeline": {"algorithmic_bytes_per_step": pipe_bytes,
-                                     "bytes_per_kmer": pipe_bytes / rows_r,
+                                     "bytes_per_kmer": pipe_bytes / max(rows_r, 1),
                                      "achieved": pipe_bytes / (ms / args.steps) / 1e6,
                                      "frac": pipe_bytes / (ms / args.steps) / 1e6 / peak,
                                      "note": "all kernels of one step on this rank / whole step time"},
-                        "per_kernel": {n: {"ms_per_launch": v["ms"] / v["launches"],
-                                           "achieved": ALG[n] / (v["ms"] / v["launches"]) / 1e6,
-                                           "frac": ALG[n] / (v["ms"] / v["launches"]) / 1e6 / peak}
-                                       for n, v in timed.items()}}
-        threads = max(1, min(os.cpu_count() or 1, 64))
-        cv, cdt, cstats, ckind, csample = cpu_reference_rate(n_bases, k, seed, threads, args.cpu_sample, reads)
-        cpu = {"value": cv, "unit": "Gkmer/s", "cores": threads, "kind": ckind,
-               "sample": f"first {csample} bases of the workload ({cdt:.1f} s), " +
-                         ("the reference's own dna.c (unmodified, PostgreSQL API shim) driven like the executor: "
-                          "generate_kmers SRF loop + hash aggregate through kmer_hash/kmer_eq"
-                          if ckind == "reference" else
-                          "oracle port: faithful per-k-mer decode/validate/encode of dna.c:803-825 + "
-                          "kmer_hash/kmer_eq hash aggregate")}
+                        "per_kernel": {n: kernel_roofline(n, v) for n, v in timed.items()}}
+            if r["bound"] == "issue":
+                roofline.update({q: r[q] for q in ("instructions_per_position", "positions_per_launch", "hbm_gbs",
+                                                   "hbm_frac")})
+            if gather:  # bases read from the other GPUs' shards, per step and rank, against the NVLink peer rate
+                nv = 8.0 * (n_words_total - n_words_local)
+                own = timed.get("part_scatter_owned")
+                if own:
+                    per = own["ms"] / own["launches"]
+                    roofline["nvlink"] = {"bytes_per_launch": nv, "achieved": nv / per / 1e6, "peak": NVLINK_PEER_GBS,
+                                          "unit": "GB/s", "frac": nv / per / 1e6 / NVLINK_PEER_GBS,
+                                          "note": "2-bit packed bases read through peer memory inside part_scatter_owned; "
+                                                  "routing 8-byte k-mers instead would move 8*(G-1)/G B per k-mer"}
+        cpu, one = cpu_baselines(n_bases, k, seed, reads, args.cpu_sample, 1_000_000)
+        par = {"gather": "base-range shards (one per GPU, (k-1)-base overlap) mapped into every GPU; each GPU reads all "
+                         "shards over NVLink and counts the k-mers it owns (dnagpu_owner_of); no k-mer exchange, one "
+                         "3-element all-reduce",
+               "peer": "base-range shards, k-mers routed to owner GPUs by hash: level-1 scatter kernel stores into the "
+                       "owners' memory over NVLink, no all-to-all",
+               "fused": "base-range shards, k-mers routed to owner GPUs by hash: level-1 layout + one NCCL all-to-all",
+               "routed": "base-range shards, dnagpu_partition + NCCL all-to-all + dnagpu_count_keys"}
+        e2e_api = ("dnagpu_count_reads(ctx, host_words, n_reads, 150, 5, k, &where, &stats, NULL)" if reads and world == 1 else
+                   "dnagpu_count_kmers(ctx, host_words, n_bases, k, NULL, &stats, NULL)" if world == 1 else
+                   "per rank: pinned host shard -> H2D into its peer-mapped ring buffer, barrier, "
+                   "dnagpu.distributed.count_sharded_gather (dnagpu_count with an owner restriction), all-reduce"
+                   if gather else
+                   "per rank: dnagpu_seq_upload* of its shard + dnagpu.distributed.count_sharded_" + args.exchange)
         line = {
             "metric": METRIC, "value": value, "unit": "Gkmer/s", "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True,
@@ -455,28 +666,24 @@ def run_b200(args):
             "config": {"workload": desc, "n_bases": n_bases, "k": k, "seed": seed,
                        "unit_of_value": "k-mers generated and tested per second" if reads else "k-mers counted per second",
                        "repeat_every": REPEAT_EVERY, "block_bases": 1024,
-                       "l2": "inputs (packed words + hash table) larger than L2; no flush needed",
-                       "parallelism": "single GPU" if world == 1 else
-                       f"{world} base-range shards, k-mers routed to owner GPUs by hash; exchange={args.exchange} (" +
-                       {"peer": "level-1 scatter kernel stores into the owners' memory over NVLink, no all-to-all",
-                        "fused": "level-1 layout + one NCCL all-to-all",
-                        "routed": "dnagpu_partition + NCCL all-to-all + dnagpu_count_keys"}[args.exchange] + ")",
+                       "l2": "inputs (packed words + partition buffers) larger than L2; no flush needed"
+                       if n_bases >= 100_000_000 else "input smaller than L2 (the reference's own CPU-sized case)",
+                       "parallelism": "single GPU" if world == 1 else f"{world} GPUs, exchange={args.exchange}: " + par[args.exchange],
                        "load_factor": args.load_factor or 0.5},
             "result": {"total": stats[0], "distinct": stats[1], "unique": stats[2],
                        "oracle": "equal to tests/golden/big_expected.json (CPU oracle at the full size)"
                        if gold is not None else "not compared (size overridden or no golden entry)"},
             "e2e": {"value": e2e_value, "unit": "Gkmer/s", "steps": args.e2e_steps,
                     "ms_per_step": 1e3 * e2e_s / args.e2e_steps,
-                    "h2d_bytes_per_step": int(8 * reads["n_reads"] * reads["stride"]) if reads
-                    else int(8 * ((n_bases + 31) // 32)), "d2h_bytes_per_step": 24 * world,
-                    "api": ("dnagpu_count_reads(ctx, host_words, n_reads, 150, 5, k, &where, &stats, NULL)" if reads else
-                            "dnagpu_count_kmers(ctx, host_words, n_bases, k, NULL, &stats, NULL)")},
+                    "h2d_bytes_per_step": int(8 * n_words_total), "d2h_bytes_per_step": 24 * world, "api": e2e_api},
             "gpu_launches": launches, "kernels": kernels, "roofline": roofline, "cpu_baseline": cpu,
-            "extract": extract, "clocks": clocks,
+            "cpu_baseline_1thread": one, "extract": extract, "clocks": clocks,
         }
         print(json.dumps(line), flush=True)
     if px is not None:
         px.close()
+    if ring is not None:
+        ring.close()
     seq.free()
     ctx.close()
     if world > 1:
@@ -491,15 +698,19 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--workload", default="c4", choices=sorted(WORKLOADS))
+    ap.add_argument("--k", type=int, default=0, help="override k (c5: one k of the sweep instead of all 30)")
     ap.add_argument("--n-bases", type=int, default=0, help="override the workload size (debugging)")
     ap.add_argument("--e2e-steps", type=int, default=3)
     ap.add_argument("--load-factor", type=float, default=0.0)
     ap.add_argument("--cpu-sample", type=int, default=16_000_000)
+    ap.add_argument("--cpu-large-sample", type=int, default=0,
+                    help="--impl reference: bases per step (e.g. 100000000: a table that no longer fits the CPU caches)")
     ap.add_argument("--no-extract", action="store_true")
-    ap.add_argument("--chunks", type=int, default=4, help="N > 1: digit sub-ranges the exchange is pipelined in")
-    ap.add_argument("--exchange", default="peer", choices=["peer", "fused", "routed"],
-                    help="N > 1: peer = scatter kernel stores into the owners' memory over NVLink (no all-to-all); "
-                         "fused = level-1 layout + NCCL all-to-all; routed = separate dnagpu_partition pass")
+    ap.add_argument("--chunks", type=int, default=4, help="--exchange fused: digit sub-ranges the exchange is pipelined in")
+    ap.add_argument("--exchange", default="gather", choices=["gather", "peer", "fused", "routed"],
+                    help="N > 1: gather = every GPU reads all shards over NVLink and counts the k-mers it owns; "
+                         "peer = scatter kernel stores routed k-mers into the owners' memory; fused = level-1 layout + "
+                         "NCCL all-to-all; routed = separate dnagpu_partition pass")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
     if args.impl == "reference":

@@ -2,12 +2,14 @@
  * bench.c -- stand-alone C harness over the libdnagpu C ABI (no Python, no torch).
  *
  *   dnagpu_bench [--bases N] [--k K] [--seed S] [--steps T] [--reads R --read-bases B]
- *                [--prefix ACGT] [--pattern IUPAC] [--host]
+ *                [--prefix ACGT] [--pattern IUPAC] [--host] [--gpus G]
  *
  * Generates the synthetic workload on the device (include/dnagpu_synth.h), runs the
  * GROUP BY kmer query T times and prints one JSON line with the per-kernel CUDA-event
  * times reported by dnagpu_profile_*.  --host times the host-buffer entry point
- * (dnagpu_count_kmers: H2D + count + D2H of the aggregates) instead.
+ * (dnagpu_count_kmers: H2D + count + D2H of the aggregates) instead.  --gpus G (with --host) runs that
+ * entry point on a multi-GPU context (dnagpu_create_multi over devices 0 .. G-1): shards uploaded on all
+ * PCIe links at once, every GPU counts the k-mers it owns out of the whole sequence.
  */
 #include <stdio.h>
 #include <stdlib.h>
@@ -37,7 +39,8 @@ int main(int argc, char **argv)
 {
     uint64_t n_bases = 100000000ull, seed = 2, n_reads = 0;
     uint32_t read_bases = 150;
-    int k = 21, steps = 5, host = 0, i;
+    int k = 21, steps = 5, host = 0, gpus = 1, i;
+    int devices[16];
     const char *prefix = NULL, *pattern = NULL;
     dnagpu_ctx *ctx = NULL;
     dnagpu_seq *seq = NULL;
@@ -57,12 +60,18 @@ int main(int argc, char **argv)
         else if (!strcmp(argv[i], "--prefix") && i + 1 < argc) prefix = argv[++i];
         else if (!strcmp(argv[i], "--pattern") && i + 1 < argc) pattern = argv[++i];
         else if (!strcmp(argv[i], "--host")) host = 1;
+        else if (!strcmp(argv[i], "--gpus") && i + 1 < argc) gpus = atoi(argv[++i]);
         else {
             fprintf(stderr, "unknown argument %s\n", argv[i]);
             return 2;
         }
     }
-    if (dnagpu_create(&ctx, 0) != DNAGPU_OK) {
+    if (gpus < 1 || gpus > 16 || (gpus > 1 && !host)) {
+        fprintf(stderr, "--gpus takes 1..16 and needs --host (the multi-GPU entry point is dnagpu_count_kmers)\n");
+        return 2;
+    }
+    for (i = 0; i < gpus; i++) devices[i] = i;
+    if ((gpus > 1 ? dnagpu_create_multi(&ctx, devices, gpus) : dnagpu_create(&ctx, 0)) != DNAGPU_OK) {
         fprintf(stderr, "dnagpu_create: %s\n", dnagpu_last_error(NULL));
         return 1;
     }
@@ -105,10 +114,10 @@ int main(int argc, char **argv)
         dt = now_s() - t0;
         CHECK(dnagpu_profile_dump(ctx, prof, sizeof prof));
     }
-    printf("{\"device\": \"%s\", \"sms\": %d, \"k\": %d, \"rows\": %llu, \"steps\": %d, \"entry\": \"%s\", "
+    printf("{\"device\": \"%s\", \"sms\": %d, \"gpus\": %d, \"k\": %d, \"rows\": %llu, \"steps\": %d, \"entry\": \"%s\", "
            "\"ms_per_step\": %.4f, \"gkmer_s\": %.3f, \"total\": %llu, \"distinct\": %llu, \"unique\": %llu, "
            "\"kernels_ms_total\": %s}\n",
-           name, sms, k, (unsigned long long)dnagpu_seq_kmer_count(seq, k), steps,
+           name, sms, dnagpu_device_count(ctx), k, (unsigned long long)dnagpu_seq_kmer_count(seq, k), steps,
            host ? "dnagpu_count_kmers (host words)" : "dnagpu_count (device resident)", 1e3 * dt / steps,
            (double)dnagpu_seq_kmer_count(seq, k) * steps / dt / 1e9, (unsigned long long)st.total,
            (unsigned long long)st.distinct, (unsigned long long)st.unique, prof);

@@ -18,6 +18,7 @@
 #include <cstring>
 #include <new>
 #include <string>
+#include <thread>
 #include <unordered_set>
 #include <vector>
 
@@ -42,7 +43,12 @@ struct dnagpu_ctx {
     int bins_ctas_per_sm = 4;            /* resident CTAs of k_count_buckets_bins (occupancy query) */
     unsigned long long *h_ctr = nullptr; /* pinned mirror */
     cudaStream_t copy_stream = nullptr; /* H2D of the host-buffer calls, overlapped with level 1 */
+    /* dnagpu_create_multi: the contexts of devices[1..] (this one is devices[0]) and one shard buffer per GPU */
+    std::vector<dnagpu_ctx *> peers;
+    std::vector<uint64_t *> shard_buf; /* plain cudaMalloc (peer-accessible), grown on demand */
+    std::vector<uint64_t> shard_cap;   /* words */
     bool profiling = false;
+    bool plane_filter = false; /* DNAGPU_WHERE_FLAG_PLANES of the running query */
     bool force_exact = false; /* DNAGPU_COUNT_FLAG_EXACT of the running query: no optimistic partition regions */
     std::vector<ProfRec> prof;
     /* live child handles: dnagpu_destroy releases their device memory and orphans them (ctx = NULL), so a
@@ -80,6 +86,7 @@ struct dnagpu_table {
     int k = 0;
     uint64_t rows = 0;
     uint64_t *d_kmers = nullptr, *d_counts = nullptr;
+    std::vector<dnagpu_table *> parts; /* multi-GPU result: the per-GPU tables (disjoint key sets), in order */
 };
 
 struct dnagpu_index {
@@ -262,6 +269,8 @@ extern "C" int dnagpu_create(dnagpu_ctx **out, int device)
     SMEM_ATTR(k_filter_collect<kSingle>);
     SMEM_ATTR(k_filter_collect<kFixed>);
     SMEM_ATTR(k_filter_collect<kRagged>);
+    SMEM_ATTR(k_filter_collect_sa<kSingle>);
+    SMEM_ATTR(k_filter_collect_sa<kFixed>);
     SMEM_ATTR((k_partition_write<kSingle, false>));
     SMEM_ATTR((k_partition_write<kSingle, true>));
     SMEM_ATTR((k_partition_write<kFixed, false>));
@@ -325,6 +334,54 @@ extern "C" int dnagpu_create(dnagpu_ctx **out, int device)
     return DNAGPU_OK;
 }
 
+extern "C" int dnagpu_create_multi(dnagpu_ctx **out, const int *devices, int n_devices)
+{
+    if (!out || !devices || n_devices < 1 || n_devices > kMaxPieces)
+        return fail(nullptr, DNAGPU_EARG, "dnagpu_create_multi: need 1..%d devices", kMaxPieces);
+    *out = nullptr;
+    for (int a = 0; a < n_devices; ++a)
+        for (int b = a + 1; b < n_devices; ++b)
+            if (devices[a] == devices[b]) return fail(nullptr, DNAGPU_EARG, "device %d is listed twice", devices[a]);
+    dnagpu_ctx *ctx = nullptr;
+    TRY(dnagpu_create(&ctx, devices[0]));
+    for (int d = 1; d < n_devices; ++d) {
+        dnagpu_ctx *p = nullptr;
+        int rc = dnagpu_create(&p, devices[d]);
+        if (rc != DNAGPU_OK) {
+            dnagpu_destroy(ctx);
+            return rc;
+        }
+        ctx->peers.push_back(p);
+    }
+    /* every GPU reads every other GPU's shard: peer access for all ordered pairs */
+    for (int a = 0; a < n_devices; ++a) {
+        cudaSetDevice(devices[a]);
+        for (int b = 0; b < n_devices; ++b) {
+            if (a == b) continue;
+            int can = 0;
+            cudaDeviceCanAccessPeer(&can, devices[a], devices[b]);
+            cudaError_t e = can ? cudaDeviceEnablePeerAccess(devices[b], 0) : cudaErrorPeerAccessUnsupported;
+            if (e == cudaErrorPeerAccessAlreadyEnabled) {
+                cudaGetLastError();
+                e = cudaSuccess;
+            }
+            if (e != cudaSuccess) {
+                cudaGetLastError();
+                dnagpu_destroy(ctx);
+                return fail(nullptr, DNAGPU_ENODEVICE, "GPU %d cannot map the memory of GPU %d (%s): no multi-GPU context",
+                            devices[a], devices[b], cudaGetErrorString(e));
+            }
+        }
+    }
+    cudaSetDevice(devices[0]);
+    ctx->shard_buf.assign((size_t)n_devices, nullptr);
+    ctx->shard_cap.assign((size_t)n_devices, 0);
+    *out = ctx;
+    return DNAGPU_OK;
+}
+
+extern "C" int dnagpu_device_count(const dnagpu_ctx *ctx) { return ctx ? 1 + (int)ctx->peers.size() : 0; }
+
 static void seq_release(dnagpu_seq *s);
 static void table_release(dnagpu_table *t);
 static void index_release(dnagpu_index *ix);
@@ -344,6 +401,14 @@ extern "C" void dnagpu_destroy(dnagpu_ctx *ctx)
     ctx->tables.clear();
     ctx->indexes.clear();
     cudaStreamSynchronize(ctx->stream);
+    for (size_t d = 0; d < ctx->shard_buf.size(); ++d)
+        if (ctx->shard_buf[d]) {
+            cudaSetDevice(d == 0 ? ctx->device : ctx->peers[d - 1]->device);
+            cudaFree(ctx->shard_buf[d]);
+        }
+    for (dnagpu_ctx *p : ctx->peers) dnagpu_destroy(p);
+    ctx->peers.clear();
+    cudaSetDevice(ctx->device);
     for (auto &r : ctx->prof) {
         cudaEventDestroy(r.e0);
         cudaEventDestroy(r.e1);
@@ -689,10 +754,11 @@ extern "C" int dnagpu_seq_wrap_pieces(dnagpu_ctx *ctx, const void *const *d_word
     uint64_t next = 0;
     for (uint32_t q = 0; q < n_pieces; ++q) {
         const uint32_t i = order[q];
-        if (!d_words[i] || ((uintptr_t)d_words[i] & 15) || (first_base[i] & 31) || first_base[i] != next ||
-            (q + 1 < n_pieces && (n_starts[i] & 31)))
-            return fail(ctx, DNAGPU_EARG,
-                        "piece %u: need a 16-byte aligned device pointer and base ranges (multiples of 32) that tile the sequence", i);
+        if (!d_words[i] || ((uintptr_t)d_words[i] & 15) || (first_base[i] & 31))
+            return fail(ctx, DNAGPU_EARG, "piece %u: need a 16-byte aligned device pointer and a first base that is a multiple of 32", i);
+        if (n_starts[i] == 0) continue; /* a GPU past the end of a short sequence */
+        if (first_base[i] != next || ((n_starts[i] & 31) && next + n_starts[i] < n_bases_total))
+            return fail(ctx, DNAGPU_EARG, "piece %u: the base ranges (multiples of 32) must tile the sequence", i);
         next += n_starts[i];
     }
     if (next < n_bases_total) return fail(ctx, DNAGPU_EARG, "the pieces cover %llu of %llu bases", (unsigned long long)next,
@@ -833,7 +899,7 @@ static int iupac_set(char c)
 static int check_filter_literals(dnagpu_ctx *ctx, const dnagpu_where *f)
 {
     if (!f) return DNAGPU_OK;
-    if (f->reserved != 0) return fail(ctx, DNAGPU_EARG, "dnagpu_where.reserved must be 0");
+    if (f->flags & ~DNAGPU_WHERE_FLAG_PLANES) return fail(ctx, DNAGPU_EARG, "unknown bit in dnagpu_where.flags");
     if (f->prefix_len < 0 || f->prefix_len > DNAGPU_MAX_K)
         return fail(ctx, DNAGPU_EARG, "prefix_len out of range");
     if (f->prefix_len > 0 && f->prefix_len < 32 && (f->prefix_bits >> (2 * f->prefix_len)))
@@ -855,6 +921,7 @@ static int build_pred(dnagpu_ctx *ctx, const dnagpu_where *f, int k, uint64_t n_
 {
     *active = false;
     p->ma = p->mt = p->mc = p->mg = ~0ull;
+    if (ctx) ctx->plane_filter = f && (f->flags & DNAGPU_WHERE_FLAG_PLANES);
     if (!f || (f->prefix_len == 0 && !f->qkmer)) return DNAGPU_OK;
     if (n_rows == 0) return DNAGPU_OK;
     if (f->prefix_len > k) return fail(ctx, DNAGPU_EPREFIX_LEN, "%s", dnagpu_strerror(DNAGPU_EPREFIX_LEN));
@@ -1838,8 +1905,37 @@ static int count_kmers_pipelined(dnagpu_ctx *ctx, const uint64_t *words, uint64_
 }
 
 /* One predicate scan, matches appended in no particular order. */
+/* the Shift-And tables of a predicate: M[b] bit (i + 32 - k) = base b is allowed at pattern position i */
+static SaPred sa_pred_of(const Pred &p, int k)
+{
+    const uint64_t plane[4] = {p.ma, p.mt, p.mc, p.mg};
+    SaPred sp;
+    for (int b = 0; b < 4; ++b) {
+        uint32_t m = 0;
+        for (int i = 0; i < k; ++i)
+            if ((plane[b] >> (2 * i)) & 1) m |= 1u << (i + 32 - k);
+        sp.m[b] = m;
+    }
+    sp.inj = 1u << (32 - k);
+    return sp;
+}
+
 static int collect_launch(dnagpu_ctx *ctx, int layout, const SeqView &v, const Pred &p, int k, uint64_t *d_out, uint64_t cap)
 {
+    if (layout != kRagged && !ctx->plane_filter) { /* Shift-And over the base stream: 6 instructions per base */
+        const SaPred sp = sa_pred_of(p, k);
+        const uint64_t runs = layout == kSingle ? (v.n_items + kSaItems - 1) / kSaItems
+                                                : v.n_seqs * ((v.items_per_seq + kSaItems - 1) / kSaItems);
+        const int smem = kSaStage * (int)sizeof(uint64_t);
+        return launch(ctx, "filter_collect", [&] {
+            if (layout == kSingle)
+                k_filter_collect_sa<kSingle><<<grid_for(runs, kThreads), kThreads, smem, ctx->stream>>>(
+                    v, sp, kmer_mask(k), k, cap, ctx->d_ctr + C_CURSOR, d_out);
+            else
+                k_filter_collect_sa<kFixed><<<grid_for(runs, kThreads), kThreads, smem, ctx->stream>>>(
+                    v, sp, kmer_mask(k), k, cap, ctx->d_ctr + C_CURSOR, d_out);
+        });
+    }
     const unsigned tiles = grid_for(v.n_items, kThreads);
     const int smem = kThreads * 32 * (int)sizeof(uint64_t);
     DISPATCH_LAYOUT(layout, TRY(launch(ctx, "filter_collect", [&] {
@@ -2118,6 +2214,97 @@ extern "C" int dnagpu_count_keys(dnagpu_ctx *ctx, const uint64_t *d_keys, uint64
     return count_any(ctx, in, k, opts, stats, table);
 }
 
+/* The host-buffer GROUP BY on every GPU of a multi context: shard d of the packed words goes to GPU d (H2D on
+ * all PCIe links at once), then every GPU walks ALL shards through peer memory -- its own first, the others in
+ * ring order -- and counts the k-mers it owns.  One host thread per GPU drives its (synchronous) count. */
+static int count_kmers_multi(dnagpu_ctx *ctx, const uint64_t *words, uint64_t n_bases, int k, dnagpu_stats *stats,
+                             dnagpu_table **table)
+{
+    const int G = 1 + (int)ctx->peers.size();
+    std::vector<dnagpu_ctx *> cx(1, ctx);
+    cx.insert(cx.end(), ctx->peers.begin(), ctx->peers.end());
+    const uint64_t n_words = words_of(n_bases);
+    const uint64_t per = ((n_bases + G - 1) / G + 31) / 32 * 32, end = (n_bases + 31) / 32 * 32;
+    std::vector<uint64_t> first(G), starts(G);
+    for (int d = 0; d < G; ++d) {
+        first[d] = std::min<uint64_t>((uint64_t)d * per, end);
+        starts[d] = n_bases > first[d] ? std::min(per, n_bases - first[d]) : 0;
+        /* the piece: its bases + the 31-base overlap, >= 1 zero pad word, an even number of words */
+        const uint64_t held = std::min(n_bases, first[d] + starts[d] + 31) - std::min(n_bases, first[d]);
+        const uint64_t w_copy = std::min(words_of(held), n_words - std::min(n_words, first[d] / 32));
+        const uint64_t w_alloc = (words_of(held) + 3) & ~1ull;
+        CU(ctx, cudaSetDevice(cx[d]->device));
+        if (ctx->shard_cap[d] < w_alloc) {
+            if (ctx->shard_buf[d]) cudaFree(ctx->shard_buf[d]);
+            ctx->shard_buf[d] = nullptr;
+            ctx->shard_cap[d] = 0;
+            cudaError_t e = cudaMalloc((void **)&ctx->shard_buf[d], w_alloc * 8);
+            if (e != cudaSuccess) {
+                cudaGetLastError();
+                return fail(ctx, DNAGPU_ENOMEM, "shard of %llu bytes on GPU %d: %s", (unsigned long long)(w_alloc * 8),
+                            cx[d]->device, cudaGetErrorString(e));
+            }
+            ctx->shard_cap[d] = w_alloc;
+        }
+        if (w_copy)
+            CU(ctx, cudaMemcpyAsync(ctx->shard_buf[d], words + first[d] / 32, w_copy * 8, cudaMemcpyHostToDevice, cx[d]->stream));
+        CU(ctx, cudaMemsetAsync(ctx->shard_buf[d] + w_copy, 0, (w_alloc - w_copy) * 8, cx[d]->stream));
+    }
+    for (int d = 0; d < G; ++d) { /* every shard must be resident before anybody reads it */
+        CU(ctx, cudaSetDevice(cx[d]->device));
+        CU(ctx, cudaStreamSynchronize(cx[d]->stream));
+    }
+    std::vector<int> rc((size_t)G, DNAGPU_OK);
+    std::vector<dnagpu_stats> st((size_t)G);
+    std::vector<dnagpu_table *> tb((size_t)G, nullptr);
+    std::vector<std::thread> th;
+    for (int d = 0; d < G; ++d)
+        th.emplace_back([&, d] {
+            cudaSetDevice(cx[d]->device);
+            const void *ptr[kMaxPieces];
+            uint64_t fb[kMaxPieces], ns[kMaxPieces];
+            for (int i = 0; i < G; ++i) {
+                const int p = (d + i) % G;
+                ptr[i] = ctx->shard_buf[p];
+                fb[i] = first[p];
+                ns[i] = starts[p];
+            }
+            dnagpu_seq *seq = nullptr;
+            rc[d] = dnagpu_seq_wrap_pieces(cx[d], ptr, fb, ns, (uint32_t)G, n_bases, &seq);
+            if (rc[d] != DNAGPU_OK) return;
+            dnagpu_count_opts o = {DNAGPU_COUNT_AUTO, 0, 0.0, 0, (uint32_t)G, (uint32_t)d};
+            rc[d] = dnagpu_count(cx[d], seq, k, nullptr, &o, &st[d], table ? &tb[d] : nullptr);
+            dnagpu_seq_free(seq);
+        });
+    for (auto &t : th) t.join();
+    CU(ctx, cudaSetDevice(ctx->device));
+    for (int d = 0; d < G; ++d)
+        if (rc[d] != DNAGPU_OK) {
+            for (dnagpu_table *t : tb) dnagpu_table_free(t);
+            return fail(ctx, rc[d], "GPU %d: %s", cx[d]->device, dnagpu_last_error(cx[d]));
+        }
+    stats->total = stats->distinct = stats->unique = 0;
+    for (int d = 0; d < G; ++d) {
+        stats->total += st[d].total;
+        stats->distinct += st[d].distinct;
+        stats->unique += st[d].unique;
+    }
+    if (table) {
+        dnagpu_table *t = new (std::nothrow) dnagpu_table();
+        if (!t) {
+            for (dnagpu_table *p : tb) dnagpu_table_free(p);
+            return fail(ctx, DNAGPU_ENOMEM, "out of host memory");
+        }
+        t->ctx = ctx;
+        ctx->tables.insert(t);
+        t->k = k;
+        t->rows = stats->distinct;
+        t->parts = tb;
+        *table = t;
+    }
+    return DNAGPU_OK;
+}
+
 extern "C" int dnagpu_count_kmers(dnagpu_ctx *ctx, const uint64_t *words, uint64_t n_bases, int k,
                                   const dnagpu_where *filter, dnagpu_stats *stats,
                                   dnagpu_table **table)
@@ -2125,6 +2312,12 @@ extern "C" int dnagpu_count_kmers(dnagpu_ctx *ctx, const uint64_t *words, uint64
     if (!ctx) return fail(ctx, DNAGPU_EARG, "dnagpu_count_kmers: NULL ctx");
     TRY(check_k(ctx, k));
     TRY(check_filter_literals(ctx, filter));
+    if (!ctx->peers.empty() && words && (!filter || (filter->prefix_len == 0 && !filter->qkmer)) &&
+        rows_of(n_bases, k) >= (1ull << 21)) { /* smaller inputs are not worth the fan-out */
+        dnagpu_stats local;
+        if (table) *table = nullptr;
+        return count_kmers_multi(ctx, words, n_bases, k, stats ? stats : &local, table);
+    }
     if (words && (!filter || (filter->prefix_len == 0 && !filter->qkmer))) {
         dnagpu_stats local;
         bool done = false;
@@ -2231,6 +2424,28 @@ extern "C" int dnagpu_count_reads(dnagpu_ctx *ctx, const uint64_t *words, uint64
 
 /* ---- the grouped result -------------------------------------------------------------------- */
 extern "C" uint64_t dnagpu_table_rows(const dnagpu_table *t) { return t ? t->rows : 0; }
+
+/* rows [offset, offset + n) of a multi-GPU table: walk the per-GPU tables */
+static int table_fetch_parts(dnagpu_ctx *ctx, const dnagpu_table *t, uint64_t offset, uint64_t n, uint64_t *kmers,
+                             uint64_t *counts)
+{
+    uint64_t base = 0;
+    for (const dnagpu_table *p : t->parts) {
+        if (n == 0) break;
+        if (offset < base + p->rows) {
+            const uint64_t o = offset - base, m = std::min(n, p->rows - o);
+            int rc = dnagpu_table_fetch(p->ctx, p, o, m, kmers, counts);
+            if (rc != DNAGPU_OK) return fail(ctx, rc, "%s", dnagpu_last_error(p->ctx));
+            offset += m;
+            n -= m;
+            if (kmers) kmers += m;
+            if (counts) counts += m;
+        }
+        base += p->rows;
+    }
+    CU(ctx, cudaSetDevice(ctx->device));
+    return DNAGPU_OK;
+}
 extern "C" int dnagpu_table_k(const dnagpu_table *t) { return t ? t->k : 0; }
 
 extern "C" int dnagpu_table_fetch(dnagpu_ctx *ctx, const dnagpu_table *t, uint64_t offset,
@@ -2239,6 +2454,7 @@ extern "C" int dnagpu_table_fetch(dnagpu_ctx *ctx, const dnagpu_table *t, uint64
     if (!ctx || !t) return fail(ctx, DNAGPU_EARG, "dnagpu_table_fetch: NULL argument");
     CHECK_OWNED(ctx, t, "the table");
     if (offset > t->rows || n > t->rows - offset) return fail(ctx, DNAGPU_EARG, "row range outside the table");
+    if (!t->parts.empty()) return table_fetch_parts(ctx, t, offset, n, kmers, counts);
     CU(ctx, cudaSetDevice(ctx->device));
     if (n && kmers) CU(ctx, cudaMemcpyAsync(kmers, t->d_kmers + offset, n * 8, cudaMemcpyDeviceToHost, ctx->stream));
     if (n && counts) CU(ctx, cudaMemcpyAsync(counts, t->d_counts + offset, n * 8, cudaMemcpyDeviceToHost, ctx->stream));
@@ -2250,6 +2466,7 @@ extern "C" int dnagpu_table_device(const dnagpu_table *t, const uint64_t **d_kme
                                    const uint64_t **d_counts)
 {
     if (!t) return fail(nullptr, DNAGPU_EARG, "table is NULL");
+    if (!t->parts.empty()) return fail(t->ctx, DNAGPU_EARG, "the rows of a multi-GPU table live on several GPUs: use dnagpu_table_fetch");
     if (d_kmers) *d_kmers = t->d_kmers;
     if (d_counts) *d_counts = t->d_counts;
     return DNAGPU_OK;
@@ -2258,6 +2475,8 @@ extern "C" int dnagpu_table_device(const dnagpu_table *t, const uint64_t **d_kme
 static void table_release(dnagpu_table *t)
 {
     if (!t->ctx) return;
+    for (dnagpu_table *p : t->parts) dnagpu_table_free(p); /* the peers' contexts are still alive here */
+    t->parts.clear();
     cudaSetDevice(t->ctx->device);
     dfree(t->ctx, t->d_kmers);
     dfree(t->ctx, t->d_counts);

@@ -477,6 +477,134 @@ __global__ void __launch_bounds__(kThreads) k_filter_collect(SeqView sv, Pred p,
     }
 }
 
+/* ---- the same WHERE clause as a Shift-And automaton over the base stream ------------------------------
+ * SURVEY 7 K2(b); replaces the per-base loop of contains() (dna.c:1114-1125).  State D has one bit per pattern
+ * position, pattern position i at bit i + 32 - k, so that a full match is the SIGN bit for every k:
+ *     t = F & M[base];   F = (t << 1) | (1 << (32 - k));   match of the k-mer ENDING at this base = t >> 31
+ * with M[b] = the positions whose IUPAC set (intersected with the ^@ prefix base) allows base b.  Per base:
+ * two instructions to turn the 2-bit base into a table offset, one shared-memory load of M[b] (four words in
+ * four banks: any mix of lanes is one wavefront), LOP3, IADD3, and one funnel shift that collects the match
+ * bits -- 6 instructions against the ~ 19 per START position of the plane test above.  A thread walks a run
+ * of up to kSaItems consecutive items (128 starts) of one sequence = up to 159 bases, the first k-1 of them
+ * warm-up: a 150-base read is exactly one run.  End-position matches are turned into start-position masks
+ * by one 160-bit funnel shift by k-1, after which rank / stage / store work as in the plane form. */
+constexpr int kSaItems = 4;
+constexpr int kSaStage = 8192; /* staged matches per round (64 KB) */
+
+struct SaPred {
+    uint32_t m[4]; /* M[A], M[T], M[C], M[G], left-aligned */
+    uint32_t inj;  /* 1 << (32 - k) */
+};
+
+/* 32 bases of one half-word pair: steps the automaton, returns the 32 end-match bits (bit j = base j) */
+__device__ __forceinline__ uint32_t sa_word(uint64_t w, uint32_t lut_sa, uint32_t inj, uint32_t &F)
+{
+    const uint32_t lo = (uint32_t)w, hi = (uint32_t)(w >> 32);
+    uint32_t e = 0;
+#pragma unroll
+    for (int j = 0; j < 32; ++j) {
+        const uint32_t h = j < 16 ? lo : hi;
+        const int s = 2 * (j & 15);
+        /* shared-memory address of M[base]: base * 4 OR-ed into the 16-byte aligned table address (one LOP3) */
+        const uint32_t addr = ((s >= 2 ? h >> (s - 2) : h << 2) & 12u) | lut_sa;
+        uint32_t m;
+        asm("ld.shared.u32 %0, [%1];" : "=r"(m) : "r"(addr));
+        const uint32_t t = F & m;
+        F = t + t + inj;
+        e = __funnelshift_l(t, e, 1); /* shifts the sign bit of t in at bit 0: step j ends at bit 31 - j */
+    }
+    return __brev(e);
+}
+
+/* run r -> (first word, starts valid in the run); runs never span sequences */
+template <int L>
+__device__ __forceinline__ const uint64_t *locate_run(const SeqView &sv, uint64_t r, uint32_t &valid)
+{
+    static_assert(L == kSingle || L == kFixed, "Shift-And runs: single sequences and fixed-stride reads");
+    if (L == kSingle) {
+        const uint64_t left = sv.n_rows - r * (32 * kSaItems);
+        valid = left < 32 * kSaItems ? (uint32_t)left : 32 * kSaItems;
+        return sv.words + r * kSaItems;
+    }
+    const uint64_t runs_per_seq = (sv.items_per_seq + kSaItems - 1) / kSaItems;
+    const uint64_t q = r / runs_per_seq, ri = r - q * runs_per_seq;
+    const uint64_t left = sv.rows_per_seq - ri * (32 * kSaItems);
+    valid = left < 32 * kSaItems ? (uint32_t)left : 32 * kSaItems;
+    return sv.words + q * sv.stride + ri * kSaItems;
+}
+
+template <int L>
+__device__ __forceinline__ uint64_t n_runs_of(const SeqView &sv)
+{
+    if (L == kSingle) return (sv.n_items + kSaItems - 1) / kSaItems;
+    return sv.n_seqs * ((sv.items_per_seq + kSaItems - 1) / kSaItems);
+}
+
+/* start-position match masks of one run; w[] receives its packed words */
+template <int L>
+__device__ __forceinline__ void sa_run_masks(const SeqView &sv, uint32_t lut, uint32_t inj, int k, uint64_t r,
+                                             uint64_t (&w)[kSaItems + 1], uint32_t (&sm)[kSaItems])
+{
+    uint32_t valid;
+    const uint64_t *p = locate_run<L>(sv, r, valid);
+    const int n_items = (int)((valid + 31) >> 5);
+#pragma unroll
+    for (int i = 0; i <= kSaItems; ++i) w[i] = i <= n_items ? ld_nc(p + i) : 0; /* + the halo word */
+    uint32_t F = inj, e[kSaItems + 1];
+#pragma unroll
+    for (int i = 0; i <= kSaItems; ++i) e[i] = i <= n_items ? sa_word(w[i], lut, inj, F) : 0u;
+#pragma unroll
+    for (int i = 0; i < kSaItems; ++i) {
+        const uint32_t m = __funnelshift_r(e[i], e[i + 1], k - 1); /* the k-mer starting at s ends at s + k - 1 */
+        const int c = (int)valid - 32 * i;
+        sm[i] = c >= 32 ? m : c > 0 ? (m & ((1u << c) - 1u)) : 0u;
+    }
+}
+
+template <int L>
+__global__ void __launch_bounds__(kThreads) k_filter_collect_sa(SeqView sv, SaPred sp, uint64_t mask, int k, uint64_t cap,
+                                                                unsigned long long *__restrict__ cursor,
+                                                                uint64_t *__restrict__ out)
+{
+    extern __shared__ uint64_t stage[]; /* kSaStage entries */
+    __shared__ __align__(16) uint32_t lut[4];
+    __shared__ unsigned long long base_s;
+    if (threadIdx.x < 4) lut[threadIdx.x] = sp.m[threadIdx.x];
+    __syncthreads();
+    const uint32_t lut_sa = (uint32_t)__cvta_generic_to_shared(lut);
+    const uint64_t n_runs = n_runs_of<L>(sv);
+    const uint64_t r = (uint64_t)blockIdx.x * kThreads + threadIdx.x;
+    uint64_t w[kSaItems + 1];
+    uint32_t sm[kSaItems] = {0, 0, 0, 0};
+    if (r < n_runs) sa_run_masks<L>(sv, lut_sa, sp.inj, k, r, w, sm);
+    uint32_t n = 0;
+#pragma unroll
+    for (int i = 0; i < kSaItems; ++i) n += __popc(sm[i]);
+    uint32_t total;
+    const uint32_t rank0 = block_exscan(n, &total);
+    if (threadIdx.x == 0 && total) base_s = atomicAdd(cursor, (unsigned long long)total);
+    __syncthreads();
+    if (total == 0 || base_s + total > cap) return; /* uniform; the cursor still counts what did not fit */
+    uint64_t *dst = out + base_s;
+    for (uint32_t round = 0; round < total; round += kSaStage) { /* one round unless > 8192 rows of the tile match */
+        uint32_t rank = rank0;
+#pragma unroll
+        for (int i = 0; i < kSaItems; ++i) {
+            uint32_t m = sm[i];
+            while (m) {
+                const int j = __ffs(m) - 1;
+                m &= m - 1;
+                if (rank >= round && rank < round + kSaStage) stage[rank - round] = window(w[i], w[i + 1], 2 * j) & mask;
+                ++rank;
+            }
+        }
+        __syncthreads();
+        const uint32_t cnt = min((uint32_t)kSaStage, total - round);
+        for (uint32_t q = threadIdx.x; q < cnt; q += kThreads) st_cs(dst + round + q, stage[q]);
+        __syncthreads();
+    }
+}
+
 /* the same predicates over a materialised kmer column (seq scan of test.sql:220-262) */
 constexpr int kKeysPerThread = 8;
 __global__ void __launch_bounds__(kThreads) k_filter_keys_count(const uint64_t *__restrict__ keys,

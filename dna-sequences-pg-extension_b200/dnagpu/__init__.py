@@ -33,11 +33,15 @@ def _check(lib, ctx_handle, rc):
         raise DnaError((msg or lib.dnagpu_strerror(rc)).decode(), code=rc)
 
 
-def _where(prefix, pattern):
+WHERE_FLAG_PLANES = 1  # DNAGPU_WHERE_FLAG_PLANES: the per-position plane test instead of the Shift-And automaton
+
+
+def _where(prefix, pattern, planes=False):
     """(Kmer|str|None, Qkmer|str|None) -> (Where struct or None, keepalive)."""
     if prefix is None and pattern is None:
         return None, None
     w = Where()
+    w.flags = WHERE_FLAG_PLANES if planes else 0
     keep = None
     if prefix is not None:
         prefix = Kmer(prefix)
@@ -224,11 +228,17 @@ class Context:
     """One GPU, one stream (dnagpu_ctx).  `torch_stream=True` issues the library's
     work on torch's current stream so torch tensors can be passed in and out."""
 
-    def __init__(self, device=0, torch_stream=False):
+    def __init__(self, device=0, torch_stream=False, devices=None):
+        """devices=[d0, d1, ...]: one context over several GPUs of the box (dnagpu_create_multi): it behaves like a
+        context on d0, and the host-buffer GROUP BY (count_kmers / count_kmers_ptr) uses all of them."""
         self.lib = _lib.load()
         self._children = weakref.WeakSet()  # live Seq / Table / Index objects (freed by close())
         h = C.c_void_p()
-        rc = self.lib.dnagpu_create(C.byref(h), device)
+        if devices is not None:
+            device = devices[0]
+            rc = self.lib.dnagpu_create_multi(C.byref(h), (C.c_int * len(devices))(*devices), len(devices))
+        else:
+            rc = self.lib.dnagpu_create(C.byref(h), device)
         if rc != 0:
             raise DnaError(self.lib.dnagpu_last_error(None).decode(), code=rc)
         self.handle = h
@@ -364,6 +374,28 @@ class Context:
                                                  ns.ctypes.data_as(_lib.u64p), n, n_bases_total, C.byref(h)))
         return Seq(self, h, keep=keep)
 
+    def fill_words(self, addr, seq, n_words_alloc):
+        """Copy a Seq's packed words to a raw device address (a peer-allocated shard) and zero the rest of the
+        n_words_alloc words there; on torch's current stream."""
+        import torch
+        n = min(seq.n_words, n_words_alloc)
+        dst = _device_view(addr, n_words_alloc, self.device)
+        if n:
+            dst[:n].copy_(_device_view(seq.device_ptr, n, self.device))
+        dst[n:].zero_()
+        if not self.shares_torch_stream:
+            torch.cuda.current_stream(self.device).synchronize()
+
+    def upload_to(self, addr, host_tensor, n_words_alloc):
+        """H2D of packed words from a (pinned) torch int64 host tensor to a raw device address; the tail is zeroed."""
+        import torch
+        n = min(host_tensor.numel(), n_words_alloc)
+        dst = _device_view(addr, n_words_alloc, self.device)
+        dst[:n].copy_(host_tensor[:n], non_blocking=True)
+        dst[n:].zero_()
+        if not self.shares_torch_stream:
+            torch.cuda.current_stream(self.device).synchronize()
+
     def wrap_reads(self, tensor, n_reads, bases_per_read, stride_words):
         self._after_torch()
         h = C.c_void_p()
@@ -455,10 +487,10 @@ class Context:
             guess = n.value
         self._ok(rc)
 
-    def collect(self, seq, k, prefix=None, pattern=None):
+    def collect(self, seq, k, prefix=None, pattern=None, planes=False):
         """The rows that pass the WHERE clause in no particular order (one predicate scan): torch int64 CUDA tensor."""
         import torch
-        w, _keep = _where(prefix, pattern)
+        w, _keep = _where(prefix, pattern, planes)
         wp = C.byref(w) if w is not None else None
         n = C.c_uint64()
         guess = seq.kmer_count(k) if w is None else max(1024, seq.kmer_count(k) // 8)
@@ -511,10 +543,10 @@ class Context:
         return o
 
     def count(self, seq, k, prefix=None, pattern=None, table=False, method=COUNT_AUTO,
-              load_factor=0.0, expected_keys=0, exact=False, owner=None):
+              load_factor=0.0, expected_keys=0, exact=False, owner=None, planes=False):
         """GROUP BY kmer over device-resident sequences -> (Stats, Table | None).
         owner=(n_parts, part): only the k-mers dnagpu_owner_of assigns to `part` (one GPU's share of a multi-GPU count)."""
-        w, _keep = _where(prefix, pattern)
+        w, _keep = _where(prefix, pattern, planes)
         o = self._opts(method, load_factor, expected_keys, exact, owner)
         st, th = Stats(), C.c_void_p()
         self._ok(self.lib.dnagpu_count(self.handle, seq.handle, k, C.byref(w) if w is not None else None,

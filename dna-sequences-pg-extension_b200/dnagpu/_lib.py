@@ -18,7 +18,7 @@ vp = C.c_void_p
 class Where(C.Structure):
     """dnagpu_where: WHERE kmer ^@ prefix AND qkmer @> kmer."""
     _fields_ = [("prefix_bits", C.c_uint64), ("prefix_len", C.c_int32),
-                ("reserved", C.c_int32), ("qkmer", C.c_char_p)]
+                ("flags", C.c_int32), ("qkmer", C.c_char_p)]
 
 
 class Stats(C.Structure):
@@ -40,6 +40,8 @@ SIGNATURES = {
     "dnagpu_version": (C.c_int, []),
     "dnagpu_strerror": (C.c_char_p, [C.c_int]),
     "dnagpu_create": (C.c_int, [C.POINTER(vp), C.c_int]),
+    "dnagpu_create_multi": (C.c_int, [C.POINTER(vp), C.POINTER(C.c_int), C.c_int]),
+    "dnagpu_device_count": (C.c_int, [vp]),
     "dnagpu_destroy": (None, [vp]),
     "dnagpu_last_error": (C.c_char_p, [vp]),
     "dnagpu_set_stream": (C.c_int, [vp, vp]),

@@ -1,5 +1,12 @@
 """Multi-GPU GROUP BY kmer: one process per GPU, torch.distributed for the plumbing.
 
+The default form (`ShardRing` + `count_sharded_gather`) moves no k-mers at all: the sequence stays sharded by
+base range, one shard per GPU with its (k-1)-base overlap, every shard is mapped into every GPU's address space
+(CUDA IPC peer memory), and each GPU walks ALL shards -- its own first, the others in ring order -- keeping the
+k-mers that dnagpu_owner_of assigns to it (libdnagpu: dnagpu_count with an owner restriction).  NVLink carries
+the 2-bit packed bases (0.25 B per start position) instead of 8-byte k-mers, there is no exchange step, and the
+only collective is the final 3-element all-reduce.  The forms below it route k-mers to their owners instead.
+
 The path shards naturally with ONE exchange step:
   1. the sequence is cut into base-range shards, each carrying a (k-1)-base overlap, so every
      k-mer starts in exactly one shard (`shard_of`); reads shard by index with no overlap;
@@ -32,6 +39,107 @@ def reads_shard_of(n_reads, world, rank):
     """Index-range shard of a batch of reads -> (first_read, n_reads_local)."""
     first = n_reads * rank // world
     return first, n_reads * (rank + 1) // world - first
+
+
+def ring_shards(n_bases, world):
+    """k-independent base ranges of one sequence, one per rank -> [(first_base, n_starts)]; first_base is a multiple
+    of 32, the ranges tile [0, n_bases), ranks past the end get empty ranges."""
+    per = ((n_bases + world - 1) // world + 31) // 32 * 32
+    end = (n_bases + 31) // 32 * 32
+    out = []
+    for r in range(world):
+        first = min(r * per, end)
+        out.append((first, max(0, min(per, n_bases - first))))
+    return out
+
+
+def shard_words(n_bases, first, starts):
+    """Packed words a piece holds: its bases plus the 31-base overlap (any k <= 32), >= 1 zero pad word, even count."""
+    held = max(0, min(n_bases, first + starts + 31) - first)
+    return ((held + 31) // 32 + 3) & ~1
+
+
+class ShardRing:
+    """Every rank's shard of one sequence in peer-mappable memory, mapped by every rank (one per process).
+
+    Collective constructor: allocates this rank's buffer (dnagpu_peer_alloc), swaps the IPC handles and opens the
+    others (dnagpu_peer_open).  Raises on EVERY rank if any rank cannot allocate or map."""
+
+    def __init__(self, ctx, world, rank, n_bases, group=None):
+        import torch.distributed as dist
+        self.ctx, self.world, self.rank, self.n_bases, self.group = ctx, world, rank, n_bases, group
+        self.shards = ring_shards(n_bases, world)
+        self.n_words = [shard_words(n_bases, f, s) for f, s in self.shards]
+        self.local, self.base, self._seq, handle, err = 0, [], None, None, None
+        try:
+            self.local, handle = ctx.peer_alloc(8 * self.n_words[rank])
+        except Exception as e:  # noqa: BLE001 - reported collectively below
+            err = str(e)
+        got = [None] * world
+        dist.all_gather_object(got, (err, handle), group=group)
+        if any(e for e, _ in got):
+            if self.local:
+                ctx.peer_free(self.local)
+            raise RuntimeError("shard ring unavailable: " + "; ".join(e for e, _ in got if e))
+        opened = []
+        try:
+            for r in range(world):
+                self.base.append(self.local if r == rank else ctx.peer_open(got[r][1]))
+                if r != rank:
+                    opened.append(self.base[-1])
+        except Exception as e:  # noqa: BLE001
+            err = str(e)
+        got = [None] * world
+        dist.all_gather_object(got, err, group=group)
+        if any(got):
+            for a in opened:
+                ctx.peer_close(a)
+            ctx.peer_free(self.local)
+            raise RuntimeError("shard ring unavailable: " + "; ".join(e for e in got if e))
+
+    @property
+    def my_shard(self):
+        return self.shards[self.rank]
+
+    def publish(self):
+        """Collective: this rank's shard has been written (ctx.fill_words / ctx.upload_to); wait until all have."""
+        import torch.distributed as dist
+        self.ctx.synchronize()
+        dist.barrier(group=self.group)
+
+    def seq(self):
+        """The whole sequence as pieces, this rank's own first and the others in ring order (so that at any
+        moment every shard is read by one GPU, not by all of them)."""
+        if self._seq is None:
+            ring = [(self.rank + i) % self.world for i in range(self.world)]
+            self._seq = self.ctx.wrap_pieces([self.base[r] for r in ring], [self.shards[r][0] for r in ring],
+                                             [self.shards[r][1] for r in ring], self.n_bases)
+        return self._seq
+
+    def close(self):
+        import torch.distributed as dist
+        if self._seq is not None:
+            self._seq.free()
+        self.ctx.synchronize()
+        dist.barrier(group=self.group)
+        for r, a in enumerate(self.base):
+            if r != self.rank:
+                self.ctx.peer_close(a)
+        dist.barrier(group=self.group)
+        self.ctx.peer_free(self.local)
+
+
+def count_sharded_gather(ctx, ring, k, group=None):
+    """One pass of the sharded query on this rank -> global (total, distinct, unique).  No k-mer moves: this rank
+    counts the k-mers it owns out of the whole sequence (all shards, read through peer memory); key sets are
+    disjoint across ranks, so the aggregates add.  The all-reduce also fences the shards for the next upload."""
+    import torch
+    import torch.distributed as dist
+    dev = getattr(ctx, "torch_device", None) or torch.device("cuda", ctx.device)
+    st, _ = ctx.count(ring.seq(), k, owner=(ring.world, ring.rank))
+    agg = torch.tensor([st.total, st.distinct, st.unique], dtype=torch.int64, device=dev)
+    dist.all_reduce(agg, group=group)
+    return tuple(int(x) for x in agg.cpu().tolist())
 
 
 class GpuEngine:

@@ -97,10 +97,16 @@ typedef struct dnagpu_table dnagpu_table; /* device-resident GROUP BY kmer resul
  * (dna.c:61-65) as kmer_make() builds them; `qkmer` is `Qkmer.sequence`
  * (dna.c:81-84), a NUL-terminated IUPAC string.
  */
+/* How an unordered predicate scan (dnagpu_collect, the WHERE clause of a GROUP BY) evaluates the clause: by
+ * default as a Shift-And automaton over the base stream (6 instructions per base); with this flag as the
+ * per-start-position test on four "allowed" bit planes (~ 19 instructions per start position), which the
+ * ordered scans (dnagpu_filter*) and ragged batches always use.  Same rows either way. */
+#define DNAGPU_WHERE_FLAG_PLANES 1
+
 typedef struct dnagpu_where {
     uint64_t prefix_bits; /* Kmer.bit_sequence of the ^@ right operand          */
     int32_t prefix_len;   /* Kmer.length of it; 0 = no ^@ predicate             */
-    int32_t reserved;     /* must be 0                                          */
+    int32_t flags;        /* DNAGPU_WHERE_FLAG_*; 0 = default                    */
     const char *qkmer;    /* @> left operand; NULL = no @> predicate            */
 } dnagpu_where;
 
@@ -142,6 +148,15 @@ typedef struct dnagpu_count_opts {
 int dnagpu_version(void);
 const char *dnagpu_strerror(int code);
 int dnagpu_create(dnagpu_ctx **out, int device);
+/* One context over several GPUs of one box: one process, no IPC, the GPUs see each other's memory through
+ * peer access (NVLink).  The context behaves like a single-GPU context on devices[0] for every call; the
+ * host-buffer GROUP BY (dnagpu_count_kmers without a WHERE clause) uses ALL of them: the packed words are
+ * cut into one base-range shard per GPU (with the (k-1)-base overlap), uploaded in parallel, and every GPU
+ * counts the k-mers it owns out of the whole sequence (see dnagpu_count_opts.owner_parts).  The aggregates
+ * are the sums, the table is the concatenation of the per-GPU tables.  n_devices <= 16. */
+int dnagpu_create_multi(dnagpu_ctx **out, const int *devices, int n_devices);
+/* GPUs behind the context (1 for dnagpu_create). */
+int dnagpu_device_count(const dnagpu_ctx *ctx);
 void dnagpu_destroy(dnagpu_ctx *ctx);
 const char *dnagpu_last_error(const dnagpu_ctx *ctx);
 /* Lend a cudaStream_t (e.g. torch's current stream); NULL = library's own. */
@@ -285,7 +300,8 @@ uint64_t dnagpu_table_rows(const dnagpu_table *table);
 int dnagpu_table_k(const dnagpu_table *table);
 int dnagpu_table_fetch(dnagpu_ctx *ctx, const dnagpu_table *table, uint64_t offset,
                        uint64_t n, uint64_t *kmers, uint64_t *counts);
-/* Device pointers of the compacted rows (valid until dnagpu_table_free). */
+/* Device pointers of the compacted rows (valid until dnagpu_table_free).  Not available for the table of a
+ * multi-GPU count (its rows live on several GPUs): DNAGPU_EARG. */
 int dnagpu_table_device(const dnagpu_table *table, const uint64_t **d_kmers,
                         const uint64_t **d_counts);
 void dnagpu_table_free(dnagpu_table *table);

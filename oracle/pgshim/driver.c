@@ -71,6 +71,7 @@ static Datum call(Datum (*fn)(PG_FUNCTION_ARGS), FmgrInfo *fl, ReturnSetInfo *rs
         shim_error_jmp = &jb_;                                            \
         if (setjmp(jb_) != 0) {                                           \
             shim_error_jmp = NULL;                                        \
+            shim_abort_cleanup(); /* AbortTransaction: contexts reset */  \
             if (err) snprintf(err, errcap, "%s", shim_error_text);        \
             return 1;                                                     \
         }                                                                 \
@@ -513,56 +514,94 @@ int dnaref_count(const uint64_t *words, uint64_t n_seqs, uint64_t bases_per_seq,
 
 #ifdef DNAREF_WITH_GLUE
 /*
- * The GPU glue's pushdown functions (dna-sequences-pg-extension_b200/pg/dna_gpu.c), linked into
- * this build together with dna.c.  The driver plays the executor: it supplies the expected row
- * type, runs the SRF loop and unpacks the composite Datums.
+ * The GPU glue's functions (dna-sequences-pg-extension_b200/pg/dna_gpu.c), linked into this build together
+ * with dna.c.  The driver plays the executor: it supplies the expected row type, passes SQL NULLs, runs the
+ * SRF loop (optionally abandoning it half way, as a LIMIT or a cancelled query does), runs an aggregate's
+ * transition / final functions over a table of values, and unpacks the composite Datums.
  */
 extern Datum kmer_stats(PG_FUNCTION_ARGS);
 extern Datum count_kmers(PG_FUNCTION_ARGS);
+extern Datum generate_kmers_where(PG_FUNCTION_ARGS);
+extern Datum kmer_stats_agg_trans(PG_FUNCTION_ARGS);
+extern Datum kmer_stats_agg_final(PG_FUNCTION_ARGS);
+extern int dna_gpu_live_tables(void);
 
-static Datum call_row(Datum (*fn)(PG_FUNCTION_ARGS), FmgrInfo *fl, ReturnSetInfo *rsi, TupleDesc desc, Datum a0,
-                      Datum a1)
+int dnaref_live_tables(void) { return dna_gpu_live_tables(); }
+int dnaref_live_contexts(void) { return shim_live_contexts(); }
+
+/* fn(dna, k) or fn(dna, k, prefix kmer | NULL, qkmer | NULL) */
+static Datum call_glue(Datum (*fn)(PG_FUNCTION_ARGS), FmgrInfo *fl, ReturnSetInfo *rsi, TupleDesc desc, RefDna *d, int k,
+                       int with_where, RefKmer *prefix, RefQkmer *q)
 {
     FunctionCallInfoBaseData fc;
     memset(&fc, 0, sizeof fc);
     fc.flinfo = fl;
     fc.resultinfo = rsi;
-    fc.nargs = 2;
-    fc.args[0].value = a0;
-    fc.args[1].value = a1;
+    fc.nargs = with_where ? 4 : 2;
+    fc.args[0].value = PointerGetDatum(d);
+    fc.args[1].value = Int32GetDatum(k);
+    if (with_where) {
+        fc.args[2].value = PointerGetDatum(prefix);
+        fc.args[2].isnull = prefix == NULL;
+        fc.args[3].value = PointerGetDatum(q);
+        fc.args[3].isnull = q == NULL;
+    }
     fc.shim_result_desc = desc;
     return fn(&fc);
 }
 
-/* SELECT * FROM kmer_stats(dna, k) */
-int dnaref_kmer_stats(const uint64_t *words, uint64_t n_bases, int k, int64_t stats[3], char *err, size_t errcap)
+static RefKmer *prefix_arg(uint64_t prefix_bits, int32_t prefix_len, RefKmer *store)
+{
+    if (prefix_len <= 0) return NULL;
+    store->length = prefix_len;
+    store->bit_sequence = prefix_bits;
+    return store;
+}
+
+/* SELECT * FROM kmer_stats(dna, k [, prefix, pattern]);  with_where = 0 calls the two-argument form */
+int dnaref_kmer_stats(const uint64_t *words, uint64_t n_bases, int k, int with_where, uint64_t prefix_bits,
+                      int32_t prefix_len, const char *pattern, int64_t stats[3], char *err, size_t errcap)
 {
     GUARDED(err, errcap, {
         RefDna *d = dna_from_words(words, n_bases);
+        RefKmer pk;
+        RefQkmer *q = pattern ? qkmer_from_text(pattern) : NULL;
         TupleDescData desc = {3};
-        HeapTuple t = (HeapTuple)DatumGetPointer(call_row(kmer_stats, &fl_, NULL, &desc, PointerGetDatum(d), Int32GetDatum(k)));
+        HeapTuple t = (HeapTuple)DatumGetPointer(call_glue(kmer_stats, &fl_, NULL, &desc, d, k, with_where,
+                                                           prefix_arg(prefix_bits, prefix_len, &pk), q));
         int i;
         for (i = 0; i < 3; i++) stats[i] = DatumGetInt64(t->values[i]);
         heap_freetuple(t);
+        if (q) pfree(q);
         pfree(d);
     });
     return 0;
 }
 
-/* SELECT * FROM count_kmers(dna, k): rows in the order the function returns them */
-int dnaref_count_kmers(const uint64_t *words, uint64_t n_bases, int k, uint64_t *kmers, int64_t *counts,
+/* SELECT * FROM count_kmers(dna, k [, prefix, pattern]) [LIMIT stop_after]: rows in the order the function
+ * returns them.  stop_after < the number of rows abandons the scan there, the way the executor does for a
+ * LIMIT or a cancelled query: the SRF is never called again and its memory context is reset. */
+int dnaref_count_kmers(const uint64_t *words, uint64_t n_bases, int k, int with_where, uint64_t prefix_bits,
+                       int32_t prefix_len, const char *pattern, uint64_t stop_after, uint64_t *kmers, int64_t *counts,
                        uint64_t cap, uint64_t *n_out, char *err, size_t errcap)
 {
     GUARDED(err, errcap, {
         RefDna *d = dna_from_words(words, n_bases);
+        RefKmer pk;
+        RefQkmer *q = pattern ? qkmer_from_text(pattern) : NULL;
         TupleDescData desc = {2};
         ReturnSetInfo rsi;
         uint64_t n = 0;
         int bad_len = 0;
         for (;;) {
             Datum r;
+            if (n >= stop_after) { /* abandoned scan: ExecEndFunctionScan -> the SRF's context goes away */
+                FuncCallContext *f = (FuncCallContext *)fl_.fn_extra;
+                if (f) shim_end_MultiFuncCall(&(FunctionCallInfoBaseData){.flinfo = &fl_}, f);
+                break;
+            }
             rsi.isDone = ExprSingleResult;
-            r = call_row(count_kmers, &fl_, &rsi, &desc, PointerGetDatum(d), Int32GetDatum(k));
+            r = call_glue(count_kmers, &fl_, &rsi, &desc, d, k, with_where, prefix_arg(prefix_bits, prefix_len, &pk), q);
             if (rsi.isDone == ExprEndResult) break;
             {
                 HeapTuple t = (HeapTuple)DatumGetPointer(r);
@@ -578,11 +617,89 @@ int dnaref_count_kmers(const uint64_t *words, uint64_t n_bases, int k, uint64_t 
             }
         }
         *n_out = n;
+        if (q) pfree(q);
         pfree(d);
         if (bad_len) {
             snprintf(shim_error_text, sizeof shim_error_text, "driver: malformed count_kmers row");
             longjmp(jb_, 1);
         }
+    });
+    return 0;
+}
+
+/* SELECT * FROM generate_kmers_where(dna, k, prefix, pattern): rows in order */
+int dnaref_generate_kmers_where(const uint64_t *words, uint64_t n_bases, int k, uint64_t prefix_bits, int32_t prefix_len,
+                                const char *pattern, uint64_t *out, uint64_t cap, uint64_t *n_out, char *err,
+                                size_t errcap)
+{
+    GUARDED(err, errcap, {
+        RefDna *d = dna_from_words(words, n_bases);
+        RefKmer pk;
+        RefQkmer *q = pattern ? qkmer_from_text(pattern) : NULL;
+        ReturnSetInfo rsi;
+        uint64_t n = 0;
+        for (;;) {
+            Datum r;
+            rsi.isDone = ExprSingleResult;
+            r = call_glue(generate_kmers_where, &fl_, &rsi, NULL, d, k, 1, prefix_arg(prefix_bits, prefix_len, &pk), q);
+            if (rsi.isDone == ExprEndResult) break;
+            {
+                RefKmer *km = (RefKmer *)DatumGetPointer(r);
+                if (n < cap) out[n] = km->bit_sequence;
+                n += km->length == k ? 1 : (1ull << 40); /* a wrong Kmer.length shows up as an absurd count */
+                pfree(km);
+            }
+        }
+        *n_out = n;
+        if (q) pfree(q);
+        pfree(d);
+    });
+    return 0;
+}
+
+/* SELECT (kmer_stats_agg(sequence, k)).* FROM t: values of n_bases[s] bases at words[word_off[s]]; a value with
+ * n_bases[s] == UINT64_MAX is a SQL NULL */
+int dnaref_kmer_stats_agg(const uint64_t *words, const uint64_t *word_off, const uint64_t *n_bases, uint64_t n_seqs, int k,
+                          int64_t stats[3], char *err, size_t errcap)
+{
+    GUARDED(err, errcap, {
+        ShimAggContext agg = {0x4147, shim_context_create()};
+        TupleDescData desc = {3};
+        Datum state = 0;
+        bool state_null = true;
+        uint64_t s;
+        int i;
+        HeapTuple t;
+        for (s = 0; s < n_seqs; s++) {
+            FunctionCallInfoBaseData fc;
+            RefDna *d = n_bases[s] == UINT64_MAX ? NULL : dna_from_words(words + word_off[s], n_bases[s]);
+            memset(&fc, 0, sizeof fc);
+            fc.flinfo = &fl_;
+            fc.context = &agg;
+            fc.nargs = 3;
+            fc.args[0].value = state;
+            fc.args[0].isnull = state_null;
+            fc.args[1].value = PointerGetDatum(d);
+            fc.args[1].isnull = d == NULL;
+            fc.args[2].value = Int32GetDatum(k);
+            state = kmer_stats_agg_trans(&fc);
+            state_null = fc.isnull;
+            if (d) pfree(d);
+        }
+        {
+            FunctionCallInfoBaseData fc;
+            memset(&fc, 0, sizeof fc);
+            fc.flinfo = &fl_;
+            fc.context = &agg;
+            fc.nargs = 1;
+            fc.args[0].value = state;
+            fc.args[0].isnull = state_null;
+            fc.shim_result_desc = &desc;
+            t = (HeapTuple)DatumGetPointer(kmer_stats_agg_final(&fc));
+        }
+        for (i = 0; i < 3; i++) stats[i] = DatumGetInt64(t->values[i]);
+        heap_freetuple(t);
+        shim_context_delete(agg.aggcontext);
     });
     return 0;
 }

@@ -50,6 +50,21 @@ void pfree(void *p);
 char *pstrdup(const char *s);
 typedef struct MemoryContextData *MemoryContext;
 extern __thread MemoryContext CurrentMemoryContext;
+/* utils/memutils.h, utils/palloc.h: contexts exist here only to carry reset callbacks (what lets an extension
+ * release non-palloc resources when a query ends or aborts); allocations stay plain malloc */
+typedef void (*MemoryContextCallbackFunction)(void *arg);
+typedef struct MemoryContextCallback {
+    MemoryContextCallbackFunction func;
+    void *arg;
+    struct MemoryContextCallback *next;
+} MemoryContextCallback;
+void MemoryContextRegisterResetCallback(MemoryContext context, MemoryContextCallback *cb);
+void *MemoryContextAllocHuge(MemoryContext context, Size size);
+void *repalloc_huge(void *p, Size size);
+MemoryContext shim_context_create(void);
+void shim_context_delete(MemoryContext c); /* fires the callbacks, newest first, like MemoryContextDelete */
+void shim_abort_cleanup(void);             /* transaction abort: every live context is deleted */
+int shim_live_contexts(void);
 static inline MemoryContext MemoryContextSwitchTo(MemoryContext c)
 {
     MemoryContext old = CurrentMemoryContext;
@@ -124,6 +139,8 @@ typedef FunctionCallInfoBaseData *FunctionCallInfo;
 #define PG_FUNCTION_ARGS FunctionCallInfo fcinfo
 #define PG_MODULE_MAGIC extern int shim_module_magic
 #define PG_FUNCTION_INFO_V1(f) extern Datum f(PG_FUNCTION_ARGS)
+#define PG_NARGS() (fcinfo->nargs)
+#define PG_ARGISNULL(n) (fcinfo->args[n].isnull)
 #define PG_GETARG_DATUM(n) (fcinfo->args[n].value)
 #define PG_GETARG_POINTER(n) DatumGetPointer(PG_GETARG_DATUM(n))
 #define PG_GETARG_CSTRING(n) DatumGetCString(PG_GETARG_DATUM(n))
@@ -172,15 +189,23 @@ FuncCallContext *shim_init_MultiFuncCall(FunctionCallInfo fcinfo);
         rsi->isDone = ExprMultipleResult;                         \
         PG_RETURN_DATUM(_result);                                 \
     } while (0)
+void shim_end_MultiFuncCall(FunctionCallInfo fcinfo, FuncCallContext *funcctx);
 #define SRF_RETURN_DONE(_funcctx)                                 \
     do {                                                          \
         ReturnSetInfo *rsi;                                       \
-        free(_funcctx);                                           \
-        fcinfo->flinfo->fn_extra = NULL;                          \
+        shim_end_MultiFuncCall(fcinfo, _funcctx);                 \
         rsi = (ReturnSetInfo *)fcinfo->resultinfo;                \
         rsi->isDone = ExprEndResult;                              \
         PG_RETURN_NULL();                                         \
     } while (0)
+
+/* ---- fmgr.h: aggregate support functions ---- */
+#define AGG_CONTEXT_AGGREGATE 1
+typedef struct ShimAggContext { /* what fcinfo->context points at when the executor calls an sfunc / finalfunc */
+    int tag;                    /* 0x4147 */
+    MemoryContext aggcontext;
+} ShimAggContext;
+int AggCheckCallContext(FunctionCallInfo fcinfo, MemoryContext *aggcontext);
 
 /* ---- funcapi.h / access/htup_details.h: composite results ---- */
 typedef struct TupleDescData {

@@ -73,12 +73,77 @@ Datum shim_DirectFunctionCall1(Datum (*fn)(PG_FUNCTION_ARGS), Datum arg)
     return fn(&fc);
 }
 
+/* ---- memory contexts: only their reset callbacks are modelled ---- */
+struct MemoryContextData {
+    MemoryContextCallback *callbacks;
+    struct MemoryContextData *prev, *next;
+};
+static __thread struct MemoryContextData *live_contexts = NULL;
+
+MemoryContext shim_context_create(void)
+{
+    MemoryContext c = (MemoryContext)calloc(1, sizeof(*c));
+    c->next = live_contexts;
+    if (live_contexts) live_contexts->prev = c;
+    live_contexts = c;
+    return c;
+}
+void shim_context_delete(MemoryContext c)
+{
+    if (!c) return;
+    while (c->callbacks) { /* newest first, each exactly once */
+        MemoryContextCallback *cb = c->callbacks;
+        c->callbacks = cb->next;
+        cb->func(cb->arg);
+    }
+    if (c->prev) c->prev->next = c->next; else live_contexts = c->next;
+    if (c->next) c->next->prev = c->prev;
+    free(c);
+}
+void shim_abort_cleanup(void)
+{
+    while (live_contexts) shim_context_delete(live_contexts);
+}
+int shim_live_contexts(void)
+{
+    int n = 0;
+    struct MemoryContextData *c;
+    for (c = live_contexts; c; c = c->next) n++;
+    return n;
+}
+void MemoryContextRegisterResetCallback(MemoryContext context, MemoryContextCallback *cb)
+{
+    cb->next = context->callbacks;
+    context->callbacks = cb;
+}
+void *MemoryContextAllocHuge(MemoryContext context, Size size)
+{
+    (void)context;
+    return malloc(size ? size : 1);
+}
+void *repalloc_huge(void *p, Size size) { return realloc(p, size ? size : 1); }
+
+int AggCheckCallContext(FunctionCallInfo fcinfo, MemoryContext *aggcontext)
+{
+    ShimAggContext *a = (ShimAggContext *)fcinfo->context;
+    if (!a || a->tag != 0x4147) return 0;
+    if (aggcontext) *aggcontext = a->aggcontext;
+    return AGG_CONTEXT_AGGREGATE;
+}
+
 /* ---- SRF ---- */
 FuncCallContext *shim_init_MultiFuncCall(FunctionCallInfo fcinfo)
 {
     FuncCallContext *f = (FuncCallContext *)calloc(1, sizeof(*f));
+    f->multi_call_memory_ctx = shim_context_create();
     fcinfo->flinfo->fn_extra = f;
     return f;
+}
+void shim_end_MultiFuncCall(FunctionCallInfo fcinfo, FuncCallContext *funcctx)
+{
+    shim_context_delete(funcctx->multi_call_memory_ctx); /* end_MultiFuncCall deletes the context: callbacks fire */
+    free(funcctx);
+    fcinfo->flinfo->fn_extra = NULL;
 }
 
 /* ---- composite results ---- */

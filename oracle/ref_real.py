@@ -73,8 +73,14 @@ class Module:
                                        u64, C.POINTER(u64)] + err),
         }
         if hasattr(L, "dnaref_kmer_stats"):   # only the glue build has the pushdown functions
-            sig["dnaref_kmer_stats"] = (C.c_int, [vp, u64, C.c_int, vp] + err)
-            sig["dnaref_count_kmers"] = (C.c_int, [vp, u64, C.c_int, vp, vp, u64, C.POINTER(u64)] + err)
+            sig["dnaref_kmer_stats"] = (C.c_int, [vp, u64, C.c_int, C.c_int, u64, C.c_int32, C.c_char_p, vp] + err)
+            sig["dnaref_count_kmers"] = (C.c_int, [vp, u64, C.c_int, C.c_int, u64, C.c_int32, C.c_char_p, u64, vp, vp,
+                                                   u64, C.POINTER(u64)] + err)
+            sig["dnaref_generate_kmers_where"] = (C.c_int, [vp, u64, C.c_int, u64, C.c_int32, C.c_char_p, vp, u64,
+                                                            C.POINTER(u64)] + err)
+            sig["dnaref_kmer_stats_agg"] = (C.c_int, [vp, vp, vp, u64, C.c_int, vp] + err)
+            sig["dnaref_live_tables"] = (C.c_int, [])
+            sig["dnaref_live_contexts"] = (C.c_int, [])
         for name, (res, args) in sig.items():
             fn = getattr(L, name)
             fn.restype, fn.argtypes = res, args
@@ -151,24 +157,75 @@ class Module:
                            cc[:n.value].copy() if want_rows else None)
 
     # ---- the glue's pushdown functions (libdnaglue.so only) ----
-    def kmer_stats(self, words, n_bases, k):
-        """SELECT * FROM kmer_stats(dna, k) -> (total, distinct, uniq)."""
+    @staticmethod
+    def _where(prefix, pattern):
+        pb, pl = (0, 0) if prefix is None else prefix
+        return pb, pl, None if pattern is None else pattern.encode("ascii", "replace")
+
+    def kmer_stats(self, words, n_bases, k, prefix=None, pattern=None, where_form=None):
+        """SELECT * FROM kmer_stats(dna, k [, prefix, pattern]) -> (total, distinct, uniq).  where_form=True calls the
+        four-argument form even with both predicates NULL."""
         words = np.ascontiguousarray(words, dtype=np.uint64)
         st = np.zeros(3, dtype=np.int64)
-        _run(self.L.dnaref_kmer_stats, words.ctypes.data, n_bases, k, st.ctypes.data)
+        pb, pl, pat = self._where(prefix, pattern)
+        four = (prefix is not None or pattern is not None) if where_form is None else where_form
+        _run(self.L.dnaref_kmer_stats, words.ctypes.data, n_bases, k, 1 if four else 0, pb, pl, pat, st.ctypes.data)
         return tuple(int(x) for x in st)
 
-    def count_kmers(self, words, n_bases, k):
-        """SELECT * FROM count_kmers(dna, k) -> (kmers, counts) sorted by kmer, plus the Kmer.length check."""
+    def count_kmers(self, words, n_bases, k, prefix=None, pattern=None, stop_after=None):
+        """SELECT * FROM count_kmers(dna, k [, prefix, pattern]) [LIMIT stop_after] -> (kmers, counts) sorted by kmer
+        (unsorted when the scan is abandoned after stop_after rows), plus the Kmer.length check."""
         words = np.ascontiguousarray(words, dtype=np.uint64)
         cap = max(0, n_bases - k + 1) if 1 <= k <= 32 else 0
         kk = np.empty(cap + 1, dtype=np.uint64)
         cc = np.empty(cap + 1, dtype=np.int64)
         n = u64()
-        _run(self.L.dnaref_count_kmers, words.ctypes.data, n_bases, k, kk.ctypes.data, cc.ctypes.data, kk.size,
+        pb, pl, pat = self._where(prefix, pattern)
+        _run(self.L.dnaref_count_kmers, words.ctypes.data, n_bases, k, 1 if (prefix is not None or pattern is not None) else 0,
+             pb, pl, pat, 2**64 - 1 if stop_after is None else stop_after, kk.ctypes.data, cc.ctypes.data, kk.size,
              C.byref(n))
+        if stop_after is not None:
+            return kk[:n.value].copy(), cc[:n.value].copy()
         order = np.argsort(kk[:n.value], kind="stable")
         return kk[:n.value][order], cc[:n.value][order]
+
+    def generate_kmers_where(self, words, n_bases, k, prefix=None, pattern=None):
+        """SELECT * FROM generate_kmers_where(dna, k, prefix, pattern): rows in sequence order."""
+        words = np.ascontiguousarray(words, dtype=np.uint64)
+        cap = max(0, n_bases - k + 1) if 1 <= k <= 32 else 0
+        out = np.empty(cap + 1, dtype=np.uint64)
+        n = u64()
+        pb, pl, pat = self._where(prefix, pattern)
+        _run(self.L.dnaref_generate_kmers_where, words.ctypes.data, n_bases, k, pb, pl, pat, out.ctypes.data, out.size,
+             C.byref(n))
+        assert n.value <= cap, "a row came back with the wrong Kmer.length"
+        return out[:n.value].copy()
+
+    def kmer_stats_agg(self, seqs, k):
+        """SELECT (kmer_stats_agg(sequence, k)).* FROM t; seqs = [(words, n_bases) | None (a SQL NULL), ...]."""
+        offs, lens, parts, pos = [], [], [], 0
+        for s in seqs:
+            if s is None:
+                offs.append(pos)
+                lens.append(2**64 - 1)
+                continue
+            w, n = s
+            w = np.ascontiguousarray(w, dtype=np.uint64)[: (n + 31) // 32]
+            offs.append(pos)
+            lens.append(n)
+            parts.append(w)
+            pos += w.size
+        words = np.concatenate(parts + [np.zeros(1, dtype=np.uint64)]) if parts else np.zeros(1, dtype=np.uint64)
+        offs, lens = np.array(offs, dtype=np.uint64), np.array(lens, dtype=np.uint64)
+        st = np.zeros(3, dtype=np.int64)
+        _run(self.L.dnaref_kmer_stats_agg, words.ctypes.data, offs.ctypes.data, lens.ctypes.data, len(seqs), k, st.ctypes.data)
+        return tuple(int(x) for x in st)
+
+    def live_tables(self):
+        return int(self.L.dnaref_live_tables())
+
+    def live_contexts(self):
+        return int(self.L.dnaref_live_contexts())
 
 
 def reference():

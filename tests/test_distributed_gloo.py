@@ -170,6 +170,109 @@ class OraclePeerCtx(OracleShuffleCtx):
         return self.shuffle_count(keys, piece_counts, n_groups, plan, k)[0]
 
 
+class OracleRingCtx(OraclePeerCtx):
+    """Test double for ShardRing + count_sharded_gather: shards live in shared-memory blocks every rank maps; the
+    owner-restricted count rebuilds the sequence from the pieces it was handed (in the order it was handed them),
+    extracts with the CPU oracle and keeps what libdnagpu's host-callable dnagpu_owner_of assigns to the rank."""
+
+    def synchronize(self):
+        pass
+
+    def fill_shard(self, addr, first, starts, n_words):
+        from oracle import ref_cpu as R
+        held = max(0, min(self.n_bases, first + starts + 31) - first)
+        words = np.zeros(n_words, dtype=np.uint64)
+        w = R.synth_seq(self.seed, self.n_bases, first_word=first // 32, n_words=(held + 31) // 32)
+        if held % 32:  # bases past the piece's reach exist in the sequence but not in the piece
+            w[-1] &= np.uint64((1 << (2 * (held % 32))) - 1)
+        words[:w.size] = w
+        self._store(addr, words)
+
+    def wrap_pieces(self, addrs, first_bases, n_starts, n_bases_total, keep=None):
+        class Pieces:
+            pass
+        p = Pieces()
+        p.addrs, p.first, p.starts, p.n_bases = list(addrs), list(first_bases), list(n_starts), n_bases_total
+        p.free = lambda: None
+        return p
+
+    def count(self, seq, k, owner=None, **kw):
+        from oracle import ref_cpu as R
+        import dnagpu
+        G, me = owner
+        rows_total = max(0, seq.n_bases - k + 1)
+        keys = []
+        for addr, first, starts in zip(seq.addrs, seq.first, seq.starts):
+            starts = max(0, min(starts, rows_total - first))
+            if not starts:
+                continue
+            held = min(seq.n_bases, first + starts + k - 1) - first
+            base = int(addr) >> 44 << 44
+            words = self.views[base][: (held + 31) // 32 + 1].copy()
+            keys.append(R.generate_kmers(words, held, k, window=True)[:starts])
+        keys = np.concatenate(keys) if keys else np.zeros(0, np.uint64)
+        mine = np.array([dnagpu.owner_of(int(x), G) == me for x in keys], dtype=bool)
+        u, c = np.unique(keys[mine], return_counts=True)
+
+        class St:
+            pass
+        st = St()
+        st.total, st.distinct, st.unique = int(c.sum()), int(u.size), int((c == 1).sum())
+        return st, None
+
+
+def _worker_gather(rank, world, port, n_bases, k, seed, out):
+    for p in (ROOT, PKG):
+        sys.path.insert(0, p)
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from dnagpu.distributed import ShardRing, count_sharded_gather
+    ctx = OracleRingCtx(n_bases, seed, rank)
+    ring = ShardRing(ctx, world, rank, n_bases)
+    first, starts = ring.my_shard
+    ctx.fill_shard(ring.local, first, starts, ring.n_words[rank])
+    ring.publish()
+    res = [count_sharded_gather(ctx, ring, k) for _ in range(2)]
+    ring.close()
+    if rank == 0:
+        out.put(res)
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("n_bases,k,world", [(30_000, 31, 2), (20_011, 21, 3), (100, 32, 2), (40, 5, 4), (4_097, 13, 2)])
+def test_gather_form_equals_single_rank(n_bases, k, world):
+    """ShardRing + count_sharded_gather (bench.py's default N > 1 path): k-independent base-range shards with the
+    31-base overlap in memory every rank maps, pieces walked in ring order, owner-restricted count, all-reduce."""
+    from oracle import ref_cpu as R
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 29400 + (n_bases + k + world) % 150
+    procs = [ctx.Process(target=_worker_gather, args=(r, world, port, n_bases, k, 31, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    got = q.get(timeout=180)
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    words = R.synth_seq(31, n_bases)
+    want = R.count_query(words, 1, n_bases, words.size, k, faithful=False)
+    assert [tuple(g) for g in got] == [want.stats, want.stats]
+
+
+def test_ring_shards_tile_the_sequence_and_hold_their_overlap():
+    from dnagpu.distributed import ring_shards, shard_words
+    for n, world in [(3_100_000_000, 8), (1000, 3), (40, 4), (33, 2), (1, 8), (100_000_007, 7)]:
+        pos = 0
+        for first, starts in ring_shards(n, world):
+            assert first % 32 == 0
+            if starts:
+                assert first == pos
+            pos += starts
+            held = max(0, min(n, first + starts + 31) - first)
+            assert shard_words(n, first, starts) >= (held + 31) // 32 + 1 and shard_words(n, first, starts) % 2 == 0
+        assert pos == n
+
+
 class FakeSeq:
     def __init__(self, shard, k):
         self.shard, self.k = shard, k

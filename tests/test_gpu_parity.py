@@ -619,3 +619,63 @@ def test_encode_dna_errors_are_the_references(gpu):
         gpu.encode_dna(two)
     with pytest.raises(R.RefError):
         R.encode_dna(two)
+
+
+# ---- the unordered predicate scan in both forms: Shift-And automaton (default) and plane test ----------------
+def _rand_pattern(rng, k, density):
+    return "".join(IUPAC[int(rng.integers(0, 16))] if rng.random() < density else "N" for _ in range(k))
+
+
+@pytest.mark.parametrize("k", [1, 2, 3, 7, 16, 17, 21, 31, 32])
+def test_collect_shift_and_equals_plane_test_equals_oracle(gpu, k):
+    rng = np.random.default_rng(900 + k)
+    for n in (k, k + 1, 127, 128, 129, 160, 1000, 4097, 200_003):
+        words = rand_dna_words(rng, n)
+        seq = gpu.upload(Dna.from_words(words, n))
+        for trial in range(3):
+            pattern = _rand_pattern(rng, k, 0.3) if trial else "N" * k
+            plen = int(rng.integers(0, min(k, 4) + 1))
+            prefix = R.decode_kmer(int(rng.integers(0, 4 ** plen)), plen) if plen else None
+            want = R.filter_kmers(words, n, k, prefix=R.kmer_make(prefix) if prefix else None, pattern=pattern)
+            a = gpu.collect(seq, k, prefix=prefix, pattern=pattern).cpu().numpy().view(np.uint64)
+            b = gpu.collect(seq, k, prefix=prefix, pattern=pattern, planes=True).cpu().numpy().view(np.uint64)
+            assert np.array_equal(np.sort(a), np.sort(want)), (n, k, prefix, pattern)
+            assert np.array_equal(np.sort(b), np.sort(want)), (n, k, prefix, pattern)
+        seq.free()
+
+
+@pytest.mark.parametrize("bases,stride,k", [(150, 5, 31), (150, 6, 21), (33, 2, 32), (64, 2, 5), (129, 5, 13), (300, 10, 31),
+                                            (31, 1, 31)])
+def test_collect_shift_and_on_reads_never_spans_rows(gpu, bases, stride, k):
+    """Reads: every read is its own dna value; the automaton restarts at every row (runs of <= 128 starts)."""
+    rng = np.random.default_rng(bases * 7 + k)
+    n_reads = 3000
+    words = np.zeros(n_reads * stride, dtype=np.uint64)
+    for r in range(n_reads):
+        w = rand_dna_words(rng, bases)
+        words[r * stride: r * stride + w.size] = w
+    seq = gpu.upload_reads(words, n_reads, bases, stride)
+    for pattern, prefix in (("N" * (k - 1) + "W", None), (_rand_pattern(rng, k, 0.2), "A"), (None, "AC"[:min(2, k)])):
+        pk = R.kmer_make(prefix) if prefix else None
+        want = np.concatenate([R.filter_kmers(words[r * stride:(r + 1) * stride], bases, k, prefix=pk, pattern=pattern)
+                               for r in range(n_reads)])
+        a = gpu.collect(seq, k, prefix=prefix, pattern=pattern).cpu().numpy().view(np.uint64)
+        b = gpu.collect(seq, k, prefix=prefix, pattern=pattern, planes=True).cpu().numpy().view(np.uint64)
+        assert np.array_equal(np.sort(a), np.sort(want)), (pattern, prefix)
+        assert np.array_equal(np.sort(b), np.sort(want)), (pattern, prefix)
+        st, _ = gpu.count(seq, k, prefix=prefix, pattern=pattern, method=dnagpu.COUNT_HASH)
+        u, c = np.unique(want, return_counts=True)
+        assert (st.total, st.distinct, st.unique) == (int(c.sum()), int(u.size), int((c == 1).sum()))
+    seq.free()
+
+
+def test_collect_shift_and_dense_matches_take_several_rounds(gpu):
+    """A clause that keeps (almost) every row: a tile's matches exceed one staging round."""
+    n, k = 3_000_000, 11
+    words = R.synth_seq(77, n)
+    seq = gpu.upload(Dna.from_words(words, n))
+    for pattern in ("N" * k, "N" * (k - 1) + "B"):
+        want = R.filter_kmers(words, n, k, pattern=pattern)
+        a = gpu.collect(seq, k, pattern=pattern).cpu().numpy().view(np.uint64)
+        assert np.array_equal(np.sort(a), np.sort(want))
+    seq.free()

@@ -96,3 +96,79 @@ def test_errors_carry_the_reference_text(mods):
             assert str(e_glue.value) == str(e_ref.value) == "Invalid k value: must be between 1 and 32"
     # the module keeps working after an ereport
     assert glue.generate_kmers(words, nb, 6).size == 3
+
+
+def test_where_pushdown_rows_equal_the_reference_quals(mods):
+    """generate_kmers_where / kmer_stats / count_kmers with the WHERE clause on the GPU against the reference's own
+    plan: generate_kmers rows filtered by ITS starts_with / contains (test.sql:67-73, 86-92)."""
+    ref, glue = mods
+    rng = np.random.default_rng(31)
+    words, nb = ref.dna_in(_random_dna(rng, 30_000))
+    for k, prefix, pattern in ((3, "AC", None), (6, None, "DNMSRN"), (9, "G", "NNWNNSNNN"), (31, "ACG", None),
+                               (32, None, "N" * 31 + "R"), (5, None, None)):
+        pk = ref.kmer_in(prefix) if prefix else None
+        want_rows = ref.generate_kmers(words, nb, k, prefix=pk, pattern=pattern)
+        assert np.array_equal(glue.generate_kmers_where(words, nb, k, prefix=pk, pattern=pattern), want_rows)
+        b = ref.count(words, 1, nb, words.size, k, prefix=pk, pattern=pattern)
+        assert glue.kmer_stats(words, nb, k, prefix=pk, pattern=pattern, where_form=True) == b.stats
+        kk, cc = glue.count_kmers(words, nb, k, prefix=pk, pattern=pattern)
+        assert np.array_equal(kk, b.kmers) and np.array_equal(cc.astype(np.uint64), b.counts)
+    # the reference's per-row ERRORs (dna.c:854-856, 1106-1108) with the reference's texts
+    for fn in (glue.generate_kmers_where, glue.kmer_stats, glue.count_kmers):
+        with pytest.raises(ref_real.PgError, match="Prefix length cannot exceed kmer length"):
+            fn(words, nb, 3, prefix=ref.kmer_in("ACGT"))
+        with pytest.raises(ref_real.PgError, match="Qkmer pattern and kmer lengths do not match"):
+            fn(words, nb, 5, pattern="NNN")
+    assert glue.live_tables() == 0 and glue.live_contexts() == 0
+
+
+def test_generate_kmers_windows_cover_long_values(mods):
+    """The drop-in extracts in windows (GLUE_WINDOW_ROWS = 4 Mi rows): a value longer than two windows, row for row
+    against the oracle, with and without a pushed-down clause."""
+    ref, glue = mods
+    n, k = 9_000_011, 21
+    words = R.synth_seq(5, n)
+    assert np.array_equal(glue.generate_kmers(words, n, k), R.generate_kmers(words, n, k, window=True))
+    pk = R.kmer_make("ACGTT")
+    assert np.array_equal(glue.generate_kmers_where(words, n, k, prefix=pk),
+                          R.filter_kmers(words, n, k, prefix=pk))
+    kk, cc = glue.count_kmers(words, n, k)             # > 2 windows of grouped rows, fetched from the GPU table
+    want = R.count_query(words, 1, n, words.size, k, faithful=False, threads=8)
+    assert np.array_equal(kk, want.kmers) and np.array_equal(cc.astype(np.uint64), want.counts)
+    assert glue.live_tables() == 0
+
+
+def test_abandoned_scan_releases_the_gpu_table(mods):
+    """LIMIT / cancel: the executor stops calling count_kmers half way and resets the SRF's memory context; the GPU
+    table must go with it (MemoryContextRegisterResetCallback), not leak until the backend exits."""
+    ref, glue = mods
+    n, k = 6_000_000, 31
+    words = R.synth_seq(9, n)
+    kk, cc = glue.count_kmers(words, n, k, stop_after=10)
+    assert kk.size == 10 and glue.live_tables() == 0 and glue.live_contexts() == 0
+    # an ERROR raised while the table is alive (bad k on the NEXT query is not it: fail inside the scan instead)
+    kk, cc = glue.count_kmers(words, n, k, stop_after=5_000_000)   # crosses a window boundary, then abandons
+    assert kk.size == 5_000_000 and glue.live_tables() == 0
+
+
+def test_table_form_aggregate_equals_the_reference_plan(mods):
+    """SELECT (kmer_stats_agg(sequence, k)).* FROM dna_sequences  ==  the reference's table-form query
+    (test.sql:140-150): k-mers never span rows, counts merge across rows, NULL rows contribute nothing."""
+    ref, glue = mods
+    rng = np.random.default_rng(5)
+    seqs = []
+    for n in (1, 9, 10, 11, 64, 1000, 4097, 33, 5000, 10):
+        seqs.append(ref.dna_in(_random_dna(rng, n)))
+    seqs.insert(3, None)
+    seqs.append(seqs[5])          # a duplicated row: its k-mers count twice
+    for k in (1, 5, 10, 32):
+        want = R.count_ragged([s for s in seqs if s is not None], k, faithful=False)
+        assert glue.kmer_stats_agg(seqs, k) == want.stats, k
+    assert glue.kmer_stats_agg([None, None], 5) == (0, 0, 0)
+    assert glue.kmer_stats_agg([], 5) == (0, 0, 0)
+    with pytest.raises(ref_real.PgError, match="Invalid k value"):
+        glue.kmer_stats_agg(seqs, 33)
+    # the reference's own numbers shape: 1 M random nt in rows of 100 k, k = 10 (test.sql:151-154: ~ 644 k distinct)
+    rows = [ref.dna_in(_random_dna(rng, 100_000)) for _ in range(10)]
+    total, distinct, unique = glue.kmer_stats_agg(rows, 10)
+    assert total == 10 * (100_000 - 9) and 640_000 < distinct < 650_000 and 380_000 < unique < 390_000

@@ -23,7 +23,8 @@ def test_reference_module_links_with_the_glue_in_place_of_generate_kmers():
     glue = ref_real.glue()
     out = subprocess.run(["nm", "-D", "--defined-only", ref_real.GLUE_SO], capture_output=True, text=True,
                          check=True).stdout
-    for sym in ("generate_kmers", "generate_kmers_cpu", "kmer_stats", "count_kmers", "starts_with", "contains",
+    for sym in ("generate_kmers", "generate_kmers_cpu", "generate_kmers_where", "kmer_stats", "count_kmers",
+                "kmer_stats_agg_trans", "kmer_stats_agg_final", "starts_with", "contains",
                 "kmer_hash", "kmer_eq", "dna_in", "kmer_in", "qkmer_in"):
         assert f" T {sym}\n" in out, sym
     assert glue.kmer_in("ACGT") == (0x78, 4)
