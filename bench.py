@@ -373,6 +373,8 @@ def run_b200(args):
             reads = dict(reads, n_reads=max(world, n_bases // reads["bases"]))
             n_bases = reads["n_reads"] * reads["bases"]
     where = {"prefix": reads["prefix"], "pattern": reads["pattern"]} if reads else {}
+    if reads and args.planes:
+        where["planes"] = True  # A/B: the per-position plane test instead of the Shift-And automaton (single GPU)
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     if world > 1:
@@ -706,6 +708,8 @@ def main():
     ap.add_argument("--cpu-large-sample", type=int, default=0,
                     help="--impl reference: bases per step (e.g. 100000000: a table that no longer fits the CPU caches)")
     ap.add_argument("--no-extract", action="store_true")
+    ap.add_argument("--planes", action="store_true",
+                    help="reads workload, N = 1: evaluate the WHERE clause with the plane test (DNAGPU_WHERE_FLAG_PLANES)")
     ap.add_argument("--chunks", type=int, default=4, help="--exchange fused: digit sub-ranges the exchange is pipelined in")
     ap.add_argument("--exchange", default="gather", choices=["gather", "peer", "fused", "routed"],
                     help="N > 1: gather = every GPU reads all shards over NVLink and counts the k-mers it owns; "

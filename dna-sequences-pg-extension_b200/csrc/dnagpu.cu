@@ -2030,8 +2030,29 @@ static int count_owned(dnagpu_ctx *ctx, const dnagpu_seq *seq, int k, const dnag
                                                                           r.cur, r.keys, ctx->d_ctr, r.cap);
         }));
         TRY(l1_regions_end(ctx, r));
+        /* level 2 and the count size their grids and regions from the number of keys: the rows this GPU kept,
+         * not the expectation (the owners' shares differ by ~ sqrt(n)) */
+        TRY(fetch_counters(ctx));
+        const uint64_t n_kept = ctx->h_ctr[C_TOTAL] - ctx->h_ctr[C_SIDE];
         ctx->force_exact = false;
-        TRY(part_finish(ctx, sc, r.keys, n_expect, r.beg, r.end, r.P1, r.P1, b1, b2, k, stats, 0, table));
+        if (n_kept == 0 && !ctx->h_ctr[C_L1OVF]) {
+            const uint64_t side = ctx->h_ctr[C_SIDE];
+            stats->total = side;
+            stats->distinct = side > 0;
+            stats->unique = side == 1;
+            if (table) {
+                TRY(table_new(ctx, k, stats->distinct, table));
+                if (side) {
+                    ctx->h_ctr[0] = kEmpty;
+                    ctx->h_ctr[1] = side;
+                    CU(ctx, cudaMemcpyAsync((*table)->d_kmers, &ctx->h_ctr[0], 8, cudaMemcpyHostToDevice, ctx->stream));
+                    CU(ctx, cudaMemcpyAsync((*table)->d_counts, &ctx->h_ctr[1], 8, cudaMemcpyHostToDevice, ctx->stream));
+                    CU(ctx, cudaStreamSynchronize(ctx->stream));
+                }
+            }
+            return DNAGPU_OK;
+        }
+        TRY(part_finish(ctx, sc, r.keys, std::max<uint64_t>(n_kept, 1), r.beg, r.end, r.P1, r.P1, b1, b2, k, stats, 0, table));
         if (!ctx->h_ctr[C_L1OVF]) return DNAGPU_OK;
         if (table && *table) {
             dnagpu_table_free(*table);

@@ -581,9 +581,10 @@ class Context:
                                              C.byref(w) if w is not None else None, C.byref(st), None))
         return st
 
-    def count_reads_ptr(self, words_ptr, n_reads, bases_per_read, stride_words, k, prefix=None, pattern=None):
+    def count_reads_ptr(self, words_ptr, n_reads, bases_per_read, stride_words, k, prefix=None, pattern=None,
+                        planes=False):
         """The C-ABI host call for a batch of reads on a raw host pointer: stats only."""
-        w, _keep = _where(prefix, pattern)
+        w, _keep = _where(prefix, pattern, planes)
         st = Stats()
         self._ok(self.lib.dnagpu_count_reads(self.handle, words_ptr, n_reads, bases_per_read, stride_words, k,
                                              C.byref(w) if w is not None else None, C.byref(st), None))
