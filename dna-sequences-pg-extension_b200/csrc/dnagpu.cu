@@ -269,8 +269,10 @@ extern "C" int dnagpu_create(dnagpu_ctx **out, int device)
     SMEM_ATTR(k_filter_collect<kSingle>);
     SMEM_ATTR(k_filter_collect<kFixed>);
     SMEM_ATTR(k_filter_collect<kRagged>);
-    SMEM_ATTR(k_filter_collect_sa<kSingle>);
-    SMEM_ATTR(k_filter_collect_sa<kFixed>);
+    SMEM_ATTR((k_filter_sa<kSingle, kSaCollect>));
+    SMEM_ATTR((k_filter_sa<kFixed, kSaCollect>));
+    SMEM_ATTR((k_filter_sa<kSingle, kSaWrite>));
+    SMEM_ATTR((k_filter_sa<kFixed, kSaWrite>));
     SMEM_ATTR((k_partition_write<kSingle, false>));
     SMEM_ATTR((k_partition_write<kSingle, true>));
     SMEM_ATTR((k_partition_write<kFixed, false>));
@@ -321,8 +323,13 @@ extern "C" int dnagpu_create(dnagpu_ctx **out, int device)
                 per_sm > 0)
                 ctx->bins_ctas_per_sm = per_sm;
         }
-        cudaFuncSetAttribute(k_part_scatter_owned, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                             2 * kOwnList * (int)sizeof(uint64_t) + (int)sizeof(ScatterSmem));
+        {
+            const int osmem = 2 * kOwnList * (int)sizeof(uint64_t) + (int)sizeof(ScatterSmem);
+#define OWNED_ATTR(WPT, ML) cudaFuncSetAttribute(k_part_scatter_owned<WPT, ML>, cudaFuncAttributeMaxDynamicSharedMemorySize, osmem)
+            OWNED_ATTR(1, true); OWNED_ATTR(2, true); OWNED_ATTR(4, true);
+            OWNED_ATTR(1, false); OWNED_ATTR(2, false); OWNED_ATTR(4, false);
+#undef OWNED_ATTR
+        }
         cudaFuncSetAttribute(k_sort_scatter<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(SortSmem));
         cudaFuncSetAttribute(k_sort_scatter<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(SortSmem));
         const int bsmem = kBucketSlots * 12;
@@ -1092,9 +1099,55 @@ static int read_u64(dnagpu_ctx *ctx, const uint64_t *d, uint64_t *h)
 }
 
 /* matches per CTA tile + their exclusive scan; *n_match = total */
-static int filter_scan(dnagpu_ctx *ctx, const dnagpu_seq *seq, const SeqView &v, const Pred &p,
+/* the Shift-And tables of a predicate: M[b] bit (i + 32 - k) = base b is allowed at pattern position i */
+static SaPred sa_pred_of(const Pred &p, int k)
+{
+    const uint64_t plane[4] = {p.ma, p.mt, p.mc, p.mg};
+    SaPred sp;
+    for (int b = 0; b < 4; ++b) {
+        uint32_t m = 0;
+        for (int i = 0; i < k; ++i)
+            if ((plane[b] >> (2 * i)) & 1) m |= 1u << (i + 32 - k);
+        sp.m[b] = m;
+    }
+    sp.inj = 1u << (32 - k);
+    return sp;
+}
+
+/* the ordered scan as a Shift-And automaton (single sequences and fixed-stride reads): count per tile, scan, write */
+static bool sa_applies(const dnagpu_ctx *ctx, const dnagpu_seq *seq) { return seq->layout != kRagged && !ctx->plane_filter; }
+static uint64_t sa_runs(const dnagpu_seq *seq, const SeqView &v)
+{
+    return seq->layout == kSingle ? (v.n_items + kSaItems - 1) / kSaItems
+                                  : v.n_seqs * ((v.items_per_seq + kSaItems - 1) / kSaItems);
+}
+template <int MODE>
+static int sa_launch(dnagpu_ctx *ctx, const char *name, const dnagpu_seq *seq, const SeqView &v, const Pred &p, int k,
+                     uint64_t *tile_io, uint64_t *d_out)
+{
+    const SaPred sp = sa_pred_of(p, k);
+    const unsigned tiles = grid_for(sa_runs(seq, v), kThreads);
+    const int smem = MODE == kSaCount ? 0 : kSaStage * (int)sizeof(uint64_t);
+    return launch(ctx, name, [&] {
+        if (seq->layout == kSingle)
+            k_filter_sa<kSingle, MODE><<<tiles, kThreads, smem, ctx->stream>>>(v, sp, kmer_mask(k), k, 0, nullptr, tile_io, d_out);
+        else
+            k_filter_sa<kFixed, MODE><<<tiles, kThreads, smem, ctx->stream>>>(v, sp, kmer_mask(k), k, 0, nullptr, tile_io, d_out);
+    });
+}
+
+static int filter_scan(dnagpu_ctx *ctx, const dnagpu_seq *seq, const SeqView &v, const Pred &p, int k,
                        Scratch &sc, uint64_t **tile_off, uint64_t *n_match)
 {
+    if (sa_applies(ctx, seq)) {
+        const unsigned tiles = grid_for(sa_runs(seq, v), kThreads);
+        uint64_t *tile_cnt;
+        TRY(sc.get((void **)&tile_cnt, ((uint64_t)tiles + 1) * 8));
+        TRY(sc.get((void **)tile_off, ((uint64_t)tiles + 1) * 8));
+        TRY(sa_launch<kSaCount>(ctx, "filter_count", seq, v, p, k, tile_cnt, nullptr));
+        TRY(scan_any(ctx, sc, tile_cnt, tiles, *tile_off));
+        return read_u64(ctx, *tile_off + tiles, n_match);
+    }
     const unsigned tiles = grid_for(v.n_items, kThreads);
     uint64_t *tile_cnt;
     TRY(sc.get((void **)&tile_cnt, ((uint64_t)tiles + 1) * 8));
@@ -1130,11 +1183,12 @@ extern "C" int dnagpu_filter(dnagpu_ctx *ctx, const dnagpu_seq *seq, int k,
     if (v.n_rows == 0) return DNAGPU_OK;
     Scratch sc(ctx);
     uint64_t *tile_off, n_match;
-    TRY(filter_scan(ctx, seq, v, p, sc, &tile_off, &n_match));
+    TRY(filter_scan(ctx, seq, v, p, k, sc, &tile_off, &n_match));
     *n_out = n_match;
     if (!d_out || n_match == 0) return DNAGPU_OK;
     if (cap < n_match)
         return fail(ctx, DNAGPU_ECAPACITY, "filter needs room for %llu rows", (unsigned long long)n_match);
+    if (sa_applies(ctx, seq)) return sa_launch<kSaWrite>(ctx, "filter_write", seq, v, p, k, tile_off, d_out);
     const unsigned tiles = grid_for(v.n_items, kThreads);
     const int smem = kThreads * 32 * (int)sizeof(uint64_t);
     DISPATCH_LAYOUT(seq->layout, TRY(launch(ctx, "filter_write", [&] {
@@ -1905,21 +1959,6 @@ static int count_kmers_pipelined(dnagpu_ctx *ctx, const uint64_t *words, uint64_
 }
 
 /* One predicate scan, matches appended in no particular order. */
-/* the Shift-And tables of a predicate: M[b] bit (i + 32 - k) = base b is allowed at pattern position i */
-static SaPred sa_pred_of(const Pred &p, int k)
-{
-    const uint64_t plane[4] = {p.ma, p.mt, p.mc, p.mg};
-    SaPred sp;
-    for (int b = 0; b < 4; ++b) {
-        uint32_t m = 0;
-        for (int i = 0; i < k; ++i)
-            if ((plane[b] >> (2 * i)) & 1) m |= 1u << (i + 32 - k);
-        sp.m[b] = m;
-    }
-    sp.inj = 1u << (32 - k);
-    return sp;
-}
-
 static int collect_launch(dnagpu_ctx *ctx, int layout, const SeqView &v, const Pred &p, int k, uint64_t *d_out, uint64_t cap)
 {
     if (layout != kRagged && !ctx->plane_filter) { /* Shift-And over the base stream: 6 instructions per base */
@@ -1929,11 +1968,11 @@ static int collect_launch(dnagpu_ctx *ctx, int layout, const SeqView &v, const P
         const int smem = kSaStage * (int)sizeof(uint64_t);
         return launch(ctx, "filter_collect", [&] {
             if (layout == kSingle)
-                k_filter_collect_sa<kSingle><<<grid_for(runs, kThreads), kThreads, smem, ctx->stream>>>(
-                    v, sp, kmer_mask(k), k, cap, ctx->d_ctr + C_CURSOR, d_out);
+                k_filter_sa<kSingle, kSaCollect><<<grid_for(runs, kThreads), kThreads, smem, ctx->stream>>>(
+                    v, sp, kmer_mask(k), k, cap, ctx->d_ctr + C_CURSOR, nullptr, d_out);
             else
-                k_filter_collect_sa<kFixed><<<grid_for(runs, kThreads), kThreads, smem, ctx->stream>>>(
-                    v, sp, kmer_mask(k), k, cap, ctx->d_ctr + C_CURSOR, d_out);
+                k_filter_sa<kFixed, kSaCollect><<<grid_for(runs, kThreads), kThreads, smem, ctx->stream>>>(
+                    v, sp, kmer_mask(k), k, cap, ctx->d_ctr + C_CURSOR, nullptr, d_out);
         });
     }
     const unsigned tiles = grid_for(v.n_items, kThreads);
@@ -2022,13 +2061,20 @@ static int count_owned(dnagpu_ctx *ctx, const dnagpu_seq *seq, int k, const dnag
         TRY(zero_counters(ctx));
         L1Regions r;
         TRY(l1_regions_begin(ctx, sc, n_expect, b1, &r));
-        const int wpt = (int)std::max<uint32_t>(1, G / 2);
+        const int wpt = G >= 8 ? 4 : G >= 4 ? 2 : 1; /* a CTA examines 512 * wpt words and keeps ~ 16384 * wpt / G k-mers */
         const int smem = 2 * kOwnList * (int)sizeof(uint64_t) + (int)sizeof(ScatterSmem);
         const unsigned grid = grid_for(n_vitems, (uint64_t)kScatThreads * wpt);
+#define OWNED_LAUNCH(WPT, ML) \
+    k_part_scatter_owned<WPT, ML><<<grid, kScatThreads, smem, ctx->stream>>>(ov, mask, own_lo, own_span, 64 - b1, r.P1, r.beg, \
+                                                                             r.cur, r.keys, ctx->d_ctr, r.cap)
         TRY(launch(ctx, "part_scatter_owned", [&] {
-            k_part_scatter_owned<<<grid, kScatThreads, smem, ctx->stream>>>(ov, mask, own_lo, own_span, wpt, 64 - b1, r.P1, r.beg,
-                                                                          r.cur, r.keys, ctx->d_ctr, r.cap);
+            if (k < 16) {
+                if (wpt == 4) OWNED_LAUNCH(4, true); else if (wpt == 2) OWNED_LAUNCH(2, true); else OWNED_LAUNCH(1, true);
+            } else {
+                if (wpt == 4) OWNED_LAUNCH(4, false); else if (wpt == 2) OWNED_LAUNCH(2, false); else OWNED_LAUNCH(1, false);
+            }
         }));
+#undef OWNED_LAUNCH
         TRY(l1_regions_end(ctx, r));
         /* level 2 and the count size their grids and regions from the number of keys: the rows this GPU kept,
          * not the expectation (the owners' shares differ by ~ sqrt(n)) */

@@ -561,12 +561,17 @@ __device__ __forceinline__ void sa_run_masks(const SeqView &sv, uint32_t lut, ui
     }
 }
 
-template <int L>
-__global__ void __launch_bounds__(kThreads) k_filter_collect_sa(SeqView sv, SaPred sp, uint64_t mask, int k, uint64_t cap,
-                                                                unsigned long long *__restrict__ cursor,
-                                                                uint64_t *__restrict__ out)
+/* MODE: kSaCollect = unordered, a tile claims its output range from `cursor` (tiles past `cap` write nothing but
+ * still count); kSaCount = matches per tile -> tile_io[tile]; kSaWrite = the tile's rows, in sequence order, at
+ * out + tile_io[tile] (the exclusive scan of the counts).  A tile = kThreads runs = 32768 start positions. */
+enum { kSaCollect = 0, kSaCount = 1, kSaWrite = 2 };
+
+template <int L, int MODE>
+__global__ void __launch_bounds__(kThreads) k_filter_sa(SeqView sv, SaPred sp, uint64_t mask, int k, uint64_t cap,
+                                                        unsigned long long *__restrict__ cursor,
+                                                        uint64_t *__restrict__ tile_io, uint64_t *__restrict__ out)
 {
-    extern __shared__ uint64_t stage[]; /* kSaStage entries */
+    extern __shared__ uint64_t stage[]; /* kSaStage entries (none for kSaCount) */
     __shared__ __align__(16) uint32_t lut[4];
     __shared__ unsigned long long base_s;
     if (threadIdx.x < 4) lut[threadIdx.x] = sp.m[threadIdx.x];
@@ -582,9 +587,16 @@ __global__ void __launch_bounds__(kThreads) k_filter_collect_sa(SeqView sv, SaPr
     for (int i = 0; i < kSaItems; ++i) n += __popc(sm[i]);
     uint32_t total;
     const uint32_t rank0 = block_exscan(n, &total);
-    if (threadIdx.x == 0 && total) base_s = atomicAdd(cursor, (unsigned long long)total);
+    if (MODE == kSaCount) {
+        if (threadIdx.x == 0) tile_io[blockIdx.x] = total;
+        return;
+    }
+    if (threadIdx.x == 0) {
+        if (MODE == kSaWrite) base_s = tile_io[blockIdx.x];
+        else if (total) base_s = atomicAdd(cursor, (unsigned long long)total);
+    }
     __syncthreads();
-    if (total == 0 || base_s + total > cap) return; /* uniform; the cursor still counts what did not fit */
+    if (total == 0 || (MODE == kSaCollect && base_s + total > cap)) return; /* uniform; the cursor still counts what did not fit */
     uint64_t *dst = out + base_s;
     for (uint32_t round = 0; round < total; round += kSaStage) { /* one round unless > 8192 rows of the tile match */
         uint32_t rank = rank0;

@@ -452,7 +452,9 @@ struct OwnedView {
     uint32_t n_pieces;
 };
 
-/* bit j of the result: start j of the item (w0, w1) is a k-mer this GPU owns */
+/* bit j of the result: start j of the item (w0, w1) is a k-mer this GPU owns.  MASKLO: k < 16, the low word
+ * of the window holds bases past the k-mer */
+template <bool MASKLO = true>
 __device__ __forceinline__ uint32_t owned_mask(uint64_t w0, uint64_t w1, uint32_t mask_lo, uint32_t own_lo,
                                                uint32_t own_span)
 {
@@ -462,7 +464,7 @@ __device__ __forceinline__ uint32_t owned_mask(uint64_t w0, uint64_t w1, uint32_
     for (int j = 0; j < 32; ++j) {
         const uint32_t lo = j == 0 ? a0 : j < 16 ? __funnelshift_r(a0, a1, 2 * j) : j == 16 ? a1
                                                                                              : __funnelshift_r(a1, a2, 2 * j - 32);
-        const uint32_t h = (lo & mask_lo) * kOwnerMul;
+        const uint32_t h = (MASKLO ? lo & mask_lo : lo) * kOwnerMul;
         km |= (uint32_t)((h - own_lo) < own_span) << j;
     }
     return km;
@@ -481,8 +483,11 @@ __device__ __forceinline__ int owned_item(const OwnedView &ov, uint64_t v, uint6
     return left < 32 ? (int)left : 32;
 }
 
+/* WPT packed words per thread (n_parts / 2, so that a CTA keeps ~ 8192 k-mers); all of them are loaded before
+ * the first is looked at: a peer-memory load takes microseconds and there is one CTA per SM to hide it. */
+template <int WPT, bool MASKLO>
 __global__ void __launch_bounds__(kScatThreads, 1) k_part_scatter_owned(OwnedView ov, uint64_t mask, uint32_t own_lo,
-                                                                       uint32_t own_span, int wpt, int shift,
+                                                                       uint32_t own_span, int shift,
                                                                        uint32_t fan,
                                                                        const uint64_t *__restrict__ child_off,
                                                                        unsigned long long *__restrict__ child_cur,
@@ -501,16 +506,25 @@ __global__ void __launch_bounds__(kScatThreads, 1) k_part_scatter_owned(OwnedVie
     __syncthreads();
     const uint32_t fm = fan - 1, mask_lo = (uint32_t)mask;
     const uint64_t n_vitems = ov.vfirst[ov.n_pieces];
-    const uint64_t v0 = (uint64_t)blockIdx.x * ((uint64_t)kScatThreads * wpt);
+    const uint64_t v0 = (uint64_t)blockIdx.x * ((uint64_t)kScatThreads * WPT);
     uint32_t wcur = 0, kept = 0, side = 0;
-    /* phase 1: keep masks, warp scan, append */
-    for (int it = 0; it < wpt; ++it) {
+    uint64_t pw0[WPT], pw1[WPT];
+    int pc[WPT];
+#pragma unroll
+    for (int it = 0; it < WPT; ++it) {
         const uint64_t v = v0 + (uint64_t)it * kScatThreads + tid;
-        uint64_t w0 = 0, w1 = 0;
+        pw0[it] = pw1[it] = 0;
+        pc[it] = 0;
+        if (v < n_vitems) pc[it] = owned_item(ov, v, pw0[it], pw1[it]);
+    }
+    /* phase 1: keep masks, warp scan, append */
+#pragma unroll
+    for (int it = 0; it < WPT; ++it) {
+        const uint64_t w0 = pw0[it], w1 = pw1[it];
+        const int c = pc[it];
         uint32_t km = 0;
-        if (v < n_vitems) {
-            const int c = owned_item(ov, v, w0, w1);
-            km = owned_mask(w0, w1, mask_lo, own_lo, own_span);
+        if (c > 0) {
+            km = owned_mask<MASKLO>(w0, w1, mask_lo, own_lo, own_span);
             if (c < 32) km &= (1u << c) - 1u;
         }
         const uint32_t n = __popc(km);

@@ -469,11 +469,11 @@ class Context:
                                         None, 0, C.byref(n)))
         return int(n.value)
 
-    def filter(self, seq, k, prefix=None, pattern=None):
+    def filter(self, seq, k, prefix=None, pattern=None, planes=False):
         """Rows of generate_kmers that pass the WHERE clause, in sequence order (torch int64 CUDA tensor).
         One pass into a buffer sized for 1/8 of the rows; a second, exactly sized pass only if that was too small."""
         import torch
-        w, _keep = _where(prefix, pattern)
+        w, _keep = _where(prefix, pattern, planes)
         wp = C.byref(w) if w is not None else None
         n = C.c_uint64()
         guess = seq.kmer_count(k) if w is None else max(1024, seq.kmer_count(k) // 8)

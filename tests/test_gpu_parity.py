@@ -575,7 +575,7 @@ def test_two_gpu_peer_exchange_end_to_end():
         pytest.skip("needs 2 GPUs")
     n, k = 20_000_000, 21
     words = R.synth_seq(2, 100_000_000, first_word=0, n_words=(n + 31) // 32)  # c2's stream, cut to n bases
-    for exchange in ("peer", "fused", "routed"):
+    for exchange in ("gather", "peer", "fused", "routed"):
         out = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2",
                               "--master-addr", "127.0.0.1", "--master-port", "29533", os.path.join(ROOT, "bench.py"),
                               "--gpus", "2", "--workload", "c2", "--steps", "1", "--warmup", "3", "--e2e-steps", "1",
@@ -584,7 +584,9 @@ def test_two_gpu_peer_exchange_end_to_end():
         assert out.returncode == 0, out.stderr[-2000:]
         d = json.loads(out.stdout.strip().splitlines()[-1])
         assert d["n_gpus"] == 2 and exchange in d["config"]["parallelism"]
-        assert d["result"] == {"total": 99999980, "distinct": 87735270, "unique": 77017094}
+        assert {q: d["result"][q] for q in ("total", "distinct", "unique")} == \
+            {"total": 99999980, "distinct": 87735270, "unique": 77017094}
+        assert d["result"]["oracle"].startswith("equal")
     del words
 
 
@@ -641,6 +643,10 @@ def test_collect_shift_and_equals_plane_test_equals_oracle(gpu, k):
             b = gpu.collect(seq, k, prefix=prefix, pattern=pattern, planes=True).cpu().numpy().view(np.uint64)
             assert np.array_equal(np.sort(a), np.sort(want)), (n, k, prefix, pattern)
             assert np.array_equal(np.sort(b), np.sort(want)), (n, k, prefix, pattern)
+            # the ordered scan (generate_kmers ... WHERE, rows in sequence order) in both forms
+            c = gpu.filter(seq, k, prefix=prefix, pattern=pattern).cpu().numpy().view(np.uint64)
+            d = gpu.filter(seq, k, prefix=prefix, pattern=pattern, planes=True).cpu().numpy().view(np.uint64)
+            assert np.array_equal(c, want) and np.array_equal(d, want), (n, k, prefix, pattern)
         seq.free()
 
 
@@ -663,6 +669,8 @@ def test_collect_shift_and_on_reads_never_spans_rows(gpu, bases, stride, k):
         b = gpu.collect(seq, k, prefix=prefix, pattern=pattern, planes=True).cpu().numpy().view(np.uint64)
         assert np.array_equal(np.sort(a), np.sort(want)), (pattern, prefix)
         assert np.array_equal(np.sort(b), np.sort(want)), (pattern, prefix)
+        assert np.array_equal(gpu.filter(seq, k, prefix=prefix, pattern=pattern).cpu().numpy().view(np.uint64), want)
+        assert gpu.filter_count(seq, k, prefix=prefix, pattern=pattern) == want.size
         st, _ = gpu.count(seq, k, prefix=prefix, pattern=pattern, method=dnagpu.COUNT_HASH)
         u, c = np.unique(want, return_counts=True)
         assert (st.total, st.distinct, st.unique) == (int(c.sum()), int(u.size), int((c == 1).sum()))
@@ -678,4 +686,5 @@ def test_collect_shift_and_dense_matches_take_several_rounds(gpu):
         want = R.filter_kmers(words, n, k, pattern=pattern)
         a = gpu.collect(seq, k, pattern=pattern).cpu().numpy().view(np.uint64)
         assert np.array_equal(np.sort(a), np.sort(want))
+        assert np.array_equal(gpu.filter(seq, k, pattern=pattern).cpu().numpy().view(np.uint64), want)
     seq.free()
