@@ -1111,6 +1111,7 @@ static SaPred sa_pred_of(const Pred &p, int k)
         sp.m[b] = m;
     }
     sp.inj = 1u << (32 - k);
+    sp.two = 2;
     return sp;
 }
 
@@ -2054,18 +2055,19 @@ static int count_owned(dnagpu_ctx *ctx, const dnagpu_seq *seq, int k, const dnag
         Scratch sc(ctx);
         int b1, b2;
         plan_bits(n_expect, 1, &b1, &b2);
-        if (b1 > 10) { /* the owned scatter keeps its per-lane dummy bins behind the digits: fan-out <= 1024 */
-            b2 = std::min(11, b2 + b1 - 10);
-            b1 = 10;
+        if (b1 > 8) { /* a tile of the owned scatter is ~ 4096 keys: level 1 takes 8 bits (16-key runs) when level 2 can take the rest */
+            const int b = b1 + b2;
+            b1 = std::max(8, b - 11);
+            b2 = b - b1;
         }
         TRY(zero_counters(ctx));
         L1Regions r;
         TRY(l1_regions_begin(ctx, sc, n_expect, b1, &r));
-        const int wpt = G >= 8 ? 4 : G >= 4 ? 2 : 1; /* a CTA examines 512 * wpt words and keeps ~ 16384 * wpt / G k-mers */
+        const int wpt = G >= 8 ? 4 : G >= 4 ? 2 : 1; /* a CTA examines 256 * wpt words and keeps ~ 8192 * wpt / G k-mers */
         const int smem = 2 * kOwnList * (int)sizeof(uint64_t) + (int)sizeof(ScatterSmem);
-        const unsigned grid = grid_for(n_vitems, (uint64_t)kScatThreads * wpt);
+        const unsigned grid = grid_for(n_vitems, (uint64_t)kOwnThreads * wpt);
 #define OWNED_LAUNCH(WPT, ML) \
-    k_part_scatter_owned<WPT, ML><<<grid, kScatThreads, smem, ctx->stream>>>(ov, mask, own_lo, own_span, 64 - b1, r.P1, r.beg, \
+    k_part_scatter_owned<WPT, ML><<<grid, kOwnThreads, smem, ctx->stream>>>(ov, mask, own_lo, own_span, 64 - b1, r.P1, r.beg, \
                                                                              r.cur, r.keys, ctx->d_ctr, r.cap)
         TRY(launch(ctx, "part_scatter_owned", [&] {
             if (k < 16) {

@@ -494,10 +494,16 @@ constexpr int kSaStage = 8192; /* staged matches per round (64 KB) */
 struct SaPred {
     uint32_t m[4]; /* M[A], M[T], M[C], M[G], left-aligned */
     uint32_t inj;  /* 1 << (32 - k) */
+    uint32_t two;  /* the constant 2, as a run-time value: keeps the two multiply-adds of a step on the FMA pipe */
 };
 
 /* 32 bases of one half-word pair: steps the automaton, returns the 32 end-match bits (bit j = base j) */
-__device__ __forceinline__ uint32_t sa_word(uint64_t w, uint32_t lut_sa, uint32_t inj, uint32_t &F)
+/* Integer SASS splits over two pipes of half the issue rate each (B300_MICROARCH.md: IMAD on the FMA pipe;
+ * LOP3 / SHF / IADD3 on the ALU pipe, one warp instruction per two clocks per SM sub-partition): a step written
+ * with shifts and adds is five ALU-pipe instructions = 10 clocks.  Here the state update and the match bit come
+ * from ONE 32 x 32 -> 64 multiply-add (low word = 2t + inj = the next F, high word = bit 31 of t = the match) and
+ * the match bits are collected by a second multiply-add (e = 2e + match): 3 ALU + 2 FMA + 1 LDS per base. */
+__device__ __forceinline__ uint32_t sa_word(uint64_t w, uint32_t lut_sa, uint32_t inj, uint32_t two, uint32_t &F)
 {
     const uint32_t lo = (uint32_t)w, hi = (uint32_t)(w >> 32);
     uint32_t e = 0;
@@ -509,9 +515,17 @@ __device__ __forceinline__ uint32_t sa_word(uint64_t w, uint32_t lut_sa, uint32_
         const uint32_t addr = ((s >= 2 ? h >> (s - 2) : h << 2) & 12u) | lut_sa;
         uint32_t m;
         asm("ld.shared.u32 %0, [%1];" : "=r"(m) : "r"(addr));
+#ifdef DNAGPU_SA_ALU
         const uint32_t t = F & m;
         F = t + t + inj;
         e = __funnelshift_l(t, e, 1); /* shifts the sign bit of t in at bit 0: step j ends at bit 31 - j */
+#else
+        const uint32_t t = (F | inj) & m; /* F carries 2t of the step before; bit 32 - k of it is never set */
+        uint64_t p;
+        asm("mul.wide.u32 %0, %1, %2;" : "=l"(p) : "r"(t), "r"(two));
+        F = (uint32_t)p;
+        asm("mad.lo.u32 %0, %1, %2, %3;" : "=r"(e) : "r"(e), "r"(two), "r"((uint32_t)(p >> 32)));
+#endif
     }
     return __brev(e);
 }
@@ -542,7 +556,7 @@ __device__ __forceinline__ uint64_t n_runs_of(const SeqView &sv)
 
 /* start-position match masks of one run; w[] receives its packed words */
 template <int L>
-__device__ __forceinline__ void sa_run_masks(const SeqView &sv, uint32_t lut, uint32_t inj, int k, uint64_t r,
+__device__ __forceinline__ void sa_run_masks(const SeqView &sv, uint32_t lut, uint32_t inj, uint32_t two, int k, uint64_t r,
                                              uint64_t (&w)[kSaItems + 1], uint32_t (&sm)[kSaItems])
 {
     uint32_t valid;
@@ -550,9 +564,13 @@ __device__ __forceinline__ void sa_run_masks(const SeqView &sv, uint32_t lut, ui
     const int n_items = (int)((valid + 31) >> 5);
 #pragma unroll
     for (int i = 0; i <= kSaItems; ++i) w[i] = i <= n_items ? ld_nc(p + i) : 0; /* + the halo word */
+#ifdef DNAGPU_SA_ALU
     uint32_t F = inj, e[kSaItems + 1];
+#else
+    uint32_t F = 0, e[kSaItems + 1]; /* the injected bit is OR-ed in at the start of every step */
+#endif
 #pragma unroll
-    for (int i = 0; i <= kSaItems; ++i) e[i] = i <= n_items ? sa_word(w[i], lut, inj, F) : 0u;
+    for (int i = 0; i <= kSaItems; ++i) e[i] = i <= n_items ? sa_word(w[i], lut, inj, two, F) : 0u;
 #pragma unroll
     for (int i = 0; i < kSaItems; ++i) {
         const uint32_t m = __funnelshift_r(e[i], e[i + 1], k - 1); /* the k-mer starting at s ends at s + k - 1 */
@@ -581,7 +599,7 @@ __global__ void __launch_bounds__(kThreads) k_filter_sa(SeqView sv, SaPred sp, u
     const uint64_t r = (uint64_t)blockIdx.x * kThreads + threadIdx.x;
     uint64_t w[kSaItems + 1];
     uint32_t sm[kSaItems] = {0, 0, 0, 0};
-    if (r < n_runs) sa_run_masks<L>(sv, lut_sa, sp.inj, k, r, w, sm);
+    if (r < n_runs) sa_run_masks<L>(sv, lut_sa, sp.inj, sp.two, k, r, w, sm);
     uint32_t n = 0;
 #pragma unroll
     for (int i = 0; i < kSaItems; ++i) n += __popc(sm[i]);

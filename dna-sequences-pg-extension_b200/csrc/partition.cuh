@@ -167,17 +167,22 @@ struct ScatterSmem {
  * one global atomicAdd per non-empty digit to claim its output run.  The atomics' results
  * stay in registers (gd[]) so that their latency hides behind the placing phase; the
  * caller hands them to scatter_publish() before the flush. */
-constexpr int kPlanPer = kMaxFan / kScatThreads; /* 4 digits per thread */
 constexpr long long kNoDest = (long long)0x8000000000000000ull; /* a run that found its region full */
 
-struct ScatterClaim { /* what scatter_plan leaves in registers for scatter_publish */
+/* THREADS = threads of the CTA (512 in the local scatters, 256 in the owned one): each plans kMaxFan / THREADS digits */
+template <int THREADS = kScatThreads>
+struct ScatterClaimT { /* what scatter_plan leaves in registers for scatter_publish */
+    static constexpr int kPlanPer = kMaxFan / THREADS;
     unsigned long long at[kPlanPer]; /* value returned by the claim of digit base + i: NOT looked at before the publish */
     uint32_t n[kPlanPer], ex[kPlanPer];
 };
+using ScatterClaim = ScatterClaimT<kScatThreads>;
 
+template <int THREADS = kScatThreads>
 __device__ __forceinline__ uint32_t scatter_plan(ScatterSmem &s, uint32_t fan,
-                                                 unsigned long long *__restrict__ child_cur, ScatterClaim &cl)
+                                                 unsigned long long *__restrict__ child_cur, ScatterClaimT<THREADS> &cl)
 {
+    constexpr int kPlanPer = ScatterClaimT<THREADS>::kPlanPer;
     uint32_t sum = 0;
     const uint32_t base = threadIdx.x * kPlanPer;
 #pragma unroll
@@ -196,7 +201,7 @@ __device__ __forceinline__ uint32_t scatter_plan(ScatterSmem &s, uint32_t fan,
     __syncthreads();
     uint32_t woff = 0, total = 0;
 #pragma unroll
-    for (int i = 0; i < kScatThreads / 32; ++i) {
+    for (int i = 0; i < THREADS / 32; ++i) {
         uint32_t t = s.warp_tot[i];
         if (i < wid) woff += t;
         total += t;
@@ -219,10 +224,12 @@ __device__ __forceinline__ uint32_t scatter_plan(ScatterSmem &s, uint32_t fan,
 
 /* After the placing phase: where every digit's run goes.  With cap != 0 (optimistic layout) a run that
  * finds its region full gets no destination and raises `full_flag`: the caller re-runs exactly. */
+template <int THREADS = kScatThreads>
 __device__ __forceinline__ void scatter_publish(ScatterSmem &s, uint32_t fan, const uint64_t *__restrict__ child_off,
-                                                const ScatterClaim &cl, uint64_t cap = 0,
+                                                const ScatterClaimT<THREADS> &cl, uint64_t cap = 0,
                                                 unsigned long long *__restrict__ ctr = nullptr, int full_flag = C_L1OVF)
 {
+    constexpr int kPlanPer = ScatterClaimT<THREADS>::kPlanPer;
     const uint32_t base = threadIdx.x * kPlanPer;
 #pragma unroll
     for (int i = 0; i < kPlanPer; ++i) {
@@ -240,13 +247,13 @@ __device__ __forceinline__ void scatter_publish(ScatterSmem &s, uint32_t fan, co
 /* stage -> global: consecutive threads copy consecutive stage entries, i.e. whole runs.  The digit of
  * a staged key is recomputed (one multiply) rather than kept in a side array: the kernel is bound by
  * L1 data-pipe wavefronts (ncu: 67 % busy), not by ALU work. */
-template <int PER = kScatPer>
+template <int PER = kScatPer, int THREADS = kScatThreads>
 __device__ __forceinline__ void scatter_flush(const ScatterSmem &s, const uint64_t *stage, uint32_t total,
                                               int shift, uint32_t fm, uint64_t *__restrict__ out)
 {
 #pragma unroll
     for (int u = 0; u < PER; ++u) {
-        const uint32_t i = (uint32_t)u * kScatThreads + threadIdx.x;
+        const uint32_t i = (uint32_t)u * THREADS + threadIdx.x;
         if (i < total) {
             const uint64_t x = stage[i];
             const long long g = s.gdelta[digit_of(part_hash(x), shift, fm)];
@@ -431,16 +438,17 @@ __global__ void __launch_bounds__(kScatThreads, (PER == 16 ? 2 : 1)) k_part_scat
  * exactly like the single-GPU level 1 (optimistic regions, one run per (tile, digit)).  There is no
  * exchange step and nothing to merge: level 2 and the bucket count then run on local data only.
  *
- * A CTA examines 512 * wpt packed words (wpt = n_parts / 2, so that it keeps ~ 8192 k-mers).  Kept k-mers
+ * A CTA examines 256 * wpt packed words (wpt = n_parts / 2, so that it keeps ~ 4096 k-mers).  Kept k-mers
  * are appended to a shared-memory list -- a compact segment per warp, filled through a warp scan of the
  * per-word keep masks, plus a small shared overflow area -- and then read back lane-strided, so the rank /
  * place / flush phases work on balanced, statically indexed register arrays. */
 constexpr int kMaxPieces = 16;
+constexpr int kOwnThreads = 256;                               /* two CTAs per SM: one's scan (ALU) under the other's scatter (L1) */
 constexpr int kOwnSeg = 576;                                   /* list slots of one warp (mean 512, sigma ~ 21) */
 constexpr int kOwnPer = kOwnSeg / 32;                          /* 18 keys per lane from the warp's segment      */
-constexpr int kOwnOvf = 1024;                                  /* shared overflow slots                         */
-constexpr int kOwnOvfPer = kOwnOvf / kScatThreads;             /* 2 per thread                                  */
-constexpr int kOwnList = (kScatThreads / 32) * kOwnSeg + kOwnOvf; /* 10240 keys                                 */
+constexpr int kOwnOvf = 512;                                   /* shared overflow slots                         */
+constexpr int kOwnOvfPer = kOwnOvf / kOwnThreads;              /* 2 per thread                                  */
+constexpr int kOwnList = (kOwnThreads / 32) * kOwnSeg + kOwnOvf; /* 5120 keys                                   */
 constexpr int kOwnRows = kOwnPer + kOwnOvfPer;                 /* keys one thread ranks and places              */
 constexpr uint32_t kOwnMaxFan = 1024;                          /* cur[fan .. fan + 31] are the per-lane dummies */
 
@@ -483,10 +491,10 @@ __device__ __forceinline__ int owned_item(const OwnedView &ov, uint64_t v, uint6
     return left < 32 ? (int)left : 32;
 }
 
-/* WPT packed words per thread (n_parts / 2, so that a CTA keeps ~ 8192 k-mers); all of them are loaded before
- * the first is looked at: a peer-memory load takes microseconds and there is one CTA per SM to hide it. */
+/* WPT packed words per thread (n_parts / 2, so that a CTA of 256 threads keeps ~ 4096 k-mers); all of them are
+ * loaded before the first is looked at (a peer-memory load takes microseconds).  Two CTAs fit an SM. */
 template <int WPT, bool MASKLO>
-__global__ void __launch_bounds__(kScatThreads, 1) k_part_scatter_owned(OwnedView ov, uint64_t mask, uint32_t own_lo,
+__global__ void __launch_bounds__(kOwnThreads, 2) k_part_scatter_owned(OwnedView ov, uint64_t mask, uint32_t own_lo,
                                                                        uint32_t own_span, int shift,
                                                                        uint32_t fan,
                                                                        const uint64_t *__restrict__ child_off,
@@ -501,18 +509,18 @@ __global__ void __launch_bounds__(kScatThreads, 1) k_part_scatter_owned(OwnedVie
     ScatterSmem &s = *reinterpret_cast<ScatterSmem *>(smem_raw + sizeof(uint64_t) * 2 * kOwnList);
     __shared__ uint32_t n_ovf_s;
     const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    for (uint32_t i = tid; i < fan + 32; i += kScatThreads) s.cur[i] = 0;
+    for (uint32_t i = tid; i < fan + 32; i += kOwnThreads) s.cur[i] = 0;
     if (tid == 0) n_ovf_s = 0;
     __syncthreads();
     const uint32_t fm = fan - 1, mask_lo = (uint32_t)mask;
     const uint64_t n_vitems = ov.vfirst[ov.n_pieces];
-    const uint64_t v0 = (uint64_t)blockIdx.x * ((uint64_t)kScatThreads * WPT);
+    const uint64_t v0 = (uint64_t)blockIdx.x * ((uint64_t)kOwnThreads * WPT);
     uint32_t wcur = 0, kept = 0, side = 0;
     uint64_t pw0[WPT], pw1[WPT];
     int pc[WPT];
 #pragma unroll
     for (int it = 0; it < WPT; ++it) {
-        const uint64_t v = v0 + (uint64_t)it * kScatThreads + tid;
+        const uint64_t v = v0 + (uint64_t)it * kOwnThreads + tid;
         pw0[it] = pw1[it] = 0;
         pc[it] = 0;
         if (v < n_vitems) pc[it] = owned_item(ov, v, pw0[it], pw1[it]);
@@ -546,7 +554,7 @@ __global__ void __launch_bounds__(kScatThreads, 1) k_part_scatter_owned(OwnedVie
                 list[warp * kOwnSeg + p] = x;
             } else {
                 const uint32_t q = atomicAdd(&n_ovf_s, 1u);
-                if (q < (uint32_t)kOwnOvf) list[(kScatThreads / 32) * kOwnSeg + q] = x;
+                if (q < (uint32_t)kOwnOvf) list[(kOwnThreads / 32) * kOwnSeg + q] = x;
             }
             ++p;
         }
@@ -565,8 +573,8 @@ __global__ void __launch_bounds__(kScatThreads, 1) k_part_scatter_owned(OwnedVie
     }
 #pragma unroll
     for (int u = 0; u < kOwnOvfPer; ++u) {
-        const uint32_t idx = (uint32_t)u * kScatThreads + tid;
-        x[kOwnPer + u] = idx < on ? list[(kScatThreads / 32) * kOwnSeg + idx] : kEmpty;
+        const uint32_t idx = (uint32_t)u * kOwnThreads + tid;
+        x[kOwnPer + u] = idx < on ? list[(kOwnThreads / 32) * kOwnSeg + idx] : kEmpty;
     }
 #pragma unroll
     for (int u = 0; u < kOwnRows; ++u) {
@@ -575,16 +583,16 @@ __global__ void __launch_bounds__(kScatThreads, 1) k_part_scatter_owned(OwnedVie
         rk[u >> 1] = (u & 1) ? __byte_perm(rk[u >> 1], r, 0x5410) : r;
     }
     __syncthreads();
-    ScatterClaim cl;
-    const uint32_t total = scatter_plan(s, fan, child_cur, cl);
+    ScatterClaimT<kOwnThreads> cl;
+    const uint32_t total = scatter_plan<kOwnThreads>(s, fan, child_cur, cl);
 #pragma unroll
     for (int u = 0; u < kOwnRows; ++u) {
         const uint32_t r = (u & 1) ? (rk[u >> 1] >> 16) : (rk[u >> 1] & 0xffffu);
         if (x[u] != kEmpty) stage[s.cur[digit_of(part_hash(x[u]), shift, fm)] + r] = x[u];
     }
-    scatter_publish(s, fan, child_off, cl, cap, ctr);
+    scatter_publish<kOwnThreads>(s, fan, child_off, cl, cap, ctr);
     __syncthreads();
-    scatter_flush<kOwnRows>(s, stage, total, shift, fm, out);
+    scatter_flush<kOwnRows, kOwnThreads>(s, stage, total, shift, fm, out);
     kept = warp_sum32(kept);
     side = warp_sum32(side);
     if (lane == 0) {

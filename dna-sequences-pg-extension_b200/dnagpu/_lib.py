@@ -8,7 +8,8 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(os.path.dirname(_HERE), "libdnagpu.so")
+# DNAGPU_LIB names another build of the same library (the -DDNAGPU_TUNING build the profiling scripts use)
+LIB_PATH = os.environ.get("DNAGPU_LIB") or os.path.join(os.path.dirname(_HERE), "libdnagpu.so")
 
 u64 = C.c_uint64
 u64p = C.POINTER(C.c_uint64)

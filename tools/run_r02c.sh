@@ -16,9 +16,16 @@ python bench.py --impl reference --workload c1 --steps 20 --warmup 2 > $O/r02c_b
 L="python bench.py --steps 1 --warmup 3 --e2e-steps 1 --cpu-sample 1000000 --no-extract"
 $L > /dev/null 2>&1 && ncu --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum --clock-control none -c 60 --csv \
     --log-file $O/r02c_c4_launches_dram.csv $L > $O/r02c_ncu_c4.log 2>&1; echo "ncu launches rc=$?" >> $O/r02c_status.txt
-K="python tools/ksweep.py --n-bases 1000000000 --seed 5 --ks 31 --reps 1"
-$K > $O/r02c_ksweep_k31.json 2>&1 && ncu --set full --import-source on --clock-control none -k regex:"k_part_scatter|k_count_buckets_bins" -s 3 -c 3 \
-    -f -o $O/r02c_1gbp_partition $K > $O/r02c_ncu_part.log 2>&1; echo "ncu part rc=$?" >> $O/r02c_status.txt
+# the two scatter kernels at the headline fan-outs (2048 / 1024) on 100 Mbp: the tuning build forces the bucket bits
+export DNAGPU_LIB=$PWD/dna-sequences-pg-extension_b200/libdnagpu_tuning.so
+K="python tools/ksweep.py --n-bases 100000000 --seed 2 --ks 31 --reps 1"
+DNAGPU_BUCKET_BITS=21 $K > $O/r02c_ksweep_fan21.json 2>&1 && DNAGPU_BUCKET_BITS=21 timeout 900 ncu --set full --import-source on --clock-control none \
+    -k regex:"k_part_scatter" -s 2 -c 2 -f -o $O/r02c_fan21_scatter $K > $O/r02c_ncu_part.log 2>&1; echo "ncu scatter rc=$?" >> $O/r02c_status.txt
+unset DNAGPU_LIB
+# the bucket count at its natural bucket size (100 Mbp, k = 21: 2^16 buckets of ~ 1526 keys)
+K="python tools/ksweep.py --n-bases 100000000 --seed 2 --ks 21 --reps 1"
+$K > $O/r02c_ksweep_c2.json 2>&1 && timeout 600 ncu --set full --import-source on --clock-control none -k regex:"k_count_buckets_bins" -s 1 -c 1 \
+    -f -o $O/r02c_c2_count_bins $K > $O/r02c_ncu_count.log 2>&1; echo "ncu count rc=$?" >> $O/r02c_status.txt
 F="python bench.py --workload c3 --n-bases 1500000000 --steps 1 --warmup 3 --e2e-steps 1 --cpu-sample 1000000"
 $F > /dev/null 2>&1 && ncu --set full --import-source on --clock-control none -k regex:"k_filter_collect" -s 3 -c 1 -f -o $O/r02c_c3_filter_sa $F > $O/r02c_ncu_f1.log 2>&1
 $F --planes > /dev/null 2>&1 && ncu --set full --import-source on --clock-control none -k regex:"k_filter_collect" -s 3 -c 1 -f -o $O/r02c_c3_filter_planes $F --planes > $O/r02c_ncu_f2.log 2>&1
