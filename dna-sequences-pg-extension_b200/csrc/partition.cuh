@@ -921,6 +921,43 @@ __device__ __forceinline__ void bins_place(const uint64_t (&x)[kBinPer], const u
     }
 }
 
+/* phase D done by the thread that placed the key (it still holds the key and its rank r): the r slots before
+ * its position are the earlier keys of its bin.  Predicated loads -- r = 0 for ~ 70 % of the keys, so most lanes
+ * of a load instruction are off and cost no shared-memory wavefront -- instead of four coalesced loads per
+ * position by a warp that walks the region; no rank array.  The place phase leaves (position, rank) in f. */
+template <int ROWS>
+__device__ __forceinline__ void bins_place_pos(const uint64_t (&x)[kBinPer], uint32_t (&f)[kBinPer / 2],
+                                               const uint16_t *st, uint64_t *stage)
+{
+#pragma unroll
+    for (int u = 0; u < ROWS; ++u) {
+        const uint32_t v = (u & 1) ? (f[u >> 1] >> 16) : (f[u >> 1] & 0xffffu);
+        const uint32_t pos = st[v & 0xfffu] + (v >> 12);
+        stage[pos] = x[u];
+        const uint32_t pv = (pos & 0xfffu) | (v & 0xf000u);
+        f[u >> 1] = (u & 1) ? __byte_perm(f[u >> 1], pv, 0x5410) : __byte_perm(pv, f[u >> 1], 0x7610);
+    }
+}
+
+template <int ROWS>
+__device__ __forceinline__ void bins_lookback(const uint64_t (&x)[kBinPer], const uint32_t (&f)[kBinPer / 2], uint32_t n,
+                                              uint32_t tid, const uint64_t *stage, uint32_t &repeats, uint32_t &second)
+{
+#pragma unroll
+    for (int u = 0; u < ROWS; ++u) {
+        const uint32_t v = (u & 1) ? (f[u >> 1] >> 16) : (f[u >> 1] & 0xffffu);
+        const uint32_t pos = v & 0xfffu, r = u * kThreads + tid < n ? v >> 12 : 0u; /* a dummy lane looks at nothing */
+        const uint64_t key = x[u];
+        uint32_t e = 0;
+        if (r >= 1) e += stage[pos - 1] == key;
+        if (r >= 2) e += stage[pos - 2] == key;
+        if (r >= 3) e += stage[pos - 3] == key;
+        for (uint32_t j = 4; j <= r; ++j) e += stage[pos - j] == key;
+        repeats += e >= 1;
+        second += e == 1;
+    }
+}
+
 #define BINS_DISPATCH(n, CALL)                                   \
     do {                                                         \
         if ((n) <= 4 * kThreads) { constexpr int ROWS = 4; CALL; } \
@@ -943,7 +980,9 @@ __global__ void __launch_bounds__(kThreads, 4) k_count_buckets_bins(const uint64
     uint64_t *const stage = stage_raw + 4;
     __shared__ __align__(16) uint32_t cnt[kBins + 32];
     __shared__ __align__(16) uint16_t st[kBins + 32];       /* start of the bin in `stage` */
+#ifdef DNAGPU_BINS_WALK
     __shared__ __align__(16) uint8_t rank_at[kBinCap + 48]; /* rank of the key at a stage position inside its bin */
+#endif
     const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     uint32_t repeats = 0, second = 0; /* keys with >= 1 / exactly 1 equal key before them in their bin */
     unsigned long long placed = 0;    /* thread 0: keys of the buckets counted here */
@@ -997,6 +1036,19 @@ __global__ void __launch_bounds__(kThreads, 4) k_count_buckets_bins(const uint64
                 make_uint4(p | ((p + s1) << 16), (p + s2) | ((p + s3) << 16), (p + s4) | ((p + s5) << 16),
                            (p + s6) | ((p + s7) << 16));
             pass_on = __syncthreads_or(bad);
+#ifndef DNAGPU_BINS_WALK
+            if (!pass_on) {
+                /* C: place; f keeps (position, rank) */
+                BINS_DISPATCH(n, bins_place_pos<ROWS>(x, f, st, stage));
+                if (tid == 0) placed += n;
+            }
+            __syncthreads();
+            /* D: every key against the r keys placed before it in its bin, by the thread that holds it */
+            if (!pass_on) BINS_DISPATCH(n, bins_lookback<ROWS>(x, f, n, tid, stage, repeats, second));
+        }
+        if (nn <= kBinCap) BINS_DISPATCH(nn, bins_load<ROWS>(x, keys + nbeg + tid, nn, tid));
+        if (n <= kBinCap) __syncthreads(); /* the stage is rewritten by the next bucket's place phase */
+#else
             if (!pass_on) {
                 /* C: place, and leave the rank beside the key */
                 BINS_DISPATCH(n, bins_place<ROWS>(x, f, st, stage, rank_at));
@@ -1024,6 +1076,7 @@ __global__ void __launch_bounds__(kThreads, 4) k_count_buckets_bins(const uint64
                 }
             }
         }
+#endif
         if (pass_on && tid == 0) list[atomicAdd(list_n, 1ull)] = (uint32_t)b;
         b = nb;
         n = nn;
