@@ -323,13 +323,6 @@ extern "C" int dnagpu_create(dnagpu_ctx **out, int device)
                 per_sm > 0)
                 ctx->bins_ctas_per_sm = per_sm;
         }
-        {
-            const int osmem = 2 * kOwnList * (int)sizeof(uint64_t) + (int)sizeof(ScatterSmem);
-#define OWNED_ATTR(WPT, ML) cudaFuncSetAttribute(k_part_scatter_owned<WPT, ML>, cudaFuncAttributeMaxDynamicSharedMemorySize, osmem)
-            OWNED_ATTR(1, true); OWNED_ATTR(2, true); OWNED_ATTR(4, true);
-            OWNED_ATTR(1, false); OWNED_ATTR(2, false); OWNED_ATTR(4, false);
-#undef OWNED_ATTR
-        }
         cudaFuncSetAttribute(k_sort_scatter<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(SortSmem));
         cudaFuncSetAttribute(k_sort_scatter<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(SortSmem));
         const int bsmem = kBucketSlots * 12;
@@ -1833,6 +1826,24 @@ static int l1_regions_scatter(dnagpu_ctx *ctx, const L1Regions &r, int layout, c
     return DNAGPU_OK;
 }
 
+/* the same from a key list on the device (the owned k-mers of a multi-GPU count, a stored column): 16384-key tiles,
+ * 'G' x 32 keys counted aside, a full region raises C_L1OVF */
+static int l1_regions_scatter_keys(dnagpu_ctx *ctx, Scratch &sc, const L1Regions &r, const uint64_t *d_keys, uint64_t n)
+{
+    uint64_t *root_off, *tiles;
+    TRY(sc.get((void **)&root_off, 2 * 8));
+    ctx->h_ctr[C_COUNT] = 0;
+    ctx->h_ctr[C_COUNT + 1] = n;
+    CU(ctx, cudaMemcpyAsync(root_off, ctx->h_ctr + C_COUNT, 16, cudaMemcpyHostToDevice, ctx->stream));
+    CU(ctx, cudaStreamSynchronize(ctx->stream)); /* pinned staging shared with the counters */
+    TRY(part_tiles(ctx, sc, root_off, root_off + 1, 1, 2 * kTileKeys, &tiles));
+    const int psmem32 = 32 * kScatThreads * (int)sizeof(uint64_t) + (int)sizeof(ScatterSmem);
+    return launch(ctx, "part_scatter", [&] {
+        k_part_scatter_keys<true, 32><<<grid_for(n, 2 * kTileKeys), kScatThreads, psmem32, ctx->stream>>>(
+            d_keys, root_off, root_off + 1, tiles, 1, 1, 64 - r.b1, r.P1, r.beg, r.cur, r.keys, ctx->d_ctr, r.cap, C_L1OVF);
+    });
+}
+
 static int l1_regions_end(dnagpu_ctx *ctx, const L1Regions &r)
 {
     return launch(ctx, "part_tiles", [&] {
@@ -1862,7 +1873,8 @@ static int count_partition(dnagpu_ctx *ctx, const CountInput &in, int k, dnagpu_
                            dnagpu_table **table)
 {
     static const bool no_optimistic = tune_env("DNAGPU_EXACT_LEVEL1") != nullptr;
-    if (in.d_keys || in.filtered || no_optimistic || ctx->force_exact) return count_partition_exact(ctx, in, k, stats, table);
+    if (in.filtered || no_optimistic || ctx->force_exact || (in.d_keys && in.n < (1ull << 24)))
+        return count_partition_exact(ctx, in, k, stats, table);
     {
         Scratch sc(ctx);
         int b1, b2;
@@ -1870,7 +1882,10 @@ static int count_partition(dnagpu_ctx *ctx, const CountInput &in, int k, dnagpu_
         TRY(zero_counters(ctx));
         L1Regions r;
         TRY(l1_regions_begin(ctx, sc, in.n, b1, &r));
-        TRY(l1_regions_scatter(ctx, r, in.seq->layout, in.v, k));
+        if (in.d_keys)
+            TRY(l1_regions_scatter_keys(ctx, sc, r, in.d_keys, in.n));
+        else
+            TRY(l1_regions_scatter(ctx, r, in.seq->layout, in.v, k));
         TRY(l1_regions_end(ctx, r));
         TRY(part_finish(ctx, sc, r.keys, in.n, r.beg, r.end, r.P1, r.P1, b1, b2, k, stats, 0, table));
         if (!ctx->h_ctr[C_L1OVF]) return DNAGPU_OK;
@@ -1997,7 +2012,7 @@ static int count_partition(dnagpu_ctx *ctx, const CountInput &in, int k, dnagpu_
 static int count_listed(dnagpu_ctx *ctx, const uint64_t *keys, uint64_t n_match, int k, const dnagpu_count_opts *opts,
                         dnagpu_stats *stats, dnagpu_table **table);
 
-/* ---- multi-GPU: the k-mers of one owner out of the whole sequence (k_part_scatter_owned) ------------------ */
+/* ---- multi-GPU: the k-mers of one owner out of the whole sequence (k_collect_owned + the key-list count) ----- */
 static int owned_view(dnagpu_ctx *ctx, const dnagpu_seq *seq, int k, OwnedView *ov)
 {
     CHECK_OWNED(ctx, seq, "the sequence");
@@ -2050,87 +2065,55 @@ static int count_owned(dnagpu_ctx *ctx, const dnagpu_seq *seq, int k, const dnag
     const uint64_t n_expect = ov.n_rows / G + 1;
     const uint64_t n_vitems = ov.vfirst[ov.n_pieces];
     const uint64_t mask = kmer_mask(k);
-    const bool exact = (opts->flags & DNAGPU_COUNT_FLAG_EXACT) != 0;
-    if (!exact) {
-        Scratch sc(ctx);
-        int b1, b2;
-        plan_bits(n_expect, 1, &b1, &b2);
-        if (b1 > 8) { /* a tile of the owned scatter is ~ 4096 keys: level 1 takes 8 bits (16-key runs) when level 2 can take the rest */
-            const int b = b1 + b2;
-            b1 = std::max(8, b - 11);
-            b2 = b - b1;
-        }
-        TRY(zero_counters(ctx));
-        L1Regions r;
-        TRY(l1_regions_begin(ctx, sc, n_expect, b1, &r));
-        const int wpt = G >= 8 ? 4 : G >= 4 ? 2 : 1; /* a CTA examines 256 * wpt words and keeps ~ 8192 * wpt / G k-mers */
-        const int smem = 2 * kOwnList * (int)sizeof(uint64_t) + (int)sizeof(ScatterSmem);
-        const unsigned grid = grid_for(n_vitems, (uint64_t)kOwnThreads * wpt);
-#define OWNED_LAUNCH(WPT, ML) \
-    k_part_scatter_owned<WPT, ML><<<grid, kOwnThreads, smem, ctx->stream>>>(ov, mask, own_lo, own_span, 64 - b1, r.P1, r.beg, \
-                                                                             r.cur, r.keys, ctx->d_ctr, r.cap)
-        TRY(launch(ctx, "part_scatter_owned", [&] {
-            if (k < 16) {
-                if (wpt == 4) OWNED_LAUNCH(4, true); else if (wpt == 2) OWNED_LAUNCH(2, true); else OWNED_LAUNCH(1, true);
-            } else {
-                if (wpt == 4) OWNED_LAUNCH(4, false); else if (wpt == 2) OWNED_LAUNCH(2, false); else OWNED_LAUNCH(1, false);
-            }
-        }));
-#undef OWNED_LAUNCH
-        TRY(l1_regions_end(ctx, r));
-        /* level 2 and the count size their grids and regions from the number of keys: the rows this GPU kept,
-         * not the expectation (the owners' shares differ by ~ sqrt(n)) */
-        TRY(fetch_counters(ctx));
-        const uint64_t n_kept = ctx->h_ctr[C_TOTAL] - ctx->h_ctr[C_SIDE];
-        ctx->force_exact = false;
-        if (n_kept == 0 && !ctx->h_ctr[C_L1OVF]) {
-            const uint64_t side = ctx->h_ctr[C_SIDE];
-            stats->total = side;
-            stats->distinct = side > 0;
-            stats->unique = side == 1;
-            if (table) {
-                TRY(table_new(ctx, k, stats->distinct, table));
-                if (side) {
-                    ctx->h_ctr[0] = kEmpty;
-                    ctx->h_ctr[1] = side;
-                    CU(ctx, cudaMemcpyAsync((*table)->d_kmers, &ctx->h_ctr[0], 8, cudaMemcpyHostToDevice, ctx->stream));
-                    CU(ctx, cudaMemcpyAsync((*table)->d_counts, &ctx->h_ctr[1], 8, cudaMemcpyHostToDevice, ctx->stream));
-                    CU(ctx, cudaStreamSynchronize(ctx->stream));
-                }
-            }
-            return DNAGPU_OK;
-        }
-        TRY(part_finish(ctx, sc, r.keys, std::max<uint64_t>(n_kept, 1), r.beg, r.end, r.P1, r.P1, b1, b2, k, stats, 0, table));
-        if (!ctx->h_ctr[C_L1OVF]) return DNAGPU_OK;
-        if (table && *table) {
-            dnagpu_table_free(*table);
-            *table = nullptr;
-        }
-    }
-    /* exact form: the owned k-mers as a key list, then the exact key-list count */
+    /* 1. the owned k-mers as a key list: the staged kernel first, the one that takes any input if a tile's list
+     *    overflowed (or the list ran past its guess: more than the expected share + 1.5 %) */
     Scratch sc(ctx);
-    uint64_t cap = n_expect + n_expect / 4 + 1024, n_own = 0, *keys = nullptr;
-    for (int attempt = 0; attempt < 2; ++attempt) {
+    uint64_t cap = n_expect + n_expect / 64 + 65536, n_own = 0, *keys = nullptr;
+    bool staged = !(opts->flags & DNAGPU_COUNT_FLAG_EXACT);
+    for (int attempt = 0; attempt < 3; ++attempt) {
         TRY(sc.get((void **)&keys, (cap + 2) * 8));
         TRY(zero_counters(ctx));
-        const unsigned grid = (unsigned)std::min<uint64_t>(grid_for(n_vitems, kScatThreads), (uint64_t)ctx->sm_count * 8);
-        TRY(launch(ctx, "collect_owned", [&] {
-            k_collect_owned<<<grid, kScatThreads, 0, ctx->stream>>>(ov, mask, own_lo, own_span, cap, ctx->d_ctr + C_CURSOR, keys);
-        }));
-        TRY(read_u64(ctx, (const uint64_t *)(ctx->d_ctr + C_CURSOR), &n_own));
-        if (n_own <= cap) break;
+        if (staged) {
+            const int wpt = G >= 8 ? 4 : G >= 4 ? 2 : 1; /* a CTA examines 256 * wpt words and keeps ~ 8192 * wpt / G k-mers */
+            const unsigned grid = grid_for(n_vitems, (uint64_t)kOwnThreads * wpt);
+#define OWNED_LAUNCH(WPT, ML) \
+    k_collect_owned<WPT, ML><<<grid, kOwnThreads, 0, ctx->stream>>>(ov, mask, own_lo, own_span, cap, ctx->d_ctr, keys)
+            TRY(launch(ctx, "collect_owned", [&] {
+                if (k < 16) {
+                    if (wpt == 4) OWNED_LAUNCH(4, true); else if (wpt == 2) OWNED_LAUNCH(2, true); else OWNED_LAUNCH(1, true);
+                } else {
+                    if (wpt == 4) OWNED_LAUNCH(4, false); else if (wpt == 2) OWNED_LAUNCH(2, false); else OWNED_LAUNCH(1, false);
+                }
+            }));
+#undef OWNED_LAUNCH
+        } else {
+            const unsigned grid = (unsigned)std::min<uint64_t>(grid_for(n_vitems, kScatThreads), (uint64_t)ctx->sm_count * 8);
+            TRY(launch(ctx, "collect_owned", [&] {
+                k_collect_owned_any<<<grid, kScatThreads, 0, ctx->stream>>>(ov, mask, own_lo, own_span, cap, ctx->d_ctr + C_CURSOR, keys);
+            }));
+        }
+        TRY(fetch_counters(ctx));
+        n_own = ctx->h_ctr[C_CURSOR];
+        const bool dropped = staged && ctx->h_ctr[C_L1OVF];
+        if (!dropped && n_own <= cap) break;
+        if (attempt == 2) return fail(ctx, DNAGPU_EINTERNAL, "the owned k-mers could not be collected");
         sc.release(keys);
         dfree(ctx, keys);
-        cap = n_own;
+        if (dropped) staged = false;   /* the cursor missed what was dropped: size the retry generously */
+        cap = dropped ? std::max(cap, n_own + n_own / 2 + 65536) : n_own;
     }
     if (n_own == 0) {
         if (table) TRY(table_new(ctx, k, 0, table));
         return DNAGPU_OK;
     }
+    /* 2. the single-GPU pipeline over the list (optimistic level 1 from keys, level 2, bucket count) */
     dnagpu_count_opts o2 = *opts;
     o2.owner_parts = o2.owner_part = 0;
     o2.method = DNAGPU_COUNT_AUTO;
-    return count_listed(ctx, keys, n_own, k, &o2, stats, table);
+    ctx->force_exact = (opts->flags & DNAGPU_COUNT_FLAG_EXACT) != 0;
+    const int rc = count_listed(ctx, keys, n_own, k, &o2, stats, table);
+    ctx->force_exact = false;
+    return rc;
 }
 
 /* GROUP BY over a key list on the device (what a WHERE clause kept) */

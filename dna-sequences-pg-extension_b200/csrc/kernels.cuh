@@ -65,7 +65,7 @@ __host__ __device__ __forceinline__ uint64_t mix64(uint64_t x)
 }
 /* Owner rank of a k-mer among n_parts GPUs: a multiplicative hash of the k-mer's low word (its first 16
  * bases; the whole k-mer for k <= 16), top bits -> rank.  One IMAD per start position, because the
- * multi-GPU count tests EVERY start position of the sequence for ownership (k_part_scatter_owned) and
+ * multi-GPU count tests EVERY start position of the sequence for ownership (k_collect_owned) and
  * keeps one in n_parts.  Independent of the partition digits (64-bit multiply-shift over the whole
  * k-mer) and of the bucket / bin hashes (fold of both words, another multiplier). */
 constexpr uint32_t kOwnerMul = 0x85EBCA6Bu;

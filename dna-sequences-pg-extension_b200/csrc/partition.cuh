@@ -376,7 +376,7 @@ __global__ void __launch_bounds__(kScatThreads, (PER == 16 ? 2 : 1)) k_part_scat
                                                                        unsigned long long *__restrict__ child_cur,
                                                                        uint64_t *__restrict__ out,
                                                                        unsigned long long *__restrict__ ctr,
-                                                                       uint64_t cap = 0)
+                                                                       uint64_t cap = 0, int full_flag = C_L2OVF)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     uint64_t *stage = reinterpret_cast<uint64_t *>(smem_raw);
@@ -416,7 +416,7 @@ __global__ void __launch_bounds__(kScatThreads, (PER == 16 ? 2 : 1)) k_part_scat
         const uint32_t pos = (s.cur[d] + r) & (TILE - 1);
         if (d != fan) stage[pos] = x[u];
     }
-    scatter_publish(s, fan, child_off + (parent % n_groups) * fan, cl, cap, ctr, C_L2OVF);
+    scatter_publish(s, fan, child_off + (parent % n_groups) * fan, cl, cap, ctr, full_flag);
     __syncthreads();
     scatter_flush<PER>(s, stage, total, shift, fm, out);
     if (COUNT_SIDE) {
@@ -429,28 +429,26 @@ __global__ void __launch_bounds__(kScatThreads, (PER == 16 ? 2 : 1)) k_part_scat
     }
 }
 
-/* ---- multi-GPU level 1: every GPU reads the WHOLE sequence and keeps the k-mers it owns ---------------
+/* ---- multi-GPU: every GPU reads the WHOLE sequence and keeps the k-mers it owns ------------------------
  * The sequence is resident as base-range shards, one per GPU, each with its (k-1)-base overlap and each
  * mapped into every GPU's address space (peer memory over NVLink).  What crosses NVLink is the 2-bit
  * packed bases (0.25 B per start position) instead of 8-byte k-mers: GPU g walks all pieces -- its own
  * first, the others in ring order so that no shard is read by everybody at once -- tests every start
- * position for owner_of(kmer) == g with one IMAD on the window's low word, and scatters the ones it keeps
- * exactly like the single-GPU level 1 (optimistic regions, one run per (tile, digit)).  There is no
- * exchange step and nothing to merge: level 2 and the bucket count then run on local data only.
+ * position for owner_of(kmer) == g with one IMAD on the window's low word, and appends the k-mers it keeps
+ * to a key list in its own HBM (k_collect_owned).  From there the single-GPU pipeline runs unchanged on
+ * local data: optimistic level 1 from the key list, level 2, bucket count.  There is no exchange step
+ * and nothing to merge.
  *
- * A CTA examines 256 * wpt packed words (wpt = n_parts / 2, so that it keeps ~ 4096 k-mers).  Kept k-mers
- * are appended to a shared-memory list -- a compact segment per warp, filled through a warp scan of the
- * per-word keep masks, plus a small shared overflow area -- and then read back lane-strided, so the rank /
- * place / flush phases work on balanced, statically indexed register arrays. */
+ * A CTA of 256 threads examines 256 * WPT packed words (WPT = n_parts / 2, so that it keeps ~ 4096 k-mers).
+ * The keep masks of a word go through a warp scan into a compact per-warp segment of a shared-memory
+ * list (+ a shared overflow area); the CTA then claims its range of the global list with ONE atomic and
+ * copies the segments out coalesced.  40 KB of shared memory and few registers: five CTAs per SM, which
+ * is what hides the microseconds a peer-memory load takes. */
 constexpr int kMaxPieces = 16;
-constexpr int kOwnThreads = 256;                               /* two CTAs per SM: one's scan (ALU) under the other's scatter (L1) */
-constexpr int kOwnSeg = 576;                                   /* list slots of one warp (mean 512, sigma ~ 21) */
-constexpr int kOwnPer = kOwnSeg / 32;                          /* 18 keys per lane from the warp's segment      */
-constexpr int kOwnOvf = 512;                                   /* shared overflow slots                         */
-constexpr int kOwnOvfPer = kOwnOvf / kOwnThreads;              /* 2 per thread                                  */
-constexpr int kOwnList = (kOwnThreads / 32) * kOwnSeg + kOwnOvf; /* 5120 keys                                   */
-constexpr int kOwnRows = kOwnPer + kOwnOvfPer;                 /* keys one thread ranks and places              */
-constexpr uint32_t kOwnMaxFan = 1024;                          /* cur[fan .. fan + 31] are the per-lane dummies */
+constexpr int kOwnThreads = 256;
+constexpr int kOwnSeg = 576;                                     /* list slots of one warp (mean 512, sigma ~ 21) */
+constexpr int kOwnOvf = 512;                                     /* shared overflow slots                         */
+constexpr int kOwnList = (kOwnThreads / 32) * kOwnSeg + kOwnOvf; /* 5120 keys                                     */
 
 struct OwnedView {
     const uint64_t *ptr[kMaxPieces];  /* first packed word of piece i (local or peer-mapped)                      */
@@ -491,41 +489,34 @@ __device__ __forceinline__ int owned_item(const OwnedView &ov, uint64_t v, uint6
     return left < 32 ? (int)left : 32;
 }
 
-/* WPT packed words per thread (n_parts / 2, so that a CTA of 256 threads keeps ~ 4096 k-mers); all of them are
- * loaded before the first is looked at (a peer-memory load takes microseconds).  Two CTAs fit an SM. */
+/* The owned k-mers of the sequence as a key list (unordered).  `cursor` ends at the number of owned rows even
+ * when tiles past `cap` wrote nothing; a tile whose shared-memory list overflowed (a long run of one k-mer owned
+ * by this GPU) raises C_L1OVF: the caller then uses k_collect_owned_any. */
 template <int WPT, bool MASKLO>
-__global__ void __launch_bounds__(kOwnThreads, 2) k_part_scatter_owned(OwnedView ov, uint64_t mask, uint32_t own_lo,
-                                                                       uint32_t own_span, int shift,
-                                                                       uint32_t fan,
-                                                                       const uint64_t *__restrict__ child_off,
-                                                                       unsigned long long *__restrict__ child_cur,
-                                                                       uint64_t *__restrict__ out,
-                                                                       unsigned long long *__restrict__ ctr,
-                                                                       uint64_t cap)
+__global__ void __launch_bounds__(kOwnThreads) k_collect_owned(OwnedView ov, uint64_t mask, uint32_t own_lo,
+                                                               uint32_t own_span, uint64_t cap,
+                                                               unsigned long long *__restrict__ ctr,
+                                                               uint64_t *__restrict__ out)
 {
-    extern __shared__ __align__(16) unsigned char smem_raw[];
-    uint64_t *list = reinterpret_cast<uint64_t *>(smem_raw);
-    uint64_t *stage = list + kOwnList;
-    ScatterSmem &s = *reinterpret_cast<ScatterSmem *>(smem_raw + sizeof(uint64_t) * 2 * kOwnList);
-    __shared__ uint32_t n_ovf_s;
+    __shared__ __align__(16) uint64_t list[kOwnList];
+    __shared__ uint32_t n_ovf_s, wtot_s[kOwnThreads / 32];
+    __shared__ unsigned long long base_s;
     const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    for (uint32_t i = tid; i < fan + 32; i += kOwnThreads) s.cur[i] = 0;
     if (tid == 0) n_ovf_s = 0;
     __syncthreads();
-    const uint32_t fm = fan - 1, mask_lo = (uint32_t)mask;
+    const uint32_t mask_lo = (uint32_t)mask;
     const uint64_t n_vitems = ov.vfirst[ov.n_pieces];
     const uint64_t v0 = (uint64_t)blockIdx.x * ((uint64_t)kOwnThreads * WPT);
-    uint32_t wcur = 0, kept = 0, side = 0;
+    uint32_t wcur = 0;
     uint64_t pw0[WPT], pw1[WPT];
     int pc[WPT];
 #pragma unroll
-    for (int it = 0; it < WPT; ++it) {
+    for (int it = 0; it < WPT; ++it) { /* all loads first */
         const uint64_t v = v0 + (uint64_t)it * kOwnThreads + tid;
         pw0[it] = pw1[it] = 0;
         pc[it] = 0;
         if (v < n_vitems) pc[it] = owned_item(ov, v, pw0[it], pw1[it]);
     }
-    /* phase 1: keep masks, warp scan, append */
 #pragma unroll
     for (int it = 0; it < WPT; ++it) {
         const uint64_t w0 = pw0[it], w1 = pw1[it];
@@ -544,12 +535,10 @@ __global__ void __launch_bounds__(kOwnThreads, 2) k_part_scatter_owned(OwnedView
         }
         uint32_t p = wcur + inc - n;
         wcur += __shfl_sync(0xffffffffu, inc, 31);
-        kept += n;
         while (km) {
             const int j = __ffs(km) - 1;
             km &= km - 1;
             const uint64_t x = window(w0, w1, 2 * j) & mask;
-            side += x == kEmpty; /* 'G' x 32 (k = 32): stays in the list as a slot that is not scattered */
             if (p < (uint32_t)kOwnSeg) {
                 list[warp * kOwnSeg + p] = x;
             } else {
@@ -559,56 +548,34 @@ __global__ void __launch_bounds__(kOwnThreads, 2) k_part_scatter_owned(OwnedView
             ++p;
         }
     }
+    const uint32_t wn = min(wcur, (uint32_t)kOwnSeg);
+    if (lane == 0) wtot_s[warp] = wn;
     __syncthreads();
-    const uint32_t n_ovf = n_ovf_s;
-    if (n_ovf > (uint32_t)kOwnOvf && tid == 0) atomicExch(&ctr[C_L1OVF], 1ull); /* keys were dropped: the caller redoes exactly */
-    const uint32_t wn = min(wcur, (uint32_t)kOwnSeg), on = min(n_ovf, (uint32_t)kOwnOvf);
-    /* phase 2: balanced read-back, then rank / plan / place / flush as in the local scatter */
-    uint64_t x[kOwnRows];
-    uint32_t rk[kOwnRows / 2];
+    const uint32_t n_ovf = n_ovf_s, on = min(n_ovf, (uint32_t)kOwnOvf);
+    uint32_t before = 0, total = on;
 #pragma unroll
-    for (int u = 0; u < kOwnPer; ++u) {
-        const uint32_t idx = (uint32_t)u * 32 + lane;
-        x[u] = idx < wn ? list[warp * kOwnSeg + idx] : kEmpty;
+    for (int i = 0; i < kOwnThreads / 32; ++i) {
+        const uint32_t t = wtot_s[i];
+        if (i < (int)warp) before += t;
+        total += t;
     }
-#pragma unroll
-    for (int u = 0; u < kOwnOvfPer; ++u) {
-        const uint32_t idx = (uint32_t)u * kOwnThreads + tid;
-        x[kOwnPer + u] = idx < on ? list[(kOwnThreads / 32) * kOwnSeg + idx] : kEmpty;
-    }
-#pragma unroll
-    for (int u = 0; u < kOwnRows; ++u) {
-        const uint32_t d = x[u] != kEmpty ? digit_of(part_hash(x[u]), shift, fm) : fan + lane;
-        const uint32_t r = atomicAdd(&s.cur[d], 1u);
-        rk[u >> 1] = (u & 1) ? __byte_perm(rk[u >> 1], r, 0x5410) : r;
+    if (tid == 0) {
+        if (n_ovf > (uint32_t)kOwnOvf) atomicExch(&ctr[C_L1OVF], 1ull); /* keys were dropped */
+        base_s = total ? atomicAdd(&ctr[C_CURSOR], (unsigned long long)total) : 0ull;
     }
     __syncthreads();
-    ScatterClaimT<kOwnThreads> cl;
-    const uint32_t total = scatter_plan<kOwnThreads>(s, fan, child_cur, cl);
-#pragma unroll
-    for (int u = 0; u < kOwnRows; ++u) {
-        const uint32_t r = (u & 1) ? (rk[u >> 1] >> 16) : (rk[u >> 1] & 0xffffu);
-        if (x[u] != kEmpty) stage[s.cur[digit_of(part_hash(x[u]), shift, fm)] + r] = x[u];
-    }
-    scatter_publish<kOwnThreads>(s, fan, child_off, cl, cap, ctr);
-    __syncthreads();
-    scatter_flush<kOwnRows, kOwnThreads>(s, stage, total, shift, fm, out);
-    kept = warp_sum32(kept);
-    side = warp_sum32(side);
-    if (lane == 0) {
-        if (kept) atomicAdd(&ctr[C_TOTAL], (unsigned long long)kept);
-        if (side) atomicAdd(&ctr[C_SIDE], (unsigned long long)side);
-    }
+    if (total == 0 || base_s + total > cap) return; /* uniform */
+    uint64_t *dst = out + base_s;
+    for (uint32_t q = lane; q < wn; q += 32) dst[before + q] = list[warp * kOwnSeg + q];
+    for (uint32_t q = tid; q < on; q += kOwnThreads) dst[total - on + q] = list[(kOwnThreads / 32) * kOwnSeg + q];
 }
 
-/* The exact fallback of the owned count (a region or a list overflowed: heavily repeated input): the owned
- * k-mers as a plain key list, appended warp by warp through one cursor; tiles past `cap` write nothing but
- * still count, so the caller can retry with a buffer of the right size.  The list is then counted by the
- * exact key-list path. */
-__global__ void __launch_bounds__(kScatThreads) k_collect_owned(OwnedView ov, uint64_t mask, uint32_t own_lo,
-                                                                uint32_t own_span, uint64_t cap,
-                                                                unsigned long long *__restrict__ cursor,
-                                                                uint64_t *__restrict__ out)
+/* The same list for ANY input (the exact fallback: heavily repeated sequences): appended warp by warp through the
+ * cursor, nothing staged, nothing dropped. */
+__global__ void __launch_bounds__(kScatThreads) k_collect_owned_any(OwnedView ov, uint64_t mask, uint32_t own_lo,
+                                                                    uint32_t own_span, uint64_t cap,
+                                                                    unsigned long long *__restrict__ cursor,
+                                                                    uint64_t *__restrict__ out)
 {
     const uint32_t lane = threadIdx.x & 31;
     const uint64_t n_vitems = ov.vfirst[ov.n_pieces];

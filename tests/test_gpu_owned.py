@@ -126,3 +126,24 @@ def test_pieces_argument_errors(gpu):
     with pytest.raises(dnagpu.DnaError):
         gpu.count(seq, 21, owner=(2, 2))
     seq.free()
+
+
+def test_count_keys_of_a_large_list_takes_the_optimistic_level_1(gpu):
+    """dnagpu_count_keys on >= 2^24 keys: fixed regions + one scatter from the list (what every GPU of a multi-GPU
+    count runs on the k-mers it kept), against the oracle; a skewed list falls back to the exact form."""
+    n, k, seed = 40_000_000, 31, 5
+    words = R.synth_seq(seed, n)
+    want = R.count_query_big(words, 1, n, words.size, k, threads=8)
+    seq = gpu.synth(n, seed)
+    keys = gpu.extract(seq, k)
+    st, table = gpu.count_keys(keys, k, table=True)
+    assert (st.total, st.distinct, st.unique) == want.stats
+    a, b = table.fetch()
+    assert np.array_equal(R.pairs_digest(a, b), want.digest)
+    table.free()
+    skew = keys.clone()
+    skew[: n // 2] = keys[12345]                      # 20 M copies of one k-mer
+    st, _ = gpu.count_keys(skew, k)
+    u, c = np.unique(skew.cpu().numpy().view(np.uint64), return_counts=True)
+    assert (st.total, st.distinct, st.unique) == (int(c.sum()), int(u.size), int((c == 1).sum()))
+    seq.free()

@@ -4,7 +4,7 @@
 # keeps the earlier forms, then ncu of the new forms.
 cd "$(dirname "$0")/.."
 O=gpurun_out
-timeout 1200 python -m pytest tests -m gpu -q --maxfail=10 -p no:cacheprovider > $O/r02e_pytest.log 2>&1; echo "pytest rc=$?" > $O/r02e_status.txt
+timeout 1500 python -m pytest tests -m gpu -q --maxfail=10 -p no:cacheprovider > $O/r02e_pytest.log 2>&1; echo "pytest rc=$?" > $O/r02e_status.txt
 T=$PWD/dna-sequences-pg-extension_b200/libdnagpu_tuning.so
 B="python bench.py --cpu-sample 1000000 --no-extract --e2e-steps 2"
 for w in c4 c3 c2; do
