@@ -266,10 +266,13 @@ def run_reference(args):
 
 
 # ================================= our arm =====================================
-# static SASS instructions of one item (32 start positions) of the fused WHERE scan, per start position
-# (cuobjdump -sass of k_filter_collect<kFixed>: 936 instructions per item incl. staging; profiles/r02_sass_hot_kernels.txt);
-# replaced by the executed-instruction count of an ncu capture when profiles/issue.json holds one
-ISSUE_INSTR_PER_POSITION = {"filter_collect": 936 / 32.0, "filter_count": 936 / 32.0}
+# Executed SASS instructions per start position of the kernels that read 0.25 B/base and test EVERY position (issue-bound,
+# not HBM-bound).  Defaults: the plane test from an ncu capture (profiles/r02c_c3_filter_planes_summary.csv: 7.34e8 warp
+# instructions for 1.2e9 positions = 19.6), the Shift-And scan and the ownership scan from their SASS listings
+# (profiles/r02_sass_hot_kernels.txt); profiles/issue.json overrides them with ncu counts of the current build.
+# Integer SASS runs on two pipes of HALF the issue rate each (ALU: LOP3 / SHF / IADD3 / ISETP, FMA: IMAD): a kernel that is
+# mostly ALU-pipe instructions saturates at frac ~ 0.5 of the issue peak.
+ISSUE_INSTR_PER_POSITION = {"filter_collect": 9.5, "filter_count": 9.5, "filter_collect:planes": 19.6, "collect_owned": 7.4}
 
 
 def issue_table():
@@ -581,17 +584,16 @@ def run_b200(args):
         rows_tested_r = n_rows_total / world   # start positions one rank's predicate scan tests
         base_b = 8.0 * n_words_local       # the packed words one launch reads (0.25 B/base)
         listed = "filter_collect" in kernels and kernels["filter_collect"]["launches"] > 0
-        from_keys = world > 1 or listed    # level 1 reads a key list (8 B/key) instead of packed words
+        l1_from_list = listed or gather    # level 1 reads a key list (8 B/key) instead of packed words
         ALG = {
             "count_hash": base_b + 16.0 * rows_r, "count_hash_keys": 8.0 * rows_r + 16.0 * rows_r,
             "count_dense": base_b + 4.0 * rows_r, "count_dense_smem": base_b,
             # exact level 1 (N > 1 routed forms, WHERE clause): histogram over the packed words or the key list
             "part_hist": 8.0 * rows_r if listed else base_b,
-            "part_scatter": (8.0 * rows_r if from_keys and listed else base_b) + 8.0 * rows_r,
+            "part_scatter": (8.0 * rows_r if l1_from_list else base_b) + 8.0 * rows_r,
             # level 1 fused with the exchange: packed words in, 8 B per k-mer out (local or over NVLink)
             "part_scatter_peer": (8.0 * rows_r if listed else base_b) + 8.0 * rows_r,
             # gather form: EVERY base of the sequence is read (all shards), the owned k-mers are written
-            "part_scatter_owned": 8.0 * n_words_total + 8.0 * rows_r,
             "collect_owned": 8.0 * n_words_total + 8.0 * rows_r,
             # a WHERE clause is evaluated once into a key list: packed words in, matching rows out
             "filter_collect": base_b + 8.0 * rows_r,
@@ -599,6 +601,9 @@ def run_b200(args):
             "partition_count": base_b, "partition_write": base_b + 8.0 * rows_r,
         }
         issue = issue_table()
+        if args.planes:
+            issue["filter_collect"] = issue["filter_collect:planes"]
+        issue = {q: v for q, v in issue.items() if ":" not in q}
         clk_hz = 1e6 * float((clocks or {}).get("sm_mhz") or 1965.0)
         issue_peak = SM_COUNT * LANES_PER_SM * clk_hz / 1e12  # T lane-instructions / s
         timed = {n: v for n, v in kernels.items() if n in ALG and v["launches"]}
@@ -606,10 +611,11 @@ def run_b200(args):
         def kernel_roofline(name, v):
             per_ms = v["ms"] / v["launches"]
             if name in issue:  # 0.25 B/base in, every start position tested: instruction issue is the bound
-                ach = issue[name] * rows_tested_r / per_ms / 1e9
+                positions = n_rows_total if name == "collect_owned" else rows_tested_r  # every GPU tests every position
+                ach = issue[name] * positions / per_ms / 1e9
                 return {"bound": "issue", "ms_per_launch": per_ms, "achieved": ach, "peak": issue_peak,
                         "unit": "T lane-instr/s", "frac": ach / issue_peak,
-                        "instructions_per_position": issue[name], "positions_per_launch": rows_tested_r,
+                        "instructions_per_position": issue[name], "positions_per_launch": positions,
                         "hbm_gbs": ALG[name] / per_ms / 1e6, "hbm_frac": ALG[name] / per_ms / 1e6 / peak}
             return {"bound": "hbm", "ms_per_launch": per_ms, "achieved": ALG[name] / per_ms / 1e6, "peak": peak,
                     "unit": "GB/s", "frac": ALG[name] / per_ms / 1e6 / peak}
@@ -640,12 +646,12 @@ def run_b200(args):
                                                    "hbm_frac")})
             if gather:  # bases read from the other GPUs' shards, per step and rank, against the NVLink peer rate
                 nv = 8.0 * (n_words_total - n_words_local)
-                own = timed.get("part_scatter_owned")
+                own = timed.get("collect_owned")
                 if own:
                     per = own["ms"] / own["launches"]
                     roofline["nvlink"] = {"bytes_per_launch": nv, "achieved": nv / per / 1e6, "peak": NVLINK_PEER_GBS,
                                           "unit": "GB/s", "frac": nv / per / 1e6 / NVLINK_PEER_GBS,
-                                          "note": "2-bit packed bases read through peer memory inside part_scatter_owned; "
+                                          "note": "2-bit packed bases read through peer memory inside collect_owned; "
                                                   "routing 8-byte k-mers instead would move 8*(G-1)/G B per k-mer"}
         cpu, one = cpu_baselines(n_bases, k, seed, reads, args.cpu_sample, 1_000_000)
         par = {"gather": "base-range shards (one per GPU, (k-1)-base overlap) mapped into every GPU; each GPU reads all "

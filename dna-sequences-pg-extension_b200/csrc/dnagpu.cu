@@ -305,14 +305,14 @@ extern "C" int dnagpu_create(dnagpu_ctx **out, int device)
         {
             const int psmem32 = 32 * kScatThreads * (int)sizeof(uint64_t) + (int)sizeof(ScatterSmem);
 #define PSMEM32_ATTR(kern) cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, psmem32)
-            PSMEM32_ATTR((k_part_scatter_keys<false, 32>));
-            PSMEM32_ATTR((k_part_scatter_keys<true, 32>));
-            PSMEM32_ATTR((k_part_scatter_seq<kSingle, false, 32>));
-            PSMEM32_ATTR((k_part_scatter_seq<kSingle, true, 32>));
-            PSMEM32_ATTR((k_part_scatter_seq<kFixed, false, 32>));
-            PSMEM32_ATTR((k_part_scatter_seq<kFixed, true, 32>));
-            PSMEM32_ATTR((k_part_scatter_seq<kRagged, false, 32>));
-            PSMEM32_ATTR((k_part_scatter_seq<kRagged, true, 32>));
+            PSMEM32_ATTR((k_part_scatter_keys<false, kBigPer, kBigThreads>));
+            PSMEM32_ATTR((k_part_scatter_keys<true, kBigPer, kBigThreads>));
+            PSMEM32_ATTR((k_part_scatter_seq<kSingle, false, kBigPer, kBigThreads>));
+            PSMEM32_ATTR((k_part_scatter_seq<kSingle, true, kBigPer, kBigThreads>));
+            PSMEM32_ATTR((k_part_scatter_seq<kFixed, false, kBigPer, kBigThreads>));
+            PSMEM32_ATTR((k_part_scatter_seq<kFixed, true, kBigPer, kBigThreads>));
+            PSMEM32_ATTR((k_part_scatter_seq<kRagged, false, kBigPer, kBigThreads>));
+            PSMEM32_ATTR((k_part_scatter_seq<kRagged, true, kBigPer, kBigThreads>));
 #undef PSMEM32_ATTR
         }
         PSMEM_ATTR(k_part_scatter_keys<true>);
@@ -1579,10 +1579,10 @@ static int part_level1(dnagpu_ctx *ctx, Scratch &sc, const CountInput &in, int k
             const unsigned grid = grid_for(in.v.n_items, kScatThreads);
             DISPATCH_LAYOUT(in.seq->layout, TRY(launch(ctx, "part_scatter", [&] {
                 if (in.filtered)
-                    k_part_scatter_seq<LY, true, 32><<<grid, kScatThreads, psmem32, ctx->stream>>>(
+                    k_part_scatter_seq<LY, true, kBigPer, kBigThreads><<<grid, kBigThreads, psmem32, ctx->stream>>>(
                         in.v, in.p, mask, shift1, P1, off1, cur1, out, ctx->d_ctr, 0);
                 else
-                    k_part_scatter_seq<LY, false, 32><<<grid, kScatThreads, psmem32, ctx->stream>>>(
+                    k_part_scatter_seq<LY, false, kBigPer, kBigThreads><<<grid, kBigThreads, psmem32, ctx->stream>>>(
                         in.v, in.p, mask, shift1, P1, off1, cur1, out, ctx->d_ctr, 0);
             })));
         } else {
@@ -1654,7 +1654,7 @@ static int part_finish_impl(dnagpu_ctx *ctx, Scratch &sc, const uint64_t *keys, 
         TRY(launch(ctx, "part_scatter2", [&] {
             if (per32) {
                 const int psmem32 = 32 * kScatThreads * (int)sizeof(uint64_t) + (int)sizeof(ScatterSmem);
-                k_part_scatter_keys<false, 32><<<grid_for(n, 2 * kTileKeys) + (unsigned)n_parents, kScatThreads, psmem32,
+                k_part_scatter_keys<false, kBigPer, kBigThreads><<<grid_for(n, 2 * kTileKeys) + (unsigned)n_parents, kBigThreads, psmem32,
                                                  ctx->stream>>>(keys, parent_off, parent_end, tiles_scat, n_parents, n_groups,
                                                                 shift2, P2, off2, cur2, bufB, ctx->d_ctr, cap);
             } else {
@@ -1812,7 +1812,7 @@ static int l1_regions_scatter(dnagpu_ctx *ctx, const L1Regions &r, int layout, c
         const int psmem = 32 * kScatThreads * (int)sizeof(uint64_t) + (int)sizeof(ScatterSmem);
         const unsigned grid = grid_for(v.n_items, kScatThreads);
         DISPATCH_LAYOUT(layout, TRY(launch(ctx, "part_scatter", [&] {
-            k_part_scatter_seq<LY, false, 32><<<grid, kScatThreads, psmem, ctx->stream>>>(
+            k_part_scatter_seq<LY, false, kBigPer, kBigThreads><<<grid, kBigThreads, psmem, ctx->stream>>>(
                 v, none, kmer_mask(k), 64 - r.b1, r.P1, r.beg, r.cur, r.keys, ctx->d_ctr, r.cap);
         })));
         return DNAGPU_OK;
@@ -1839,7 +1839,7 @@ static int l1_regions_scatter_keys(dnagpu_ctx *ctx, Scratch &sc, const L1Regions
     TRY(part_tiles(ctx, sc, root_off, root_off + 1, 1, 2 * kTileKeys, &tiles));
     const int psmem32 = 32 * kScatThreads * (int)sizeof(uint64_t) + (int)sizeof(ScatterSmem);
     return launch(ctx, "part_scatter", [&] {
-        k_part_scatter_keys<true, 32><<<grid_for(n, 2 * kTileKeys), kScatThreads, psmem32, ctx->stream>>>(
+        k_part_scatter_keys<true, kBigPer, kBigThreads><<<grid_for(n, 2 * kTileKeys), kBigThreads, psmem32, ctx->stream>>>(
             d_keys, root_off, root_off + 1, tiles, 1, 1, 64 - r.b1, r.P1, r.beg, r.cur, r.keys, ctx->d_ctr, r.cap, C_L1OVF);
     });
 }
@@ -2823,10 +2823,10 @@ extern "C" int dnagpu_shuffle_scatter_to(dnagpu_ctx *ctx, const dnagpu_seq *seq,
     const unsigned grid = grid_for(in.v.n_items, kScatThreads);
     DISPATCH_LAYOUT(seq->layout, TRY(launch(ctx, "part_scatter_peer", [&] {
         if (in.filtered)
-            k_part_scatter_seq<LY, true, 32><<<grid, kScatThreads, psmem, ctx->stream>>>(
+            k_part_scatter_seq<LY, true, kBigPer, kBigThreads><<<grid, kBigThreads, psmem, ctx->stream>>>(
                 in.v, in.p, mask, shift1, P1, d_idx, cur1, (uint64_t *)nullptr, ctx->d_ctr, 0);
         else
-            k_part_scatter_seq<LY, false, 32><<<grid, kScatThreads, psmem, ctx->stream>>>(
+            k_part_scatter_seq<LY, false, kBigPer, kBigThreads><<<grid, kBigThreads, psmem, ctx->stream>>>(
                 in.v, in.p, mask, shift1, P1, d_idx, cur1, (uint64_t *)nullptr, ctx->d_ctr, 0);
     })));
     TRY(fetch_counters(ctx)); /* synchronises: every store of this rank has been issued and retired */
@@ -2896,7 +2896,7 @@ extern "C" int dnagpu_shuffle_scatter_keys_to(dnagpu_ctx *ctx, const uint64_t *d
     TRY(zero_counters(ctx));
     const int psmem32 = 32 * kScatThreads * (int)sizeof(uint64_t) + (int)sizeof(ScatterSmem);
     TRY(launch(ctx, "part_scatter_peer", [&] {
-        k_part_scatter_keys<true, 32><<<grid_for(n, 2 * kTileKeys), kScatThreads, psmem32, ctx->stream>>>(
+        k_part_scatter_keys<true, kBigPer, kBigThreads><<<grid_for(n, 2 * kTileKeys), kBigThreads, psmem32, ctx->stream>>>(
             d_keys, root_off, root_off + 1, tiles, 1, 1, 64 - plan->bits1, P1, d_idx, cur1, (uint64_t *)nullptr, ctx->d_ctr);
     }));
     TRY(fetch_counters(ctx)); /* synchronises: every store of this rank has been issued and retired */

@@ -489,7 +489,7 @@ __global__ void __launch_bounds__(kThreads) k_filter_collect(SeqView sv, Pred p,
  * warm-up: a 150-base read is exactly one run.  End-position matches are turned into start-position masks
  * by one 160-bit funnel shift by k-1, after which rank / stage / store work as in the plane form. */
 constexpr int kSaItems = 4;
-constexpr int kSaStage = 8192; /* staged matches per round (64 KB) */
+constexpr int kSaStage = 2048; /* staged matches per round (16 KB: five CTAs per SM; a selective clause needs one round) */
 
 struct SaPred {
     uint32_t m[4]; /* M[A], M[T], M[C], M[G], left-aligned */
@@ -616,7 +616,7 @@ __global__ void __launch_bounds__(kThreads) k_filter_sa(SeqView sv, SaPred sp, u
     __syncthreads();
     if (total == 0 || (MODE == kSaCollect && base_s + total > cap)) return; /* uniform; the cursor still counts what did not fit */
     uint64_t *dst = out + base_s;
-    for (uint32_t round = 0; round < total; round += kSaStage) { /* one round unless > 8192 rows of the tile match */
+    for (uint32_t round = 0; round < total; round += kSaStage) { /* one round unless > 2048 rows of the tile match */
         uint32_t rank = rank0;
 #pragma unroll
         for (int i = 0; i < kSaItems; ++i) {

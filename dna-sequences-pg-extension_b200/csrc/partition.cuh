@@ -35,6 +35,14 @@ constexpr int kScatPer = 16;
 constexpr int kTileKeys = kScatThreads * kScatPer; /* 8192 keys staged per scatter tile (64 KB) */
 constexpr int kSuperTile = kTileKeys * 8;  /* keys per CTA in a histogram pass              */
 constexpr int kMaxFan = 2048;              /* partitions per level                          */
+/* the 16384-key tile (one CTA per SM): 1024 threads x 16 keys -- 32 warps instead of 16 to cover the latency of the
+ * shared-memory atomics and of the dependent shifts (ncu r02c: short-scoreboard and wait stalls at 25 % occupancy);
+ * -DDNAGPU_SCATTER_512 keeps the earlier 512 x 32 form for A/B */
+#ifdef DNAGPU_SCATTER_512
+constexpr int kBigPer = 32, kBigThreads = 512;
+#else
+constexpr int kBigPer = 16, kBigThreads = 1024;
+#endif
 #ifndef DNAGPU_BUCKET_SLOTS
 #define DNAGPU_BUCKET_SLOTS 4096
 #endif
@@ -159,7 +167,7 @@ __global__ void __launch_bounds__(kThreads) k_part_hist_keys(const uint64_t *__r
  * gdelta[d] turns a stage position into the global output index. */
 struct ScatterSmem {
     uint32_t cur[kMaxFan + 1]; /* cur[fan] = dummy bin of the keys that are not scattered */
-    uint32_t warp_tot[kScatThreads / 32 + 1];
+    uint32_t warp_tot[1024 / 32 + 1];
     long long gdelta[kMaxFan];
 };
 
@@ -268,8 +276,8 @@ __device__ __forceinline__ void scatter_flush(const ScatterSmem &s, const uint64
  * Straight-line code: a key that is not scattered (past the end, rejected by the WHERE
  * clause, or the k = 32 sentinel) is ranked into the dummy bin cur[fan] and its stores
  * are predicated off, so the unrolled loops carry no branches. */
-template <int L, bool FILTER, int PER = kScatPer>
-__global__ void __launch_bounds__(kScatThreads, (PER == 16 ? 2 : 1)) k_part_scatter_seq(SeqView sv, Pred p, uint64_t mask, int shift,
+template <int L, bool FILTER, int PER = kScatPer, int THREADS = kScatThreads>
+__global__ void __launch_bounds__(THREADS, (PER * THREADS == 8192 ? 2 : 1)) k_part_scatter_seq(SeqView sv, Pred p, uint64_t mask, int shift,
                                                                       uint32_t fan,
                                                                       const uint64_t *__restrict__ child_off,
                                                                       unsigned long long *__restrict__ child_cur,
@@ -279,7 +287,7 @@ __global__ void __launch_bounds__(kScatThreads, (PER == 16 ? 2 : 1)) k_part_scat
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     uint64_t *stage = reinterpret_cast<uint64_t *>(smem_raw);
-    ScatterSmem &s = *reinterpret_cast<ScatterSmem *>(smem_raw + sizeof(uint64_t) * (PER * kScatThreads));
+    ScatterSmem &s = *reinterpret_cast<ScatterSmem *>(smem_raw + sizeof(uint64_t) * (PER * THREADS));
 #ifdef DNAGPU_PHASE_TIMING
     long long tq[6];
     tq[0] = clock64();
@@ -287,12 +295,12 @@ __global__ void __launch_bounds__(kScatThreads, (PER == 16 ? 2 : 1)) k_part_scat
 #else
 #define PHASE_MARK(i)
 #endif
-    for (uint32_t i = threadIdx.x; i <= fan; i += kScatThreads) s.cur[i] = 0;
+    for (uint32_t i = threadIdx.x; i <= fan; i += THREADS) s.cur[i] = 0;
     __syncthreads();
     const uint32_t fm = fan - 1;
     constexpr int SPLIT = 32 / PER; /* threads sharing one packed word */
-    constexpr uint32_t TILE = PER * kScatThreads;
-    const uint64_t t = (uint64_t)blockIdx.x * (kScatThreads / SPLIT) + (threadIdx.x / SPLIT);
+    constexpr uint32_t TILE = PER * THREADS;
+    const uint64_t t = (uint64_t)blockIdx.x * (THREADS / SPLIT) + (threadIdx.x / SPLIT);
     const int half = threadIdx.x % SPLIT;
     uint64_t a0 = 0, a1 = 0; /* the PER windows of this thread start at bit 0 of a0 */
     int c = 0;
@@ -328,8 +336,8 @@ __global__ void __launch_bounds__(kScatThreads, (PER == 16 ? 2 : 1)) k_part_scat
     PHASE_MARK(1);
     __syncthreads();
     PHASE_MARK(2);
-    ScatterClaim cl;
-    const uint32_t total = scatter_plan(s, fan, child_cur, cl);
+    ScatterClaimT<THREADS> cl;
+    const uint32_t total = scatter_plan<THREADS>(s, fan, child_cur, cl);
     PHASE_MARK(3);
     {
         uint64_t cur = a0, nxt = a1;
@@ -344,10 +352,10 @@ __global__ void __launch_bounds__(kScatThreads, (PER == 16 ? 2 : 1)) k_part_scat
             nxt >>= 2;
         }
     }
-    scatter_publish(s, fan, child_off, cl, cap, ctr);
+    scatter_publish<THREADS>(s, fan, child_off, cl, cap, ctr);
     __syncthreads();
     PHASE_MARK(4);
-    scatter_flush<PER>(s, stage, total, shift, fm, out);
+    scatter_flush<PER, THREADS>(s, stage, total, shift, fm, out);
     PHASE_MARK(5);
 #ifdef DNAGPU_PHASE_TIMING
     if (threadIdx.x == 0) {
@@ -365,8 +373,8 @@ __global__ void __launch_bounds__(kScatThreads, (PER == 16 ? 2 : 1)) k_part_scat
 
 /* scatter the keys of every parent partition into its children: out[child_off[parent*fan+d] ...].
  * COUNT_SIDE: first level over a raw key list (the caller's keys may hold 'G' x 32). */
-template <bool COUNT_SIDE, int PER = kScatPer>
-__global__ void __launch_bounds__(kScatThreads, (PER == 16 ? 2 : 1)) k_part_scatter_keys(const uint64_t *__restrict__ keys,
+template <bool COUNT_SIDE, int PER = kScatPer, int THREADS = kScatThreads>
+__global__ void __launch_bounds__(THREADS, (PER * THREADS == 8192 ? 2 : 1)) k_part_scatter_keys(const uint64_t *__restrict__ keys,
                                                                        const uint64_t *__restrict__ parent_off,
                                                                        const uint64_t *__restrict__ parent_end,
                                                                        const uint64_t *__restrict__ tile_off,
@@ -380,10 +388,10 @@ __global__ void __launch_bounds__(kScatThreads, (PER == 16 ? 2 : 1)) k_part_scat
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     uint64_t *stage = reinterpret_cast<uint64_t *>(smem_raw);
-    ScatterSmem &s = *reinterpret_cast<ScatterSmem *>(smem_raw + sizeof(uint64_t) * (PER * kScatThreads));
-    constexpr uint32_t TILE = PER * kScatThreads;
+    ScatterSmem &s = *reinterpret_cast<ScatterSmem *>(smem_raw + sizeof(uint64_t) * (PER * THREADS));
+    constexpr uint32_t TILE = PER * THREADS;
     if (blockIdx.x >= tile_off[n_parents]) return; /* the grid is an upper bound on the tiles */
-    for (uint32_t i = threadIdx.x; i <= fan; i += kScatThreads) s.cur[i] = 0;
+    for (uint32_t i = threadIdx.x; i <= fan; i += THREADS) s.cur[i] = 0;
     __syncthreads();
     uint64_t parent, beg, end;
     tile_range(parent_off, parent_end, tile_off, n_parents, TILE, parent, beg, end);
@@ -393,7 +401,7 @@ __global__ void __launch_bounds__(kScatThreads, (PER == 16 ? 2 : 1)) k_part_scat
     uint32_t side = 0, kept = 0;
 #pragma unroll
     for (int u = 0; u < PER; ++u) {
-        uint64_t i = beg + (uint64_t)u * kScatThreads + threadIdx.x;
+        uint64_t i = beg + (uint64_t)u * THREADS + threadIdx.x;
         x[u] = i < end ? ld_nc(keys + i) : kEmpty;
         if (COUNT_SIDE) {
             kept += (i < end);
@@ -407,8 +415,8 @@ __global__ void __launch_bounds__(kScatThreads, (PER == 16 ? 2 : 1)) k_part_scat
         rk[u >> 1] = (u & 1) ? __byte_perm(rk[u >> 1], r, 0x5410) : r;
     }
     __syncthreads();
-    ScatterClaim cl;
-    const uint32_t total = scatter_plan(s, fan, child_cur + (parent % n_groups) * fan, cl);
+    ScatterClaimT<THREADS> cl;
+    const uint32_t total = scatter_plan<THREADS>(s, fan, child_cur + (parent % n_groups) * fan, cl);
 #pragma unroll
     for (int u = 0; u < PER; ++u) {
         const uint32_t r = (u & 1) ? (rk[u >> 1] >> 16) : (rk[u >> 1] & 0xffffu);
@@ -416,9 +424,9 @@ __global__ void __launch_bounds__(kScatThreads, (PER == 16 ? 2 : 1)) k_part_scat
         const uint32_t pos = (s.cur[d] + r) & (TILE - 1);
         if (d != fan) stage[pos] = x[u];
     }
-    scatter_publish(s, fan, child_off + (parent % n_groups) * fan, cl, cap, ctr, full_flag);
+    scatter_publish<THREADS>(s, fan, child_off + (parent % n_groups) * fan, cl, cap, ctr, full_flag);
     __syncthreads();
-    scatter_flush<PER>(s, stage, total, shift, fm, out);
+    scatter_flush<PER, THREADS>(s, stage, total, shift, fm, out);
     if (COUNT_SIDE) {
         kept = warp_sum32(kept);
         side = warp_sum32(side);
@@ -888,43 +896,6 @@ __device__ __forceinline__ void bins_place(const uint64_t (&x)[kBinPer], const u
     }
 }
 
-/* phase D done by the thread that placed the key (it still holds the key and its rank r): the r slots before
- * its position are the earlier keys of its bin.  Predicated loads -- r = 0 for ~ 70 % of the keys, so most lanes
- * of a load instruction are off and cost no shared-memory wavefront -- instead of four coalesced loads per
- * position by a warp that walks the region; no rank array.  The place phase leaves (position, rank) in f. */
-template <int ROWS>
-__device__ __forceinline__ void bins_place_pos(const uint64_t (&x)[kBinPer], uint32_t (&f)[kBinPer / 2],
-                                               const uint16_t *st, uint64_t *stage)
-{
-#pragma unroll
-    for (int u = 0; u < ROWS; ++u) {
-        const uint32_t v = (u & 1) ? (f[u >> 1] >> 16) : (f[u >> 1] & 0xffffu);
-        const uint32_t pos = st[v & 0xfffu] + (v >> 12);
-        stage[pos] = x[u];
-        const uint32_t pv = (pos & 0xfffu) | (v & 0xf000u);
-        f[u >> 1] = (u & 1) ? __byte_perm(f[u >> 1], pv, 0x5410) : __byte_perm(pv, f[u >> 1], 0x7610);
-    }
-}
-
-template <int ROWS>
-__device__ __forceinline__ void bins_lookback(const uint64_t (&x)[kBinPer], const uint32_t (&f)[kBinPer / 2], uint32_t n,
-                                              uint32_t tid, const uint64_t *stage, uint32_t &repeats, uint32_t &second)
-{
-#pragma unroll
-    for (int u = 0; u < ROWS; ++u) {
-        const uint32_t v = (u & 1) ? (f[u >> 1] >> 16) : (f[u >> 1] & 0xffffu);
-        const uint32_t pos = v & 0xfffu, r = u * kThreads + tid < n ? v >> 12 : 0u; /* a dummy lane looks at nothing */
-        const uint64_t key = x[u];
-        uint32_t e = 0;
-        if (r >= 1) e += stage[pos - 1] == key;
-        if (r >= 2) e += stage[pos - 2] == key;
-        if (r >= 3) e += stage[pos - 3] == key;
-        for (uint32_t j = 4; j <= r; ++j) e += stage[pos - j] == key;
-        repeats += e >= 1;
-        second += e == 1;
-    }
-}
-
 #define BINS_DISPATCH(n, CALL)                                   \
     do {                                                         \
         if ((n) <= 4 * kThreads) { constexpr int ROWS = 4; CALL; } \
@@ -947,9 +918,7 @@ __global__ void __launch_bounds__(kThreads, 4) k_count_buckets_bins(const uint64
     uint64_t *const stage = stage_raw + 4;
     __shared__ __align__(16) uint32_t cnt[kBins + 32];
     __shared__ __align__(16) uint16_t st[kBins + 32];       /* start of the bin in `stage` */
-#ifdef DNAGPU_BINS_WALK
     __shared__ __align__(16) uint8_t rank_at[kBinCap + 48]; /* rank of the key at a stage position inside its bin */
-#endif
     const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     uint32_t repeats = 0, second = 0; /* keys with >= 1 / exactly 1 equal key before them in their bin */
     unsigned long long placed = 0;    /* thread 0: keys of the buckets counted here */
@@ -1003,19 +972,6 @@ __global__ void __launch_bounds__(kThreads, 4) k_count_buckets_bins(const uint64
                 make_uint4(p | ((p + s1) << 16), (p + s2) | ((p + s3) << 16), (p + s4) | ((p + s5) << 16),
                            (p + s6) | ((p + s7) << 16));
             pass_on = __syncthreads_or(bad);
-#ifndef DNAGPU_BINS_WALK
-            if (!pass_on) {
-                /* C: place; f keeps (position, rank) */
-                BINS_DISPATCH(n, bins_place_pos<ROWS>(x, f, st, stage));
-                if (tid == 0) placed += n;
-            }
-            __syncthreads();
-            /* D: every key against the r keys placed before it in its bin, by the thread that holds it */
-            if (!pass_on) BINS_DISPATCH(n, bins_lookback<ROWS>(x, f, n, tid, stage, repeats, second));
-        }
-        if (nn <= kBinCap) BINS_DISPATCH(nn, bins_load<ROWS>(x, keys + nbeg + tid, nn, tid));
-        if (n <= kBinCap) __syncthreads(); /* the stage is rewritten by the next bucket's place phase */
-#else
             if (!pass_on) {
                 /* C: place, and leave the rank beside the key */
                 BINS_DISPATCH(n, bins_place<ROWS>(x, f, st, stage, rank_at));
@@ -1043,7 +999,6 @@ __global__ void __launch_bounds__(kThreads, 4) k_count_buckets_bins(const uint64
                 }
             }
         }
-#endif
         if (pass_on && tid == 0) list[atomicAdd(list_n, 1ull)] = (uint32_t)b;
         b = nb;
         n = nn;

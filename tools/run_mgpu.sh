@@ -17,6 +17,10 @@ run_bench() { # n exchange tag [extra args]
 run_bench $NG gather gather
 [ $NG -ge 8 ] && run_bench 4 gather gather
 [ $NG -ge 4 ] && run_bench 2 gather gather
+# reads + WHERE (configs[2]) on all GPUs: every rank evaluates the clause on its reads (Shift-And), the rows that pass are routed
+timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node $NG --master-addr 127.0.0.1 --master-port 29531 \
+    bench.py --gpus $NG --workload c3 --steps 10 --warmup 3 --e2e-steps 2 --cpu-sample 1000000 \
+    2> $O/${TAG}_bench_c3_n${NG}.err | grep '^{' > $O/${TAG}_bench_c3_n${NG}.json; echo "bench c3 n=$NG rc=${PIPESTATUS[0]}" >> $O/${TAG}_status.txt
 for g in $NG 4 2 1; do
   [ $g -le $NG ] && timeout 300 ./dna-sequences-pg-extension_b200/dnagpu_bench --bases 3100000000 --k 31 --seed 4 --steps 5 --host --gpus $g \
       > $O/${TAG}_cbench_n$g.json 2>> $O/${TAG}_cbench.err
@@ -25,7 +29,7 @@ timeout 900 python -m pytest tests/test_gpu_multi.py tests/test_gpu_owned.py -m 
 cat $O/${TAG}_status.txt; tail -3 $O/${TAG}_pytest.log
 python - <<'PY'
 import json, glob, os
-for f in sorted(glob.glob("gpurun_out/" + os.environ.get("TAG", "r02g") + "_bench_c4_*.json")):
+for f in sorted(glob.glob("gpurun_out/" + os.environ.get("TAG", "r02g") + "_bench_c[34]_*.json")):
     try:
         d=json.load(open(f))
         print(f.split("/")[-1], "value", round(d["value"],1), "ms", round(d["ms_per_step"],2), "e2e", round(d["e2e"]["value"],1), {k:round(v["ms"]/v["launches"],2) for k,v in d["kernels"].items() if v["ms"]/v["launches"]>0.05})
