@@ -305,8 +305,8 @@ extern "C" int dnagpu_create(dnagpu_ctx **out, int device)
         {
             const int psmem32 = 32 * kScatThreads * (int)sizeof(uint64_t) + (int)sizeof(ScatterSmem);
 #define PSMEM32_ATTR(kern) cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, psmem32)
-            PSMEM32_ATTR((k_part_scatter_keys<false, kBigPer, kBigThreads>));
-            PSMEM32_ATTR((k_part_scatter_keys<true, kBigPer, kBigThreads>));
+            PSMEM32_ATTR((k_part_scatter_keys<false, kBigPerKeys, kBigThreadsKeys>));
+            PSMEM32_ATTR((k_part_scatter_keys<true, kBigPerKeys, kBigThreadsKeys>));
             PSMEM32_ATTR((k_part_scatter_seq<kSingle, false, kBigPer, kBigThreads>));
             PSMEM32_ATTR((k_part_scatter_seq<kSingle, true, kBigPer, kBigThreads>));
             PSMEM32_ATTR((k_part_scatter_seq<kFixed, false, kBigPer, kBigThreads>));
@@ -1488,8 +1488,10 @@ static int bucket_bits(uint64_t n)
 
 /* tile prefix sums of a partitioned key array: out_tile_off[n_parents + 1] */
 static int part_tiles(dnagpu_ctx *ctx, Scratch &sc, const uint64_t *parent_off, const uint64_t *parent_end,
-                      uint64_t n_parents, uint64_t tile_keys, uint64_t **out_tile_off)
+                      uint64_t n_parents, uint64_t tile_keys, uint64_t **out_tile_off, uint32_t **out_tile_parent = nullptr,
+                      uint64_t max_tiles = 0)
 {
+    if (out_tile_parent) *out_tile_parent = nullptr;
     uint64_t *tiles;
     TRY(sc.get((void **)&tiles, (n_parents + 1) * 8));
     TRY(sc.get((void **)out_tile_off, (n_parents + 1) * 8));
@@ -1497,7 +1499,15 @@ static int part_tiles(dnagpu_ctx *ctx, Scratch &sc, const uint64_t *parent_off, 
         k_part_tiles<<<grid_for(n_parents, kThreads), kThreads, 0, ctx->stream>>>(parent_off, parent_end, n_parents,
                                                                                 tile_keys, tiles);
     }));
-    return scan_any(ctx, sc, tiles, n_parents, *out_tile_off);
+    TRY(scan_any(ctx, sc, tiles, n_parents, *out_tile_off));
+    if (out_tile_parent && n_parents > 1) { /* tile -> parent map for the CTAs (max_tiles = the grid of the consumer) */
+        TRY(sc.get((void **)out_tile_parent, (max_tiles + 1) * 4));
+        TRY(launch(ctx, "part_tiles", [&] {
+            k_tile_parents<<<grid_for(n_parents, kThreads), kThreads, 0, ctx->stream>>>(*out_tile_off, n_parents, max_tiles,
+                                                                                      *out_tile_parent);
+        }));
+    }
+    return DNAGPU_OK;
 }
 
 /* ---- GROUP BY kmer by radix partition + shared-memory count (partition.cuh) -------------------- */
@@ -1619,6 +1629,7 @@ static int part_finish_impl(dnagpu_ctx *ctx, Scratch &sc, const uint64_t *keys, 
         n_buckets = n_groups * P2;
         unsigned long long *hist2 = nullptr, *cur2;
         uint64_t *off2, *end2 = nullptr, *tiles_hist = nullptr, *tiles_scat, *bufB;
+        uint32_t *tparent_hist = nullptr, *tparent_scat = nullptr;
         /* Optimistic level 2 (like level 1): hashing spreads a parent's keys evenly over its children, so every
          * bucket gets a fixed region of mean + 7 sigma and the histogram pass is skipped; a run that finds its
          * region full flags C_L2OVF and part_finish redoes level 2 with the exact histogram + scan. */
@@ -1637,16 +1648,18 @@ static int part_finish_impl(dnagpu_ctx *ctx, Scratch &sc, const uint64_t *keys, 
             TRY(sc.get((void **)&hist2, n_buckets * 8));
             TRY(sc.get((void **)&bufB, (n + 2) * 8));
             CU(ctx, cudaMemsetAsync(hist2, 0, n_buckets * 8, ctx->stream));
-            TRY(part_tiles(ctx, sc, parent_off, parent_end, n_parents, kSuperTile, &tiles_hist));
+            TRY(part_tiles(ctx, sc, parent_off, parent_end, n_parents, kSuperTile, &tiles_hist, &tparent_hist,
+                           (uint64_t)grid_for(n, kSuperTile) + n_parents));
         }
         /* measured on the headline workload: at a fan-out of 2048 a (tile, digit) run of an 8192-key tile
          * is only 4 keys; 16384-key tiles (one CTA per SM) win 13 % there, are even at 1024 and lose 10 % at 256 */
         const bool per32 = scatter_tile32(P2, 2);
-        TRY(part_tiles(ctx, sc, parent_off, parent_end, n_parents, per32 ? 2 * kTileKeys : kTileKeys, &tiles_scat));
+        TRY(part_tiles(ctx, sc, parent_off, parent_end, n_parents, per32 ? 2 * kTileKeys : kTileKeys, &tiles_scat, &tparent_scat,
+                       (uint64_t)grid_for(n, per32 ? 2 * kTileKeys : kTileKeys) + n_parents));
         if (!optimistic2) {
             TRY(launch(ctx, "part_hist2", [&] {
                 k_part_hist_keys<<<grid_for(n, kSuperTile) + (unsigned)n_parents, kThreads, 0, ctx->stream>>>(
-                    keys, parent_off, parent_end, tiles_hist, n_parents, n_groups, shift2, P2, hist2);
+                    keys, parent_off, parent_end, tiles_hist, n_parents, n_groups, shift2, P2, hist2, tparent_hist);
             }));
             TRY(scan_any(ctx, sc, (const uint64_t *)hist2, n_buckets, off2));
         }
@@ -1654,13 +1667,14 @@ static int part_finish_impl(dnagpu_ctx *ctx, Scratch &sc, const uint64_t *keys, 
         TRY(launch(ctx, "part_scatter2", [&] {
             if (per32) {
                 const int psmem32 = 32 * kScatThreads * (int)sizeof(uint64_t) + (int)sizeof(ScatterSmem);
-                k_part_scatter_keys<false, kBigPer, kBigThreads><<<grid_for(n, 2 * kTileKeys) + (unsigned)n_parents, kBigThreads, psmem32,
+                k_part_scatter_keys<false, kBigPerKeys, kBigThreadsKeys><<<grid_for(n, 2 * kTileKeys) + (unsigned)n_parents, kBigThreadsKeys, psmem32,
                                                  ctx->stream>>>(keys, parent_off, parent_end, tiles_scat, n_parents, n_groups,
-                                                                shift2, P2, off2, cur2, bufB, ctx->d_ctr, cap);
+                                                                shift2, P2, off2, cur2, bufB, ctx->d_ctr, cap, C_L2OVF,
+                                                                tparent_scat);
             } else {
                 k_part_scatter_keys<false><<<grid_for(n, kTileKeys) + (unsigned)n_parents, kScatThreads, psmem, ctx->stream>>>(
                     keys, parent_off, parent_end, tiles_scat, n_parents, n_groups, shift2, P2, off2, cur2, bufB, ctx->d_ctr,
-                    cap);
+                    cap, C_L2OVF, tparent_scat);
             }
         }));
         bucket_keys = bufB;
@@ -1839,7 +1853,7 @@ static int l1_regions_scatter_keys(dnagpu_ctx *ctx, Scratch &sc, const L1Regions
     TRY(part_tiles(ctx, sc, root_off, root_off + 1, 1, 2 * kTileKeys, &tiles));
     const int psmem32 = 32 * kScatThreads * (int)sizeof(uint64_t) + (int)sizeof(ScatterSmem);
     return launch(ctx, "part_scatter", [&] {
-        k_part_scatter_keys<true, kBigPer, kBigThreads><<<grid_for(n, 2 * kTileKeys), kBigThreads, psmem32, ctx->stream>>>(
+        k_part_scatter_keys<true, kBigPerKeys, kBigThreadsKeys><<<grid_for(n, 2 * kTileKeys), kBigThreadsKeys, psmem32, ctx->stream>>>(
             d_keys, root_off, root_off + 1, tiles, 1, 1, 64 - r.b1, r.P1, r.beg, r.cur, r.keys, ctx->d_ctr, r.cap, C_L1OVF);
     });
 }
@@ -2896,7 +2910,7 @@ extern "C" int dnagpu_shuffle_scatter_keys_to(dnagpu_ctx *ctx, const uint64_t *d
     TRY(zero_counters(ctx));
     const int psmem32 = 32 * kScatThreads * (int)sizeof(uint64_t) + (int)sizeof(ScatterSmem);
     TRY(launch(ctx, "part_scatter_peer", [&] {
-        k_part_scatter_keys<true, kBigPer, kBigThreads><<<grid_for(n, 2 * kTileKeys), kBigThreads, psmem32, ctx->stream>>>(
+        k_part_scatter_keys<true, kBigPerKeys, kBigThreadsKeys><<<grid_for(n, 2 * kTileKeys), kBigThreadsKeys, psmem32, ctx->stream>>>(
             d_keys, root_off, root_off + 1, tiles, 1, 1, 64 - plan->bits1, P1, d_idx, cur1, (uint64_t *)nullptr, ctx->d_ctr);
     }));
     TRY(fetch_counters(ctx)); /* synchronises: every store of this rank has been issued and retired */

@@ -35,14 +35,12 @@ constexpr int kScatPer = 16;
 constexpr int kTileKeys = kScatThreads * kScatPer; /* 8192 keys staged per scatter tile (64 KB) */
 constexpr int kSuperTile = kTileKeys * 8;  /* keys per CTA in a histogram pass              */
 constexpr int kMaxFan = 2048;              /* partitions per level                          */
-/* the 16384-key tile (one CTA per SM): 1024 threads x 16 keys -- 32 warps instead of 16 to cover the latency of the
- * shared-memory atomics and of the dependent shifts (ncu r02c: short-scoreboard and wait stalls at 25 % occupancy);
- * -DDNAGPU_SCATTER_512 keeps the earlier 512 x 32 form for A/B */
-#ifdef DNAGPU_SCATTER_512
-constexpr int kBigPer = 32, kBigThreads = 512;
-#else
-constexpr int kBigPer = 16, kBigThreads = 1024;
-#endif
+/* the 16384-key tile (one CTA per SM).  From packed words (level 1): 1024 threads x 16 keys -- 32 warps instead of 16
+ * to cover the latency of the shared-memory atomics and of the dependent shifts (ncu r02c: short-scoreboard and wait
+ * stalls at 25 % occupancy; r02h: 16.96 -> 15.75 ms on the headline workload).  From a key list (level 2): 512 x 32,
+ * which measured 2.5 % faster there than 1024 x 16 (17.46 vs 17.90 ms). */
+constexpr int kBigPer = 16, kBigThreads = 1024;        /* k_part_scatter_seq  */
+constexpr int kBigPerKeys = 32, kBigThreadsKeys = 512; /* k_part_scatter_keys */
 #ifndef DNAGPU_BUCKET_SLOTS
 #define DNAGPU_BUCKET_SLOTS 4096
 #endif
@@ -73,11 +71,24 @@ __global__ void __launch_bounds__(kThreads) k_part_tiles(const uint64_t *__restr
 
 /* CTA -> (parent partition, key range).  A partition is keys[parent_beg[p] .. parent_end[p]): exact
  * layouts pass (off, off + 1), the optimistic level 1 passes region starts and fill marks. */
+/* tile -> parent map: a CTA that had to find its parent by binary search over tile_off spent ten DEPENDENT global
+ * loads (~ 1.5 us, with nothing else resident on the SM to cover them) before its first key: ncu r02c put 14 % of the
+ * instructions and 21 % of the stall samples of the level-2 scatter there */
+__global__ void __launch_bounds__(kThreads) k_tile_parents(const uint64_t *__restrict__ tile_off, uint64_t n_parents,
+                                                           uint64_t max_tiles, uint32_t *__restrict__ tile_parent)
+{
+    const uint64_t p = (uint64_t)blockIdx.x * kThreads + threadIdx.x;
+    if (p >= n_parents) return;
+    const uint64_t t1 = min(tile_off[p + 1], max_tiles);
+    for (uint64_t t = tile_off[p]; t < t1; ++t) tile_parent[t] = (uint32_t)p;
+}
+
 __device__ __forceinline__ void tile_range(const uint64_t *parent_beg, const uint64_t *parent_end,
                                            const uint64_t *tile_off, uint64_t n_parents, uint64_t tile_keys,
-                                           uint64_t &parent, uint64_t &beg, uint64_t &end)
+                                           uint64_t &parent, uint64_t &beg, uint64_t &end,
+                                           const uint32_t *tile_parent = nullptr)
 {
-    parent = n_parents == 1 ? 0 : upper_seq(tile_off, n_parents, blockIdx.x);
+    parent = n_parents == 1 ? 0 : tile_parent ? (uint64_t)tile_parent[blockIdx.x] : upper_seq(tile_off, n_parents, blockIdx.x);
     uint64_t t = blockIdx.x - tile_off[parent];
     beg = parent_beg[parent] + t * tile_keys;
     end = min(beg + tile_keys, parent_end[parent]);
@@ -135,14 +146,15 @@ __global__ void __launch_bounds__(kThreads) k_part_hist_keys(const uint64_t *__r
                                                              const uint64_t *__restrict__ tile_off,
                                                              uint64_t n_parents, uint64_t n_groups, int shift,
                                                              uint32_t fan,
-                                                             unsigned long long *__restrict__ hist)
+                                                             unsigned long long *__restrict__ hist,
+                                                             const uint32_t *__restrict__ tile_parent = nullptr)
 {
     __shared__ uint32_t h[kMaxFan];
     if (blockIdx.x >= tile_off[n_parents]) return; /* the grid is an upper bound on the tiles */
     for (uint32_t i = threadIdx.x; i < fan; i += kThreads) h[i] = 0;
     __syncthreads();
     uint64_t parent, beg, end;
-    tile_range(parent_off, parent_end, tile_off, n_parents, kSuperTile, parent, beg, end);
+    tile_range(parent_off, parent_end, tile_off, n_parents, kSuperTile, parent, beg, end, tile_parent);
     const uint32_t fm = fan - 1;
     for (uint64_t base = beg; base < end; base += kThreads * 8) {
         uint64_t x[8];
@@ -384,7 +396,8 @@ __global__ void __launch_bounds__(THREADS, (PER * THREADS == 8192 ? 2 : 1)) k_pa
                                                                        unsigned long long *__restrict__ child_cur,
                                                                        uint64_t *__restrict__ out,
                                                                        unsigned long long *__restrict__ ctr,
-                                                                       uint64_t cap = 0, int full_flag = C_L2OVF)
+                                                                       uint64_t cap = 0, int full_flag = C_L2OVF,
+                                                                       const uint32_t *__restrict__ tile_parent = nullptr)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     uint64_t *stage = reinterpret_cast<uint64_t *>(smem_raw);
@@ -394,7 +407,7 @@ __global__ void __launch_bounds__(THREADS, (PER * THREADS == 8192 ? 2 : 1)) k_pa
     for (uint32_t i = threadIdx.x; i <= fan; i += THREADS) s.cur[i] = 0;
     __syncthreads();
     uint64_t parent, beg, end;
-    tile_range(parent_off, parent_end, tile_off, n_parents, TILE, parent, beg, end);
+    tile_range(parent_off, parent_end, tile_off, n_parents, TILE, parent, beg, end, tile_parent);
     const uint32_t fm = fan - 1;
     uint64_t x[PER];
     uint32_t rk[PER / 2]; /* two 16-bit ranks per register; the digit is recomputed */
