@@ -1488,10 +1488,10 @@ static int bucket_bits(uint64_t n)
 
 /* tile prefix sums of a partitioned key array: out_tile_off[n_parents + 1] */
 static int part_tiles(dnagpu_ctx *ctx, Scratch &sc, const uint64_t *parent_off, const uint64_t *parent_end,
-                      uint64_t n_parents, uint64_t tile_keys, uint64_t **out_tile_off, uint32_t **out_tile_parent = nullptr,
+                      uint64_t n_parents, uint64_t tile_keys, uint64_t **out_tile_off, TileInfo **out_tile_table = nullptr,
                       uint64_t max_tiles = 0)
 {
-    if (out_tile_parent) *out_tile_parent = nullptr;
+    if (out_tile_table) *out_tile_table = nullptr;
     uint64_t *tiles;
     TRY(sc.get((void **)&tiles, (n_parents + 1) * 8));
     TRY(sc.get((void **)out_tile_off, (n_parents + 1) * 8));
@@ -1500,11 +1500,12 @@ static int part_tiles(dnagpu_ctx *ctx, Scratch &sc, const uint64_t *parent_off, 
                                                                                 tile_keys, tiles);
     }));
     TRY(scan_any(ctx, sc, tiles, n_parents, *out_tile_off));
-    if (out_tile_parent && n_parents > 1) { /* tile -> parent map for the CTAs (max_tiles = the grid of the consumer) */
-        TRY(sc.get((void **)out_tile_parent, (max_tiles + 1) * 4));
+    if (out_tile_table && n_parents > 1) { /* one 16-byte entry per CTA of the consumer (max_tiles = its grid) */
+        TRY(sc.get((void **)out_tile_table, (max_tiles + 1) * sizeof(TileInfo)));
+        CU(ctx, cudaMemsetAsync(*out_tile_table, 0, (max_tiles + 1) * sizeof(TileInfo), ctx->stream));
         TRY(launch(ctx, "part_tiles", [&] {
-            k_tile_parents<<<grid_for(n_parents, kThreads), kThreads, 0, ctx->stream>>>(*out_tile_off, n_parents, max_tiles,
-                                                                                      *out_tile_parent);
+            k_tile_table<<<grid_for(n_parents, kThreads), kThreads, 0, ctx->stream>>>(parent_off, parent_end, *out_tile_off, n_parents,
+                                                                                    tile_keys, max_tiles, *out_tile_table);
         }));
     }
     return DNAGPU_OK;
@@ -1629,7 +1630,7 @@ static int part_finish_impl(dnagpu_ctx *ctx, Scratch &sc, const uint64_t *keys, 
         n_buckets = n_groups * P2;
         unsigned long long *hist2 = nullptr, *cur2;
         uint64_t *off2, *end2 = nullptr, *tiles_hist = nullptr, *tiles_scat, *bufB;
-        uint32_t *tparent_hist = nullptr, *tparent_scat = nullptr;
+        TileInfo *tparent_hist = nullptr, *tparent_scat = nullptr;
         /* Optimistic level 2 (like level 1): hashing spreads a parent's keys evenly over its children, so every
          * bucket gets a fixed region of mean + 7 sigma and the histogram pass is skipped; a run that finds its
          * region full flags C_L2OVF and part_finish redoes level 2 with the exact histogram + scan. */

@@ -71,27 +71,53 @@ __global__ void __launch_bounds__(kThreads) k_part_tiles(const uint64_t *__restr
 
 /* CTA -> (parent partition, key range).  A partition is keys[parent_beg[p] .. parent_end[p]): exact
  * layouts pass (off, off + 1), the optimistic level 1 passes region starts and fill marks. */
-/* tile -> parent map: a CTA that had to find its parent by binary search over tile_off spent ten DEPENDENT global
- * loads (~ 1.5 us, with nothing else resident on the SM to cover them) before its first key: ncu r02c put 14 % of the
- * instructions and 21 % of the stall samples of the level-2 scatter there */
-__global__ void __launch_bounds__(kThreads) k_tile_parents(const uint64_t *__restrict__ tile_off, uint64_t n_parents,
-                                                           uint64_t max_tiles, uint32_t *__restrict__ tile_parent)
+/* Tile table: what a CTA needs to know about its tile in ONE 16-byte load.  A CTA that found its parent by binary
+ * search over tile_off spent ten DEPENDENT global loads (~ 1.5 us, with nothing else resident on the SM to cover them)
+ * before its first key: ncu r02c put 14 % of the instructions and 21 % of the stall samples of the level-2 scatter
+ * there (17.46 -> 15.47 ms on the headline workload with the parent looked up, r02i).  The table is zeroed first, so
+ * the CTAs past the last tile (the grid is an upper bound) see cnt = 0. */
+struct __align__(16) TileInfo {
+    uint64_t beg;    /* first key of the tile */
+    uint32_t cnt;    /* keys in the tile      */
+    uint32_t parent; /* partition it lies in  */
+};
+
+__global__ void __launch_bounds__(kThreads) k_tile_table(const uint64_t *__restrict__ parent_beg,
+                                                         const uint64_t *__restrict__ parent_end,
+                                                         const uint64_t *__restrict__ tile_off, uint64_t n_parents,
+                                                         uint64_t tile_keys, uint64_t max_tiles, TileInfo *__restrict__ table)
 {
     const uint64_t p = (uint64_t)blockIdx.x * kThreads + threadIdx.x;
     if (p >= n_parents) return;
-    const uint64_t t1 = min(tile_off[p + 1], max_tiles);
-    for (uint64_t t = tile_off[p]; t < t1; ++t) tile_parent[t] = (uint32_t)p;
+    const uint64_t t0 = tile_off[p], t1 = min(tile_off[p + 1], max_tiles), pb = parent_beg[p], pe = parent_end[p];
+    for (uint64_t t = t0; t < t1; ++t) {
+        const uint64_t beg = pb + (t - t0) * tile_keys;
+        TileInfo ti;
+        ti.beg = beg;
+        ti.cnt = (uint32_t)(min(beg + tile_keys, pe) - beg);
+        ti.parent = (uint32_t)p;
+        table[t] = ti;
+    }
 }
 
-__device__ __forceinline__ void tile_range(const uint64_t *parent_beg, const uint64_t *parent_end,
+/* -> false when the CTA has no tile */
+__device__ __forceinline__ bool tile_range(const uint64_t *parent_beg, const uint64_t *parent_end,
                                            const uint64_t *tile_off, uint64_t n_parents, uint64_t tile_keys,
-                                           uint64_t &parent, uint64_t &beg, uint64_t &end,
-                                           const uint32_t *tile_parent = nullptr)
+                                           uint64_t &parent, uint64_t &beg, uint64_t &end, const TileInfo *table = nullptr)
 {
-    parent = n_parents == 1 ? 0 : tile_parent ? (uint64_t)tile_parent[blockIdx.x] : upper_seq(tile_off, n_parents, blockIdx.x);
+    if (table) {
+        const uint4 v = __ldg(reinterpret_cast<const uint4 *>(table + blockIdx.x));
+        beg = ((uint64_t)v.y << 32) | v.x;
+        end = beg + v.z;
+        parent = v.w;
+        return v.z != 0;
+    }
+    if (blockIdx.x >= tile_off[n_parents]) return false; /* the grid is an upper bound on the tiles */
+    parent = n_parents == 1 ? 0 : upper_seq(tile_off, n_parents, blockIdx.x);
     uint64_t t = blockIdx.x - tile_off[parent];
     beg = parent_beg[parent] + t * tile_keys;
     end = min(beg + tile_keys, parent_end[parent]);
+    return true;
 }
 
 /* optimistic layouts: region d starts at d * cap */
@@ -147,14 +173,13 @@ __global__ void __launch_bounds__(kThreads) k_part_hist_keys(const uint64_t *__r
                                                              uint64_t n_parents, uint64_t n_groups, int shift,
                                                              uint32_t fan,
                                                              unsigned long long *__restrict__ hist,
-                                                             const uint32_t *__restrict__ tile_parent = nullptr)
+                                                             const TileInfo *__restrict__ tile_table = nullptr)
 {
     __shared__ uint32_t h[kMaxFan];
-    if (blockIdx.x >= tile_off[n_parents]) return; /* the grid is an upper bound on the tiles */
+    uint64_t parent, beg, end;
+    if (!tile_range(parent_off, parent_end, tile_off, n_parents, kSuperTile, parent, beg, end, tile_table)) return;
     for (uint32_t i = threadIdx.x; i < fan; i += kThreads) h[i] = 0;
     __syncthreads();
-    uint64_t parent, beg, end;
-    tile_range(parent_off, parent_end, tile_off, n_parents, kSuperTile, parent, beg, end, tile_parent);
     const uint32_t fm = fan - 1;
     for (uint64_t base = beg; base < end; base += kThreads * 8) {
         uint64_t x[8];
@@ -397,17 +422,16 @@ __global__ void __launch_bounds__(THREADS, (PER * THREADS == 8192 ? 2 : 1)) k_pa
                                                                        uint64_t *__restrict__ out,
                                                                        unsigned long long *__restrict__ ctr,
                                                                        uint64_t cap = 0, int full_flag = C_L2OVF,
-                                                                       const uint32_t *__restrict__ tile_parent = nullptr)
+                                                                       const TileInfo *__restrict__ tile_table = nullptr)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     uint64_t *stage = reinterpret_cast<uint64_t *>(smem_raw);
     ScatterSmem &s = *reinterpret_cast<ScatterSmem *>(smem_raw + sizeof(uint64_t) * (PER * THREADS));
     constexpr uint32_t TILE = PER * THREADS;
-    if (blockIdx.x >= tile_off[n_parents]) return; /* the grid is an upper bound on the tiles */
+    uint64_t parent, beg, end;
+    if (!tile_range(parent_off, parent_end, tile_off, n_parents, TILE, parent, beg, end, tile_table)) return;
     for (uint32_t i = threadIdx.x; i <= fan; i += THREADS) s.cur[i] = 0;
     __syncthreads();
-    uint64_t parent, beg, end;
-    tile_range(parent_off, parent_end, tile_off, n_parents, TILE, parent, beg, end, tile_parent);
     const uint32_t fm = fan - 1;
     uint64_t x[PER];
     uint32_t rk[PER / 2]; /* two 16-bit ranks per register; the digit is recomputed */
@@ -1006,7 +1030,10 @@ __global__ void __launch_bounds__(kThreads, 4) k_count_buckets_bins(const uint64
                     const uint64_t key = stage[q], k1 = stage[q - 1], k2 = stage[q - 2], k3 = stage[q - 3];
                     uint32_t e = (uint32_t)((r >= 1) & (k1 == key)) + (uint32_t)((r >= 2) & (k2 == key)) +
                                  (uint32_t)((r >= 3) & (k3 == key));
-                    for (uint32_t j = 4; j <= r; ++j) e += stage[q - j] == key;
+                    if (r > 3) { /* rare: kept out of line (the rolled loop's set-up was 13 % of the kernel's instructions, ncu r02c) */
+#pragma unroll 1
+                        for (uint32_t j = 4; j <= r; ++j) e += stage[q - j] == key;
+                    }
                     repeats += e >= 1;
                     second += e == 1;
                 }
