@@ -1517,7 +1517,9 @@ static void plan_bits(uint64_t n, uint32_t n_parts, int *b1, int *b2)
 {
     const int b = bucket_bits(n);
     if (n_parts <= 1) {
-        *b1 = b <= 11 ? b : (b + 1) / 2; /* the odd bit goes to level 1: level 2 moves twice the bytes per key and
+        *b1 = b <= 11 ? b : (b + 1) / 2;
+        if (const char *e = tune_env("DNAGPU_L1_BITS")) /* profiling aid: how the bits split over the two levels */
+            if (atoi(e) >= 1 && atoi(e) <= 11 && b - atoi(e) <= 11) *b1 = atoi(e); /* the odd bit goes to level 1: level 2 moves twice the bytes per key and
                                           * gains more from the longer runs of the smaller fan-out (measured: 50.8 -> 49.9 ms) */
         *b2 = std::max(0, std::min(11, b - *b1));
         return;
