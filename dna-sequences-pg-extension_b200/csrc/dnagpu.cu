@@ -1814,11 +1814,10 @@ static int l1_regions_begin(dnagpu_ctx *ctx, Scratch &sc, uint64_t n_rows, int b
     TRY(sc.get((void **)&r->beg, (uint64_t)r->P1 * 8));
     TRY(sc.get((void **)&r->end, (uint64_t)r->P1 * 8));
     TRY(sc.get((void **)&r->cur, (uint64_t)r->P1 * 8));
-    std::vector<uint64_t> beg(r->P1);
-    for (uint32_t d = 0; d < r->P1; ++d) beg[d] = (uint64_t)d * r->cap;
-    CU(ctx, cudaMemcpyAsync(r->beg, beg.data(), (uint64_t)r->P1 * 8, cudaMemcpyHostToDevice, ctx->stream));
+    TRY(launch(ctx, "part_tiles", [&] {
+        k_region_begs<<<grid_for(r->P1, kThreads), kThreads, 0, ctx->stream>>>(r->cap, r->P1, r->beg);
+    }));
     CU(ctx, cudaMemsetAsync(r->cur, 0, (uint64_t)r->P1 * 8, ctx->stream));
-    CU(ctx, cudaStreamSynchronize(ctx->stream)); /* beg is a host temporary */
     return DNAGPU_OK;
 }
 
@@ -1949,7 +1948,8 @@ static int count_kmers_pipelined(dnagpu_ctx *ctx, const uint64_t *words, uint64_
     plan_bits(rows, 1, &b1, &b2);
     TRY(zero_counters(ctx));
     L1Regions r;
-    TRY(l1_regions_begin(ctx, sc, rows, b1, &r)); /* synchronises ctx->stream: d_words exists for the copy stream */
+    TRY(l1_regions_begin(ctx, sc, rows, b1, &r));
+    CU(ctx, cudaStreamSynchronize(ctx->stream)); /* d_words (stream-ordered allocation) exists before the copy stream writes it */
     const int n_chunks = 8;
     const uint64_t chunk_words = ((n_words + n_chunks - 1) / n_chunks + 255) & ~255ull;
     std::vector<cudaEvent_t> ev;
