@@ -2030,7 +2030,8 @@ static int count_listed(dnagpu_ctx *ctx, const uint64_t *keys, uint64_t n_match,
                         dnagpu_stats *stats, dnagpu_table **table);
 
 /* ---- multi-GPU: the k-mers of one owner out of the whole sequence (k_collect_owned + the key-list count) ----- */
-static int owned_view(dnagpu_ctx *ctx, const dnagpu_seq *seq, int k, OwnedView *ov)
+/* the walk order of k_collect_owned: every piece padded to whole tiles of `tile` items */
+static int owned_view(dnagpu_ctx *ctx, const dnagpu_seq *seq, int k, uint64_t tile, OwnedView *ov)
 {
     CHECK_OWNED(ctx, seq, "the sequence");
     memset(ov, 0, sizeof *ov);
@@ -2038,7 +2039,8 @@ static int owned_view(dnagpu_ctx *ctx, const dnagpu_seq *seq, int k, OwnedView *
         uint64_t r = rows_of(seq->bases, k);
         if (seq->start_limit) r = std::min(r, seq->start_limit);
         ov->ptr[0] = seq->d_words;
-        ov->vfirst[1] = (r + 31) / 32;
+        ov->nitems[0] = (r + 31) / 32;
+        ov->vfirst[1] = (ov->nitems[0] + tile - 1) / tile * tile;
         ov->n_rows = r;
         ov->n_pieces = 1;
         return DNAGPU_OK;
@@ -2055,7 +2057,8 @@ static int owned_view(dnagpu_ctx *ctx, const dnagpu_seq *seq, int k, OwnedView *
         ov->ptr[i] = seq->piece_ptr[i];
         ov->gfirst[i] = fb / 32;
         ov->vfirst[i] = v;
-        v += (starts + 31) / 32;
+        ov->nitems[i] = (starts + 31) / 32;
+        v += (ov->nitems[i] + tile - 1) / tile * tile;
     }
     ov->vfirst[ov->n_pieces] = v;
     return DNAGPU_OK;
@@ -2070,15 +2073,15 @@ static int count_owned(dnagpu_ctx *ctx, const dnagpu_seq *seq, int k, const dnag
     if (!stats) stats = &local;
     stats->total = stats->distinct = stats->unique = 0;
     if (table) *table = nullptr;
+    const int wpt = G >= 8 ? 4 : G >= 4 ? 2 : 1; /* a CTA examines 256 * wpt words and keeps ~ 8192 * wpt / G k-mers */
     OwnedView ov;
-    TRY(owned_view(ctx, seq, k, &ov));
+    TRY(owned_view(ctx, seq, k, (uint64_t)kOwnThreads * wpt, &ov));
     if (ov.n_rows == 0) {
         if (table) TRY(table_new(ctx, k, 0, table));
         return DNAGPU_OK;
     }
-    /* owner r holds the hashes [ceil(r 2^32 / G), ceil((r + 1) 2^32 / G)): what (hash * G) >> 32 == r says */
-    const uint64_t lo = (((uint64_t)me << 32) + G - 1) / G, hi = (((uint64_t)(me + 1) << 32) + G - 1) / G;
-    const uint32_t own_lo = (uint32_t)lo, own_span = (uint32_t)(hi - lo);
+    const OwnRange own = own_range_of(G, me, k); /* what owner_of maps to `me` */
+    const int lin = owner_lin_bits(G);
     const uint64_t n_expect = ov.n_rows / G + 1;
     const uint64_t n_vitems = ov.vfirst[ov.n_pieces];
     const uint64_t mask = kmer_mask(k);
@@ -2091,23 +2094,26 @@ static int count_owned(dnagpu_ctx *ctx, const dnagpu_seq *seq, int k, const dnag
         TRY(sc.get((void **)&keys, (cap + 2) * 8));
         TRY(zero_counters(ctx));
         if (staged) {
-            const int wpt = G >= 8 ? 4 : G >= 4 ? 2 : 1; /* a CTA examines 256 * wpt words and keeps ~ 8192 * wpt / G k-mers */
             const unsigned grid = grid_for(n_vitems, (uint64_t)kOwnThreads * wpt);
-#define OWNED_LAUNCH(WPT, ML) \
-    k_collect_owned<WPT, ML><<<grid, kOwnThreads, 0, ctx->stream>>>(ov, mask, own_lo, own_span, cap, ctx->d_ctr, keys)
+#define OWNED_LAUNCH(WPT, LIN, ML) \
+    k_collect_owned<WPT, LIN, ML><<<grid, kOwnThreads, 0, ctx->stream>>>(ov, mask, own, cap, ctx->d_ctr, keys)
             TRY(launch(ctx, "collect_owned", [&] {
                 if (k < 16) {
-                    if (wpt == 4) OWNED_LAUNCH(4, true); else if (wpt == 2) OWNED_LAUNCH(2, true); else OWNED_LAUNCH(1, true);
+                    if (lin == 3) OWNED_LAUNCH(4, 3, true); else if (lin == 2) OWNED_LAUNCH(2, 2, true); else if (lin == 1) OWNED_LAUNCH(1, 1, true);
+                    else if (wpt == 4) OWNED_LAUNCH(4, 0, true); else if (wpt == 2) OWNED_LAUNCH(2, 0, true); else OWNED_LAUNCH(1, 0, true);
                 } else {
-                    if (wpt == 4) OWNED_LAUNCH(4, false); else if (wpt == 2) OWNED_LAUNCH(2, false); else OWNED_LAUNCH(1, false);
+                    if (lin == 3) OWNED_LAUNCH(4, 3, false); else if (lin == 2) OWNED_LAUNCH(2, 2, false); else if (lin == 1) OWNED_LAUNCH(1, 1, false);
+                    else if (wpt == 4) OWNED_LAUNCH(4, 0, false); else if (wpt == 2) OWNED_LAUNCH(2, 0, false); else OWNED_LAUNCH(1, 0, false);
                 }
             }));
 #undef OWNED_LAUNCH
         } else {
             const unsigned grid = (unsigned)std::min<uint64_t>(grid_for(n_vitems, kScatThreads), (uint64_t)ctx->sm_count * 8);
+#define OWNED_ANY(LIN) k_collect_owned_any<LIN><<<grid, kScatThreads, 0, ctx->stream>>>(ov, mask, own, cap, ctx->d_ctr + C_CURSOR, keys)
             TRY(launch(ctx, "collect_owned", [&] {
-                k_collect_owned_any<<<grid, kScatThreads, 0, ctx->stream>>>(ov, mask, own_lo, own_span, cap, ctx->d_ctr + C_CURSOR, keys);
+                if (lin == 3) OWNED_ANY(3); else if (lin == 2) OWNED_ANY(2); else if (lin == 1) OWNED_ANY(1); else OWNED_ANY(0);
             }));
+#undef OWNED_ANY
         }
         TRY(fetch_counters(ctx));
         n_own = ctx->h_ctr[C_CURSOR];

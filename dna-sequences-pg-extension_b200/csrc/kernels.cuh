@@ -63,15 +63,54 @@ __host__ __device__ __forceinline__ uint64_t mix64(uint64_t x)
     x ^= x >> 33;
     return x;
 }
-/* Owner rank of a k-mer among n_parts GPUs: a multiplicative hash of the k-mer's low word (its first 16
- * bases; the whole k-mer for k <= 16), top bits -> rank.  One IMAD per start position, because the
- * multi-GPU count tests EVERY start position of the sequence for ownership (k_collect_owned) and
- * keeps one in n_parts.  Independent of the partition digits (64-bit multiply-shift over the whole
- * k-mer) and of the bucket / bin hashes (fold of both words, another multiplier). */
+/* Owner rank of a k-mer among n_parts GPUs -- a function of the k-mer's low word (its first 16 bases; the whole
+ * k-mer for k <= 16), because the multi-GPU count tests EVERY start position of the sequence for ownership
+ * (k_collect_owned) and keeps one in n_parts.  Independent of the partition digits (64-bit multiply-shift over the
+ * whole k-mer) and of the bucket / bin hashes (fold of both words, another multiplier).
+ *   n_parts = 2, 4, 8 (the machines that exist): bit i of the rank is the parity of the low word under kOwnTap[i]
+ *     -- a GF(2)-linear hash, five taps per bit out of a pool of ten bit offsets that mixes both bits of ten of the
+ *     sixteen bases (any XOR of the three tap sets keeps >= 5 taps).  Linear means bit-parallel: the funnel shift
+ *     of a packed word by a tap offset holds that tap for all 32 start positions at once, so the ownership of 32
+ *     starts costs ~ 40 instructions instead of 32 x (shift, multiply, compare, select).
+ *   any other n_parts: multiplicative hash of the low word, top bits -> rank; one IMAD per start position. */
 constexpr uint32_t kOwnerMul = 0x85EBCA6Bu;
+constexpr int kOwnPool = 10;
+__host__ __device__ constexpr int own_tau(int p)
+{ /* bit offsets of the pool inside the low word */
+    return p == 0 ? 0 : p == 1 ? 3 : p == 2 ? 6 : p == 3 ? 9 : p == 4 ? 13 : p == 5 ? 16 : p == 6 ? 19 : p == 7 ? 22 : p == 8 ? 26 : 29;
+}
+__host__ __device__ constexpr uint32_t own_sub(int i)
+{ /* pool members of rank bit i */
+    return i == 0 ? 0x06Eu : i == 1 ? 0x2D1u : 0x1B4u;
+}
+__host__ __device__ constexpr uint32_t own_tap(int i)
+{
+    uint32_t m = 0;
+    for (int p = 0; p < kOwnPool; ++p)
+        if (own_sub(i) >> p & 1u) m |= 1u << own_tau(p);
+    return m;
+}
+/* rank bits of the linear form: 1, 2, 3 for 2, 4, 8 owners; 0 = multiplicative form */
+__host__ __device__ __forceinline__ int owner_lin_bits(uint32_t n_parts) { return n_parts == 2 ? 1 : n_parts == 4 ? 2 : n_parts == 8 ? 3 : 0; }
 __host__ __device__ __forceinline__ uint32_t owner_hash(uint64_t kmer) { return (uint32_t)kmer * kOwnerMul; }
+__host__ __device__ __forceinline__ uint32_t parity32(uint32_t x)
+{
+#ifdef __CUDA_ARCH__
+    return (uint32_t)__popc(x) & 1u;
+#else
+    return (uint32_t)__builtin_popcount(x) & 1u;
+#endif
+}
 __host__ __device__ __forceinline__ uint32_t owner_of(uint64_t kmer, uint32_t n_parts)
 {
+    const int lin = owner_lin_bits(n_parts);
+    if (lin) {
+        const uint32_t x = (uint32_t)kmer;
+        uint32_t r = parity32(x & own_tap(0));
+        if (lin > 1) r |= parity32(x & own_tap(1)) << 1;
+        if (lin > 2) r |= parity32(x & own_tap(2)) << 2;
+        return r;
+    }
     return (uint32_t)(((uint64_t)owner_hash(kmer) * (uint64_t)n_parts) >> 32);
 }
 

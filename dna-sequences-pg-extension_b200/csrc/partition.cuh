@@ -484,49 +484,120 @@ __global__ void __launch_bounds__(THREADS, (PER * THREADS == 8192 ? 2 : 1)) k_pa
  * local data: optimistic level 1 from the key list, level 2, bucket count.  There is no exchange step
  * and nothing to merge.
  *
- * A CTA of 256 threads examines 256 * WPT packed words (WPT = n_parts / 2, so that it keeps ~ 4096 k-mers).
- * The keep masks of a word go through a warp scan into a compact per-warp segment of a shared-memory
- * list (+ a shared overflow area); the CTA then claims its range of the global list with ONE atomic and
- * copies the segments out coalesced.  40 KB of shared memory and few registers: five CTAs per SM, which
- * is what hides the microseconds a peer-memory load takes. */
+ * A CTA of 256 threads examines a tile of 256 * WPT packed words of ONE piece (WPT = n_parts / 2, so that it keeps
+ * ~ 4096 k-mers; the pieces are padded to whole tiles in the walk order).  The tile's words are staged once in shared
+ * memory (one coalesced read, peer or local).  Every thread builds the ownership masks of its WPT consecutive words
+ * (bit-parallel for 2 / 4 / 8 owners, see owner_of), one warp scan places the thread in its warp's segment of a
+ * shared-memory list (+ a shared overflow area), and ONE loop over the thread's set bits appends a 16-bit code
+ * (word << 5 | bit) per owned start -- a dozen instructions per start, the only divergent part.  The CTA then claims
+ * its range of the global list with ONE atomic and the warps expand their codes into k-mers from the staged words,
+ * lane per slot: balanced, coalesced 8-byte stores.  ~ 19 KB of shared memory, 32 registers: eight CTAs per SM hide
+ * the microseconds a peer load takes. */
 constexpr int kMaxPieces = 16;
 constexpr int kOwnThreads = 256;
-constexpr int kOwnSeg = 576;                                     /* list slots of one warp (mean 512, sigma ~ 21) */
-constexpr int kOwnOvf = 512;                                     /* shared overflow slots                         */
-constexpr int kOwnList = (kOwnThreads / 32) * kOwnSeg + kOwnOvf; /* 5120 keys                                     */
+constexpr int kOwnSeg = 576;                                     /* list slots of one warp (mean <= 512, sigma ~ 22) */
+constexpr int kOwnOvf = 512;                                     /* shared overflow slots                            */
+constexpr int kOwnList = (kOwnThreads / 32) * kOwnSeg + kOwnOvf; /* 5120 codes                                       */
 
 struct OwnedView {
     const uint64_t *ptr[kMaxPieces];  /* first packed word of piece i (local or peer-mapped)                      */
-    uint64_t vfirst[kMaxPieces + 1];  /* this GPU walks the items in the order of its piece list: [vfirst[i], vfirst[i+1]) */
+    uint64_t vfirst[kMaxPieces + 1];  /* this GPU walks the items in the order of its piece list: [vfirst[i], vfirst[i+1]), */
+    uint64_t nitems[kMaxPieces];      /* of which the first nitems[i] exist (the rest pads the piece to whole tiles) */
     uint64_t gfirst[kMaxPieces];      /* index of the piece's first item (= packed word) in the whole sequence     */
     uint64_t n_rows;                  /* generate_kmers rows of the whole sequence                                */
     uint32_t n_pieces;
 };
 
-/* bit j of the result: start j of the item (w0, w1) is a k-mer this GPU owns.  MASKLO: k < 16, the low word
- * of the window holds bases past the k-mer */
-template <bool MASKLO = true>
-__device__ __forceinline__ uint32_t owned_mask(uint64_t w0, uint64_t w1, uint32_t mask_lo, uint32_t own_lo,
-                                               uint32_t own_span)
+/* What a kernel needs to tell its owner's k-mers: the hash range of the multiplicative form (lo, span), or for the
+ * linear form the XOR seeds of the rank bits (inv[i] = ~0 when bit i of the rank is 0: the chain then ends in "bit
+ * matches") and the taps in force (en, bit p: tap p lies inside the k-mer, i.e. own_tau(p) < 2k). */
+struct OwnRange {
+    uint32_t lo, span, en, inv[3];
+};
+__host__ inline OwnRange own_range_of(uint32_t n_parts, uint32_t part, int k)
 {
-    const uint32_t a0 = (uint32_t)w0, a1 = (uint32_t)(w0 >> 32), a2 = (uint32_t)w1;
-    uint32_t km = 0;
-#pragma unroll
-    for (int j = 0; j < 32; ++j) {
-        const uint32_t lo = j == 0 ? a0 : j < 16 ? __funnelshift_r(a0, a1, 2 * j) : j == 16 ? a1
-                                                                                             : __funnelshift_r(a1, a2, 2 * j - 32);
-        const uint32_t h = (MASKLO ? lo & mask_lo : lo) * kOwnerMul;
-        km |= (uint32_t)((h - own_lo) < own_span) << j;
-    }
-    return km;
+    OwnRange r;
+    const uint64_t lo = (((uint64_t)part << 32) + n_parts - 1) / n_parts, hi = (((uint64_t)(part + 1) << 32) + n_parts - 1) / n_parts;
+    r.lo = (uint32_t)lo; /* owner r holds the hashes [ceil(r 2^32 / G), ceil((r + 1) 2^32 / G)): what (hash * G) >> 32 == r says */
+    r.span = (uint32_t)(hi - lo);
+    r.en = 0;
+    for (int p = 0; p < kOwnPool; ++p)
+        if (own_tau(p) < 2 * k) r.en |= 1u << p;
+    for (int i = 0; i < 3; ++i) r.inv[i] = (part >> i & 1u) ? 0u : ~0u;
+    return r;
 }
 
-/* virtual item v -> packed words and number of valid starts */
+/* Ownership of the 32 starts of the item (w0, low word a2 of its neighbour) as a mask.  MASKLO: k < 16, the low
+ * word of a start's window holds bases past the k-mer.
+ *   LIN = 0: bit j = start j; per start the funnel shift, hash - lo in one IMAD, compare, select (+ half an add).
+ *   LIN = 1..3: bit 2j = start j, bit 2j + 1 = start 16 + j (the two 32-bit halves of the 64 bit positions, of which
+ *     the even ones are starts, interleaved): per pool tap one funnel shift per half, per rank bit one XOR chain. */
+template <int LIN, bool MASKLO>
+__device__ __forceinline__ uint32_t owned_mask(uint64_t w0, uint32_t a2, uint32_t mask_lo, const OwnRange &own)
+{
+    const uint32_t a0 = (uint32_t)w0, a1 = (uint32_t)(w0 >> 32);
+    if (LIN == 0) {
+        uint32_t km = 0;
+#pragma unroll
+        for (int j = 0; j < 32; ++j) {
+            const uint32_t lo = j == 0 ? a0 : j < 16 ? __funnelshift_r(a0, a1, 2 * j) : j == 16 ? a1
+                                                                                                 : __funnelshift_r(a1, a2, 2 * j - 32);
+            const uint32_t t = (MASKLO ? lo & mask_lo : lo) * kOwnerMul - own.lo;
+            km |= (uint32_t)(t < own.span) << j;
+        }
+        return km;
+    }
+    uint32_t f0[3] = {own.inv[0], own.inv[1], own.inv[2]}, f1[3] = {own.inv[0], own.inv[1], own.inv[2]};
+#pragma unroll
+    for (int p = 0; p < kOwnPool; ++p) {
+        bool used = false;
+#pragma unroll
+        for (int i = 0; i < LIN; ++i) used |= (own_sub(i) >> p & 1u) != 0;
+        if (!used) continue;
+        uint32_t s0 = own_tau(p) ? __funnelshift_r(a0, a1, own_tau(p)) : a0;
+        uint32_t s1 = own_tau(p) ? __funnelshift_r(a1, a2, own_tau(p)) : a1;
+        if (MASKLO) {
+            const uint32_t on = 0u - (own.en >> p & 1u);
+            s0 &= on;
+            s1 &= on;
+        }
+#pragma unroll
+        for (int i = 0; i < LIN; ++i)
+            if (own_sub(i) >> p & 1u) f0[i] ^= s0, f1[i] ^= s1;
+    }
+    uint32_t o0 = f0[0], o1 = f1[0];
+#pragma unroll
+    for (int i = 1; i < LIN; ++i) o0 &= f0[i], o1 &= f1[i];
+    return (o0 & 0x55555555u) | ((o1 & 0x55555555u) << 1);
+}
+/* the mask of the first `n` starts (n < 32) in the layout of owned_mask<LIN> */
+template <int LIN>
+__device__ __forceinline__ uint32_t first_starts(uint32_t n)
+{
+    const uint32_t vm = (1u << n) - 1u;
+    if (LIN == 0) return vm;
+    auto spread = [](uint32_t x) { /* bit j -> bit 2j, j < 16 */
+        x = (x | x << 8) & 0x00FF00FFu;
+        x = (x | x << 4) & 0x0F0F0F0Fu;
+        x = (x | x << 2) & 0x33333333u;
+        return (x | x << 1) & 0x55555555u;
+    };
+    return spread(vm & 0xFFFFu) | spread(vm >> 16) << 1;
+}
+/* bit offset (2 * start) of the window a mask bit stands for */
+template <int LIN>
+__device__ __forceinline__ uint32_t start_shift(uint32_t bit)
+{
+    return LIN == 0 ? 2 * bit : (bit & 30u) | (bit & 1u) << 5;
+}
+
+/* virtual item v -> packed words and number of valid starts (0: padding) */
 __device__ __forceinline__ int owned_item(const OwnedView &ov, uint64_t v, uint64_t &w0, uint64_t &w1)
 {
     uint32_t i = 0;
     while (i + 1 < ov.n_pieces && v >= ov.vfirst[i + 1]) ++i;
     const uint64_t off = v - ov.vfirst[i];
+    if (off >= ov.nitems[i]) return 0;
     const uint64_t *w = ov.ptr[i] + off;
     w0 = ld_nc(w);
     w1 = ld_nc(w + 1);
@@ -537,58 +608,102 @@ __device__ __forceinline__ int owned_item(const OwnedView &ov, uint64_t v, uint6
 /* The owned k-mers of the sequence as a key list (unordered).  `cursor` ends at the number of owned rows even
  * when tiles past `cap` wrote nothing; a tile whose shared-memory list overflowed (a long run of one k-mer owned
  * by this GPU) raises C_L1OVF: the caller then uses k_collect_owned_any. */
-template <int WPT, bool MASKLO>
-__global__ void __launch_bounds__(kOwnThreads) k_collect_owned(OwnedView ov, uint64_t mask, uint32_t own_lo,
-                                                               uint32_t own_span, uint64_t cap,
+template <int WPT, int LIN, bool MASKLO>
+__global__ void __launch_bounds__(kOwnThreads) k_collect_owned(OwnedView ov, uint64_t mask, OwnRange own, uint64_t cap,
                                                                unsigned long long *__restrict__ ctr,
                                                                uint64_t *__restrict__ out)
 {
-    __shared__ __align__(16) uint64_t list[kOwnList];
+    constexpr int T = kOwnThreads * WPT; /* words of a tile; vfirst[] are multiples of T */
+    static_assert(T <= 2048 && (WPT == 1 || WPT == 2 || WPT == 4), "a code holds 11 bits of word index");
+    __shared__ __align__(16) uint64_t words[T + 2];
+    __shared__ uint16_t codes[kOwnList];
     __shared__ uint32_t n_ovf_s, wtot_s[kOwnThreads / 32];
     __shared__ unsigned long long base_s;
     const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     if (tid == 0) n_ovf_s = 0;
+    const uint64_t v0 = (uint64_t)blockIdx.x * T;
+    uint32_t pi = 0;
+    while (pi + 1 < ov.n_pieces && v0 >= ov.vfirst[pi + 1]) ++pi;
+    const uint64_t off0 = v0 - ov.vfirst[pi];
+    const uint64_t have = ov.nitems[pi] > off0 ? ov.nitems[pi] - off0 : 0;
+    const uint32_t n_valid = have < (uint64_t)T ? (uint32_t)have : (uint32_t)T; /* uniform */
+    if (n_valid == 0) return;
+    {
+        const uint64_t *src = ov.ptr[pi] + off0;
+#pragma unroll
+        for (int it = 0; it < WPT; ++it) {
+            const uint32_t idx = it * kOwnThreads + tid;
+            words[idx] = idx <= n_valid ? ld_nc(src + idx) : 0ull; /* [n_valid]: the last item's neighbour (overlap or pad word) */
+        }
+        if (tid == 0 && n_valid == (uint32_t)T) words[T] = ld_nc(src + T);
+    }
     __syncthreads();
     const uint32_t mask_lo = (uint32_t)mask;
-    const uint64_t n_vitems = ov.vfirst[ov.n_pieces];
-    const uint64_t v0 = (uint64_t)blockIdx.x * ((uint64_t)kOwnThreads * WPT);
-    uint32_t wcur = 0;
-    uint64_t pw0[WPT], pw1[WPT];
-    int pc[WPT];
+    /* starts from the tile's first word to the end of the sequence (>= 1 per existing item) */
+    const uint64_t left0_64 = ov.n_rows - (ov.gfirst[pi] + off0) * 32;
+    const uint32_t left0 = left0_64 < (uint64_t)T * 32 ? (uint32_t)left0_64 : (uint32_t)T * 32;
+    /* 1. the masks of this thread's WPT consecutive words */
+    const uint32_t i0 = tid * WPT;
+    uint32_t km[WPT];
+    {
+        uint64_t w[WPT];
+        if (WPT == 4) {
+            const uint4 x = *reinterpret_cast<const uint4 *>(&words[i0]), y = *reinterpret_cast<const uint4 *>(&words[i0 + 2]);
+            w[0] = (uint64_t)x.y << 32 | x.x, w[1] = (uint64_t)x.w << 32 | x.z;
+            w[WPT - 2] = (uint64_t)y.y << 32 | y.x, w[WPT - 1] = (uint64_t)y.w << 32 | y.z;
+        } else if (WPT == 2) {
+            const uint4 x = *reinterpret_cast<const uint4 *>(&words[i0]);
+            w[0] = (uint64_t)x.y << 32 | x.x, w[WPT - 1] = (uint64_t)x.w << 32 | x.z;
+        } else {
+            w[0] = words[i0];
+        }
+        /* the low word after the thread's last: the next lane's first (lane 31 reads it) */
+        uint32_t nxt = __shfl_down_sync(0xffffffffu, (uint32_t)w[0], 1);
+        if (lane == 31) nxt = (uint32_t)words[i0 + WPT];
 #pragma unroll
-    for (int it = 0; it < WPT; ++it) { /* all loads first */
-        const uint64_t v = v0 + (uint64_t)it * kOwnThreads + tid;
-        pw0[it] = pw1[it] = 0;
-        pc[it] = 0;
-        if (v < n_vitems) pc[it] = owned_item(ov, v, pw0[it], pw1[it]);
+        for (int it = 0; it < WPT; ++it) {
+            const uint32_t idx = i0 + it;
+            km[it] = 0;
+            if (idx < n_valid) {
+                km[it] = owned_mask<LIN, MASKLO>(w[it], it + 1 < WPT ? (uint32_t)w[it + 1 < WPT ? it + 1 : it] : nxt, mask_lo, own);
+                const uint32_t left = left0 - idx * 32;
+                if (left < 32) km[it] &= first_starts<LIN>(left);
+            }
+        }
     }
+    /* 2. the thread's place in the warp's segment */
+    uint32_t n = 0;
 #pragma unroll
-    for (int it = 0; it < WPT; ++it) {
-        const uint64_t w0 = pw0[it], w1 = pw1[it];
-        const int c = pc[it];
-        uint32_t km = 0;
-        if (c > 0) {
-            km = owned_mask<MASKLO>(w0, w1, mask_lo, own_lo, own_span);
-            if (c < 32) km &= (1u << c) - 1u;
-        }
-        const uint32_t n = __popc(km);
-        uint32_t inc = n;
+    for (int it = 0; it < WPT; ++it) n += __popc(km[it]);
+    uint32_t inc = n;
 #pragma unroll
-        for (int o = 1; o < 32; o <<= 1) {
-            const uint32_t y = __shfl_up_sync(0xffffffffu, inc, o);
-            if (lane >= (uint32_t)o) inc += y;
-        }
-        uint32_t p = wcur + inc - n;
-        wcur += __shfl_sync(0xffffffffu, inc, 31);
-        while (km) {
-            const int j = __ffs(km) - 1;
-            km &= km - 1;
-            const uint64_t x = window(w0, w1, 2 * j) & mask;
-            if (p < (uint32_t)kOwnSeg) {
-                list[warp * kOwnSeg + p] = x;
+    for (int o = 1; o < 32; o <<= 1) {
+        const uint32_t y = __shfl_up_sync(0xffffffffu, inc, o);
+        if (lane >= (uint32_t)o) inc += y;
+    }
+    uint32_t p = inc - n;
+    const uint32_t wcur = __shfl_sync(0xffffffffu, inc, 31);
+    /* 3. one loop over all set bits of the thread: masks move down as they empty */
+    {
+        const uint32_t seg_addr = (uint32_t)__cvta_generic_to_shared(&codes[warp * kOwnSeg]);
+        uint32_t m0 = km[0], m1 = WPT > 1 ? km[WPT > 1 ? 1 : 0] : 0, m2 = WPT > 2 ? km[WPT > 2 ? 2 : 0] : 0, m3 = WPT > 3 ? km[WPT > 3 ? 3 : 0] : 0;
+        uint32_t code0 = i0 << 5;
+#pragma unroll 1
+        for (; n; --n) {
+            if (m0 == 0) {
+#pragma unroll 1
+                do {
+                    m0 = m1, m1 = m2, m2 = m3, m3 = 0;
+                    code0 += 32;
+                } while (m0 == 0);
+            }
+            const uint32_t code = code0 | (uint32_t)(__ffs(m0) - 1);
+            m0 &= m0 - 1;
+            if (p < (uint32_t)kOwnSeg) { /* (the address spelled out: the compiler rebuilds the array base per store) */
+                asm volatile("st.shared.u16 [%0], %1;" ::"r"(seg_addr + 2 * p), "h"((uint16_t)code) : "memory");
             } else {
                 const uint32_t q = atomicAdd(&n_ovf_s, 1u);
-                if (q < (uint32_t)kOwnOvf) list[(kOwnThreads / 32) * kOwnSeg + q] = x;
+                if (q < (uint32_t)kOwnOvf) codes[(kOwnThreads / 32) * kOwnSeg + q] = (uint16_t)code;
             }
             ++p;
         }
@@ -610,15 +725,20 @@ __global__ void __launch_bounds__(kOwnThreads) k_collect_owned(OwnedView ov, uin
     }
     __syncthreads();
     if (total == 0 || base_s + total > cap) return; /* uniform */
+    /* 4. codes -> k-mers, lane per slot */
     uint64_t *dst = out + base_s;
-    for (uint32_t q = lane; q < wn; q += 32) dst[before + q] = list[warp * kOwnSeg + q];
-    for (uint32_t q = tid; q < on; q += kOwnThreads) dst[total - on + q] = list[(kOwnThreads / 32) * kOwnSeg + q];
+    auto kmer_of = [&](uint32_t code) {
+        const uint32_t idx = code >> 5;
+        return window(words[idx], words[idx + 1], start_shift<LIN>(code & 31u)) & mask;
+    };
+    for (uint32_t q = lane; q < wn; q += 32) dst[before + q] = kmer_of(codes[warp * kOwnSeg + q]);
+    for (uint32_t q = tid; q < on; q += kOwnThreads) dst[total - on + q] = kmer_of(codes[(kOwnThreads / 32) * kOwnSeg + q]);
 }
 
 /* The same list for ANY input (the exact fallback: heavily repeated sequences): appended warp by warp through the
  * cursor, nothing staged, nothing dropped. */
-__global__ void __launch_bounds__(kScatThreads) k_collect_owned_any(OwnedView ov, uint64_t mask, uint32_t own_lo,
-                                                                    uint32_t own_span, uint64_t cap,
+template <int LIN>
+__global__ void __launch_bounds__(kScatThreads) k_collect_owned_any(OwnedView ov, uint64_t mask, OwnRange own, uint64_t cap,
                                                                     unsigned long long *__restrict__ cursor,
                                                                     uint64_t *__restrict__ out)
 {
@@ -630,8 +750,8 @@ __global__ void __launch_bounds__(kScatThreads) k_collect_owned_any(OwnedView ov
         uint32_t km = 0;
         if (v < n_vitems) {
             const int c = owned_item(ov, v, w0, w1);
-            km = owned_mask(w0, w1, (uint32_t)mask, own_lo, own_span);
-            if (c < 32) km &= (1u << c) - 1u;
+            if (c > 0) km = owned_mask<LIN, true>(w0, (uint32_t)w1, (uint32_t)mask, own);
+            if (c < 32) km &= first_starts<LIN>((uint32_t)c);
         }
         const uint32_t n = __popc(km);
         uint32_t inc = n;
@@ -649,7 +769,7 @@ __global__ void __launch_bounds__(kScatThreads) k_collect_owned_any(OwnedView ov
         while (km) {
             const int j = __ffs(km) - 1;
             km &= km - 1;
-            out[p++] = window(w0, w1, 2 * j) & mask;
+            out[p++] = window(w0, w1, start_shift<LIN>((uint32_t)j)) & mask;
         }
     }
 }

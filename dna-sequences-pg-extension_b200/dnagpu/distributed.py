@@ -63,12 +63,16 @@ class ShardRing:
     """Every rank's shard of one sequence in peer-mappable memory, mapped by every rank (one per process).
 
     Collective constructor: allocates this rank's buffer (dnagpu_peer_alloc), swaps the IPC handles and opens the
-    others (dnagpu_peer_open).  Raises on EVERY rank if any rank cannot allocate or map."""
+    others (dnagpu_peer_open).  Raises on EVERY rank if any rank cannot allocate or map.  `shards` replaces the
+    equal base ranges of ring_shards ([(first_base, n_starts)] per rank, first_base a multiple of 32, tiling the
+    sequence)."""
 
-    def __init__(self, ctx, world, rank, n_bases, group=None):
+    def __init__(self, ctx, world, rank, n_bases, group=None, shards=None):
         import torch.distributed as dist
         self.ctx, self.world, self.rank, self.n_bases, self.group = ctx, world, rank, n_bases, group
-        self.shards = ring_shards(n_bases, world)
+        self.shards = list(shards) if shards is not None else ring_shards(n_bases, world)
+        if len(self.shards) != world:
+            raise ValueError("one base range per rank")
         self.n_words = [shard_words(n_bases, f, s) for f, s in self.shards]
         self.local, self.base, self._seq, handle, err = 0, [], None, None, None
         try:

@@ -62,6 +62,28 @@ def test_owner_of_is_a_pure_host_function():
             assert len(set(owners)) == parts
 
 
+def test_owner_of_forms():
+    """2 / 4 / 8 owners: GF(2)-linear in the k-mer's low word (kernels.cuh owner_of: parities under three tap masks), so
+    owner(x ^ y) = owner(x) ^ owner(y); every other count: multiplicative hash of the low word.  Both ignore the
+    high word and spread random k-mers evenly."""
+    import random
+    from dnagpu import owner_of
+    rnd = random.Random(7)
+    xs = [rnd.getrandbits(64) for _ in range(4000)]
+    for parts in (2, 4, 8):
+        assert owner_of(0, parts) == 0
+        for x, y in zip(xs[:500], xs[500:1000]):
+            assert owner_of(x ^ y, parts) == owner_of(x, parts) ^ owner_of(y, parts)
+        # the ranks of 4 and 2 owners are the low bits of the rank among 8
+        assert all(owner_of(x, parts) == owner_of(x, 8) & (parts - 1) for x in xs[:500])
+    for parts in (2, 3, 4, 5, 8, 16):
+        assert all(owner_of(x, parts) == owner_of(x & 0xFFFFFFFF, parts) for x in xs[:500])
+        share = [0] * parts
+        for x in xs:
+            share[owner_of(x, parts)] += 1
+        assert max(share) - min(share) < 0.35 * len(xs) / parts, (parts, share)
+
+
 def test_no_cpu_fallback_without_a_device():
     import torch
     if torch.cuda.is_available():

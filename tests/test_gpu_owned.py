@@ -31,7 +31,7 @@ def _owned_union(gpu, seq, k, G, **kw):
     return (total, distinct, unique), kmers[order], counts[order]
 
 
-@pytest.mark.parametrize("G", [2, 3, 8])
+@pytest.mark.parametrize("G", [2, 3, 5, 8, 16])
 @pytest.mark.parametrize("k", [5, 14, 21, 31, 32])
 def test_owner_shares_are_disjoint_and_add_up_to_the_oracle(gpu, G, k):
     n, seed = 3_000_000, 5            # seed 5 / words 8-9: contains 'G' x 32 (the k = 32 sentinel key)
