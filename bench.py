@@ -272,7 +272,8 @@ def run_reference(args):
 # (profiles/r02_sass_hot_kernels.txt); profiles/issue.json overrides them with ncu counts of the current build.
 # Integer SASS runs on two pipes of HALF the issue rate each (ALU: LOP3 / SHF / IADD3 / ISETP, FMA: IMAD): a kernel that is
 # mostly ALU-pipe instructions saturates at frac ~ 0.5 of the issue peak.
-ISSUE_INSTR_PER_POSITION = {"filter_collect": 9.5, "filter_count": 9.5, "filter_collect:planes": 19.6, "collect_owned": 7.4}
+ISSUE_INSTR_PER_POSITION = {"filter_collect": 9.5, "filter_count": 9.5, "filter_collect:planes": 19.6, "collect_owned": 27.4,
+                            "collect_owned:2": 30.75, "collect_owned:4": 19.39, "collect_owned:8": 11.72}
 
 
 def issue_table():
@@ -603,6 +604,8 @@ def run_b200(args):
         issue = issue_table()
         if args.planes:
             issue["filter_collect"] = issue["filter_collect:planes"]
+        if f"collect_owned:{world}" in issue:  # the ownership scan costs less per position for 2 / 4 / 8 owners (linear form)
+            issue["collect_owned"] = issue[f"collect_owned:{world}"]
         issue = {q: v for q, v in issue.items() if ":" not in q}
         clk_hz = 1e6 * float((clocks or {}).get("sm_mhz") or 1965.0)
         issue_peak = SM_COUNT * LANES_PER_SM * clk_hz / 1e12  # T lane-instructions / s

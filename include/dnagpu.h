@@ -307,7 +307,9 @@ int dnagpu_table_device(const dnagpu_table *table, const uint64_t **d_kmers,
 void dnagpu_table_free(dnagpu_table *table);
 
 /* ---- multi-GPU owner routing ------------------------------------------------- */
-/* Owner rank of a k-mer among n_parts ranks (pure function; host-callable). */
+/* Owner rank of a k-mer among n_parts ranks (pure function; host-callable).  A function of the k-mer's first
+ * 16 bases: for 2, 4 and 8 ranks a GF(2)-linear hash (parities under three tap masks; the rank among 2 or 4 is
+ * the low bits of the rank among 8), for any other count a multiplicative hash. */
 uint32_t dnagpu_owner_of(uint64_t kmer, uint32_t n_parts);
 /* Extract (+filter) and bucket the k-mers by owner: bucket p occupies
  * d_out[offset_p, offset_p + part_counts[p]) with offset_p the exclusive prefix

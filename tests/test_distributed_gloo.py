@@ -221,14 +221,14 @@ class OracleRingCtx(OraclePeerCtx):
         return st, None
 
 
-def _worker_gather(rank, world, port, n_bases, k, seed, out):
+def _worker_gather(rank, world, port, n_bases, k, seed, out, shards=None):
     for p in (ROOT, PKG):
         sys.path.insert(0, p)
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
     dist.init_process_group("gloo", rank=rank, world_size=world)
     from dnagpu.distributed import ShardRing, count_sharded_gather
     ctx = OracleRingCtx(n_bases, seed, rank)
-    ring = ShardRing(ctx, world, rank, n_bases)
+    ring = ShardRing(ctx, world, rank, n_bases, shards=shards)
     first, starts = ring.my_shard
     ctx.fill_shard(ring.local, first, starts, ring.n_words[rank])
     ring.publish()
@@ -248,6 +248,26 @@ def test_gather_form_equals_single_rank(n_bases, k, world):
     q = ctx.Queue()
     port = 29400 + (n_bases + k + world) % 150
     procs = [ctx.Process(target=_worker_gather, args=(r, world, port, n_bases, k, 31, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    got = q.get(timeout=180)
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    words = R.synth_seq(31, n_bases)
+    want = R.count_query(words, 1, n_bases, words.size, k, faithful=False)
+    assert [tuple(g) for g in got] == [want.stats, want.stats]
+
+
+def test_gather_form_with_uneven_shards():
+    """ShardRing(shards=...): base ranges of the caller's choosing (tools/probe_collect.py gives rank 0 an eighth of the
+    sequence), one of them empty."""
+    from oracle import ref_cpu as R
+    n_bases, k, world = 10_000, 21, 3
+    shards = [(0, 1_248), (1_248, n_bases - 1_248), (n_bases // 32 * 32 + 32, 0)]
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_worker_gather, args=(r, world, 29391, n_bases, k, 31, q, shards)) for r in range(world)]
     for p in procs:
         p.start()
     got = q.get(timeout=180)
