@@ -1,6 +1,7 @@
 #!/bin/bash
 # GPU run r02o (2 GPUs): ownership test as compare + select (main build) against IMAD.HI + funnel shift (tuning build,
-# -DDNAGPU_OWN_CARRY): owned tests on both, the N=8/4/2 traffic probe on both.
+# -DDNAGPU_OWN_CARRY): owned tests on both, the N=8/4/2 traffic probe on both.  The variant measured slower
+# (profiles/README.md, r02o) and was removed from the source afterwards; this script records how it was run.
 cd "$(dirname "$0")/.."
 O=gpurun_out; TAG=${1:-r02o}
 T=$PWD/dna-sequences-pg-extension_b200/libdnagpu_tuning.so
