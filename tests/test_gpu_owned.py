@@ -31,7 +31,7 @@ def _owned_union(gpu, seq, k, G, **kw):
     return (total, distinct, unique), kmers[order], counts[order]
 
 
-@pytest.mark.parametrize("G", [2, 3, 5, 8, 16])
+@pytest.mark.parametrize("G", [2, 3, 4, 5, 8, 16])
 @pytest.mark.parametrize("k", [5, 14, 21, 31, 32])
 def test_owner_shares_are_disjoint_and_add_up_to_the_oracle(gpu, G, k):
     n, seed = 3_000_000, 5            # seed 5 / words 8-9: contains 'G' x 32 (the k = 32 sentinel key)
@@ -49,7 +49,7 @@ def test_owner_share_exact_flag_and_tiny_inputs(gpu):
         words = R.synth_seq(3, n)
         want = R.count_query(words, 1, n, words.size, k, faithful=False)
         seq = gpu.upload(dnagpu.Dna.from_words(words, n))
-        for G in (2, 5):
+        for G in (2, 5, 8):
             for exact in (False, True):
                 stats, kmers, counts = _owned_union(gpu, seq, k, G, exact=exact)
                 assert stats == want.stats, (n, k, G, exact)
@@ -57,10 +57,12 @@ def test_owner_share_exact_flag_and_tiny_inputs(gpu):
         seq.free()
 
 
-def test_owner_share_of_heavily_repeated_input_falls_back_exactly(gpu):
+@pytest.mark.parametrize("G", [3, 4])
+def test_owner_share_of_heavily_repeated_input_falls_back_exactly(gpu, G):
     """poly-A + a short tandem repeat: one owner keeps millions of copies of a few k-mers -- the optimistic regions
-    and the per-CTA lists overflow and the exact key-list form takes over."""
-    n, k, G = 4_000_000, 21, 4
+    and the per-CTA lists overflow and the exact key-list form takes over (both ownership forms: 4 owners = linear,
+    3 = multiplicative)."""
+    n, k = 4_000_000, 21
     rng = np.random.default_rng(7)
     words = rng.integers(0, 2**64, size=n // 32, dtype=np.uint64)
     words[1000:60_000] = 0                                        # ~1.9 M x 'A'
