@@ -497,14 +497,47 @@ def run_b200(args):
         ctx.profile_reset()
 
         # ---- e2e leg: host buffers in, aggregates out, wall clock around synchronous calls ----
-        for _ in range(min(args.warmup, 2)):
-            count_e2e()
+        # Gather form: two shard rings; the H2D of step s + 1 (copy stream) runs under the count of step s.  Every step
+        # still uploads its own input and reads its own result inside the timed region.
+        ring2, copy_stream = None, None
+        if gather:
+            try:  # collective: raises on every rank or on none
+                ring2 = ShardRing(ctx, world, rank, n_bases)
+                copy_stream = torch.cuda.Stream(device=dev)
+            except RuntimeError as e:
+                if rank == 0:
+                    print(f"bench: no second shard ring ({e}); the e2e uploads are not overlapped", file=sys.stderr)
+
+        def e2e_steps(n_steps):
+            if ring2 is None:
+                r = None
+                for _ in range(n_steps):
+                    r = count_e2e()
+                return r
+            rings, r = [ring, ring2], None
+
+            def upload(rg):
+                copy_stream.wait_stream(stream)  # nothing of ours still reads that ring (the all-reduce fenced the peers)
+                with torch.cuda.stream(copy_stream):
+                    ctx.upload_to(rg.local, host[:n_words_local], rg.n_words[rank])
+            upload(rings[0])
+            for s_ in range(n_steps):
+                copy_stream.synchronize()          # this rank's shard of step s_ is in place ...
+                dist.barrier(device_ids=[local])   # ... and everybody's
+                if s_ + 1 < n_steps:
+                    upload(rings[(s_ + 1) % 2])
+                r = count_sharded_gather(ctx, rings[s_ % 2], k)
+            return r
+
+        e2e_steps(min(args.warmup, 2))
         barrier()
         t0 = time.perf_counter()
-        for _ in range(args.e2e_steps):
-            stats_e2e = count_e2e()
+        stats_e2e = e2e_steps(args.e2e_steps)
         barrier()
         e2e_s = time.perf_counter() - t0
+        e2e_overlapped = ring2 is not None
+        if ring2 is not None:
+            ring2.close()
 
         # ---- extraction GB/s (the second half of the metric), timed on its own ----
         extract = None
@@ -666,8 +699,9 @@ def run_b200(args):
                "routed": "base-range shards, dnagpu_partition + NCCL all-to-all + dnagpu_count_keys"}
         e2e_api = ("dnagpu_count_reads(ctx, host_words, n_reads, 150, 5, k, &where, &stats, NULL)" if reads and world == 1 else
                    "dnagpu_count_kmers(ctx, host_words, n_bases, k, NULL, &stats, NULL)" if world == 1 else
-                   "per rank: pinned host shard -> H2D into its peer-mapped ring buffer, barrier, "
+                   "per rank and step: pinned host shard -> H2D into its peer-mapped ring buffer, barrier, "
                    "dnagpu.distributed.count_sharded_gather (dnagpu_count with an owner restriction), all-reduce"
+                   + ("; two rings: the H2D of step s + 1 overlaps the count of step s" if e2e_overlapped else "")
                    if gather else
                    "per rank: dnagpu_seq_upload* of its shard + dnagpu.distributed.count_sharded_" + args.exchange)
         line = {
@@ -711,7 +745,7 @@ def main():
     ap.add_argument("--workload", default="c4", choices=sorted(WORKLOADS))
     ap.add_argument("--k", type=int, default=0, help="override k (c5: one k of the sweep instead of all 30)")
     ap.add_argument("--n-bases", type=int, default=0, help="override the workload size (debugging)")
-    ap.add_argument("--e2e-steps", type=int, default=3)
+    ap.add_argument("--e2e-steps", type=int, default=10)
     ap.add_argument("--load-factor", type=float, default=0.0)
     ap.add_argument("--cpu-sample", type=int, default=16_000_000)
     ap.add_argument("--cpu-large-sample", type=int, default=0,
