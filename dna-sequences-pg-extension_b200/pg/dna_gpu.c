@@ -65,17 +65,51 @@ typedef struct Qkmer {
 static dnagpu_ctx *backend_ctx = NULL;
 static int live_tables = 0; /* GPU tables held across calls (tests watch this) */
 
+/* Which GPUs the backend uses: "0" (default), or a list such as "0,1,2,3,4,5,6,7" -- then the context spans them
+ * (dnagpu_create_multi) and the GROUP BY entry points (kmer_stats, count_kmers without a WHERE clause) shard the
+ * sequence over all of them; everything else runs on the first.  Read once, when the backend first touches a dna
+ * value.  In an installed extension this is the string GUC dna_gpu.devices (DefineCustomStringVariable in
+ * _PG_init, PGC_BACKEND); the environment variable DNAGPU_DEVICES stands in for it here. */
+static int
+gpu_devices(int *devs, int max)
+{
+    const char *spec = getenv("DNAGPU_DEVICES");
+    int         n = 0;
+
+    while (spec && *spec && n < max)
+    {
+        char       *end;
+        long        v = strtol(spec, &end, 10);
+
+        if (end == spec || v < 0 || v > 1023)
+            ereport(ERROR, (errmsg("dnagpu: invalid device list \"%s\"", getenv("DNAGPU_DEVICES"))));
+        devs[n++] = (int) v;
+        spec = *end == ',' ? end + 1 : end;
+        if (*end != ',' && *end != '\0')
+            ereport(ERROR, (errmsg("dnagpu: invalid device list \"%s\"", getenv("DNAGPU_DEVICES"))));
+    }
+    return n;
+}
+
 static dnagpu_ctx *
 gpu(void)
 {
     if (backend_ctx == NULL)
     {
-        int rc = dnagpu_create(&backend_ctx, 0);
+        int         devs[16];
+        int         n = gpu_devices(devs, 16);
+        int         rc = n > 1 ? dnagpu_create_multi(&backend_ctx, devs, n) : dnagpu_create(&backend_ctx, n == 1 ? devs[0] : 0);
 
         if (rc != DNAGPU_OK)
             ereport(ERROR, (errmsg("dnagpu: %s", dnagpu_last_error(NULL))));
     }
     return backend_ctx;
+}
+
+int
+dna_gpu_device_count(void)
+{
+    return backend_ctx ? dnagpu_device_count(backend_ctx) : 0; /* GPUs of the backend's context, 0 before first use (tests) */
 }
 
 int

@@ -525,8 +525,10 @@ extern Datum generate_kmers_where(PG_FUNCTION_ARGS);
 extern Datum kmer_stats_agg_trans(PG_FUNCTION_ARGS);
 extern Datum kmer_stats_agg_final(PG_FUNCTION_ARGS);
 extern int dna_gpu_live_tables(void);
+extern int dna_gpu_device_count(void);
 
 int dnaref_live_tables(void) { return dna_gpu_live_tables(); }
+int dnaref_device_count(void) { return dna_gpu_device_count(); }
 int dnaref_live_contexts(void) { return shim_live_contexts(); }
 
 /* fn(dna, k) or fn(dna, k, prefix kmer | NULL, qkmer | NULL) */

@@ -80,6 +80,7 @@ class Module:
                                                             C.POINTER(u64)] + err)
             sig["dnaref_kmer_stats_agg"] = (C.c_int, [vp, vp, vp, u64, C.c_int, vp] + err)
             sig["dnaref_live_tables"] = (C.c_int, [])
+            sig["dnaref_device_count"] = (C.c_int, [])
             sig["dnaref_live_contexts"] = (C.c_int, [])
         for name, (res, args) in sig.items():
             fn = getattr(L, name)
@@ -223,6 +224,10 @@ class Module:
 
     def live_tables(self):
         return int(self.L.dnaref_live_tables())
+
+    def device_count(self):
+        """GPUs of the glue's backend context (0 before its first use; DNAGPU_DEVICES selects them)."""
+        return int(self.L.dnaref_device_count())
 
     def live_contexts(self):
         return int(self.L.dnaref_live_contexts())

@@ -172,3 +172,47 @@ def test_table_form_aggregate_equals_the_reference_plan(mods):
     rows = [ref.dna_in(_random_dna(rng, 100_000)) for _ in range(10)]
     total, distinct, unique = glue.kmer_stats_agg(rows, 10)
     assert total == 10 * (100_000 - 9) and 640_000 < distinct < 650_000 and 380_000 < unique < 390_000
+
+
+_ALL_GPUS_SCRIPT = r"""
+import os, sys
+import numpy as np
+sys.path.insert(0, sys.argv[1])
+from oracle import ref_cpu as R
+from oracle import ref_real
+glue = ref_real.glue()
+assert glue.device_count() == 0                      # the backend has not touched a dna value yet
+rng = np.random.default_rng(5)
+for n, k in ((3_000_000, 31), (3_000_000, 21), (500_000, 13), (70_000, 8), (40, 32)):
+    text = "".join(rng.choice(list("ATCG"), size=n)) if n != 40 else "G" * 40
+    words, nb = glue.dna_in(text)
+    want = R.count_query(words, 1, nb, words.size, k, faithful=False, threads=8)
+    assert glue.kmer_stats(words, nb, k) == (want.total, want.distinct, want.unique), (n, k)
+    kk, cc = glue.count_kmers(words, nb, k)
+    assert np.array_equal(kk, want.kmers) and np.array_equal(cc.astype(np.uint64), want.counts), (n, k)
+    # a WHERE clause and the SRF run on the first GPU of the same context
+    assert np.array_equal(glue.generate_kmers(words, nb, k), R.generate_kmers(words, nb, k))
+    got = glue.generate_kmers(words, nb, k, prefix=(2, 1), pattern="N" * k)       # WHERE kmer ^@ 'C' AND 'NN..N' @> kmer
+    assert np.array_equal(got, R.filter_kmers(words, nb, k, prefix=(2, 1), pattern="N" * k))
+assert glue.device_count() == int(sys.argv[2]), glue.device_count()
+assert glue.live_tables() == 0
+print("glue on", glue.device_count(), "GPUs ok")
+"""
+
+
+def test_glue_backend_context_over_all_gpus(gpu):
+    """DNAGPU_DEVICES (the stand-in for the GUC dna_gpu.devices) = every GPU of the box: the backend's context is a
+    multi-GPU one (dnagpu_create_multi) and kmer_stats / count_kmers shard the sequence over the GPUs -- from C, through
+    the fmgr surface, no Python orchestration.  Own process: a backend creates its context once."""
+    import os
+    import subprocess
+    import sys
+    import torch
+    n = torch.cuda.device_count()
+    if n < 2:
+        pytest.skip("one GPU")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    env = dict(os.environ, DNAGPU_DEVICES=",".join(str(i) for i in range(n)))
+    p = subprocess.run([sys.executable, "-c", _ALL_GPUS_SCRIPT, root, str(n)], env=env, capture_output=True, text=True, timeout=600)
+    assert p.returncode == 0, p.stdout + p.stderr
+    assert f"glue on {n} GPUs ok" in p.stdout
